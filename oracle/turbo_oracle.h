@@ -1,0 +1,104 @@
+/*
+ * turbo_oracle.h -- CPU oracle for the turbo-decode hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C restatement of the reference's
+ * algorithm (xinxu27/turbo_decoder_cuda, ITTC/log_map.cpp) used as the parity
+ * checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.
+ * Nothing in the product path (turbo_decoder_cuda_b200/, include/) may link or
+ * call it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_ref.py checks this restatement
+ * against the reference's own code compiled in place (oracle/_ref, built by
+ * oracle/Makefile from /root/reference/ITTC/{log_map,modanddem}.cpp) and against
+ * the golden vectors under tests/golden/ generated from that build
+ * (tests/golden/make_golden.py).
+ */
+#ifndef TURBO_ORACLE_H
+#define TURBO_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { TDO_ALGO_LOGMAP_LUT = 1, TDO_ALGO_MAXLOG = 2 };
+
+/* (13,15)_8 trellis tables, same layout as TURBO_TRELLIS (ITTC/log_map.h:61-68):
+ * nextout[8*4] = {in0,par0,in1,par1} as +-1, nextstat[8*2], lastout[8*4], laststat[8*2]. */
+void tdo_gen_trellis(int *nextout, int *nextstat, int *lastout, int *laststat);
+
+/* QPP interleaver pi(i) = (f1*i + f2*i^2) mod K   (ITTC/log_map.cpp:616-624). */
+void tdo_qpp_index(int K, int f1, int f2, int *pi);
+
+/* LTE (K,f1,f2) table lookup (TS 36.212 Table 5.1.3-3).
+ * Returns 0 on success, -1 if K is not an LTE block size. */
+int tdo_lte_qpp_params(int K, int *f1, int *f2);
+int tdo_lte_num_sizes(void);
+int tdo_lte_size_at(int idx);
+
+/* PCCC encoder, reference mux order: out[3i]=sys, [3i+1]=par1, [3i+2]=par2, then
+ * (x,z)x3 tail of RSC1 and (x',z')x3 tail of RSC2  (ITTC/log_map.cpp:451-583). */
+void tdo_turbo_encode(const int *bits, int K, const int *pi, int *coded /*3K+12*/);
+
+/* BPSK (+1 for bit 1) over AWGN, LLR = 2 r / sigma^2  (ITTC/main.cpp:174,197-202,
+ * ITTC/modanddem.cpp:189-224).  Noise is Box-Muller on a counter-based generator
+ * (seeded, reproducible) -- NOT the reference's rand()/CLT noise, which is not
+ * reproducible (ITTC/main.cpp:170). */
+void tdo_channel_llr(const int *coded, int n, double sigma, unsigned long long seed,
+                     unsigned long long stream, double *llr);
+double tdo_sigma_from_ebn0(double ebn0_db, int K);
+
+/* max*(x,y) with the reference's 16-entry LUT  (ITTC/log_map.cpp:14-18,779-801). */
+double tdo_max_star_lut(double x, double y);
+
+/* One BCJR pass  (ITTC/log_map.cpp:898-1047).  recs = 2*T interleaved (xs,xp)
+ * half-LLRs, La[T], LLR[T] out.  algo selects LUT max* or plain max.
+ * tempmax_floor: the reference compares against an uninitialised malloc'd
+ * tempmax[] (log_map.cpp:925,989); NAN here means "max over states only",
+ * a finite value v means tempmax = max(v, max_j alpha).  */
+void tdo_siso(const double *recs, const double *La, int terminated, double *LLR,
+              int T, int algo, double tempmax_floor);
+
+/* Iterative PCCC decode  (ITTC/log_map.cpp:1146-1280).  Input is NOT mutated
+ * (the reference halves it in place, :1202-1205).
+ *   llr_in[3K+12]                      channel LLRs, reference mux order
+ *   bits_out[n_iter*K]                 hard decisions after every iteration (may be NULL)
+ *   llr1_out[T], llr2_out[T]           a-posteriori LLRs of SISO1 (natural order) and
+ *                                      SISO2 (interleaved order) of the LAST iteration (may be NULL)
+ *   le_out[T]                          extrinsic of SISO2 of the last iteration (may be NULL)  */
+void tdo_turbo_decode(const double *llr_in, int K, const int *pi, int n_iter, int algo,
+                      int *bits_out, double *llr1_out, double *llr2_out, double *le_out);
+
+/* Same, one codeblock per thread over n_threads host threads.  llr_in is
+ * [n_cb][3K+12]; bits_last[n_cb][K] gets the last iteration's decisions.
+ * Returns wall seconds spent inside the decode calls (steady clock). */
+double tdo_turbo_decode_batch(const double *llr_in, int n_cb, int K, const int *pi,
+                              int n_iter, int algo, int *bits_last, int n_threads);
+
+/* ------------------------------------------------------------------------
+ * Fixed-point windowed max-log-MAP model.  Bit-exact integer mirror of the
+ * s16x2 CUDA kernel (turbo_decoder_cuda_b200/csrc/tdb200_maxlog.cu): same
+ * quantisation, same sub-block schedule, same boundary initialisation, same
+ * extrinsic scaling -- plain int32 arithmetic with range checks.
+ * ---------------------------------------------------------------------- */
+typedef struct tdo_fx_params {
+    int K;
+    int n_iter;
+    int sub_len;      /* L: trellis steps per sub-block, multiple of 8, divides K */
+    int warmup;       /* guard steps re-run from the neighbouring sub-block (0 = NII only) */
+    int frac_bits;    /* LLR quantisation: q = rint(llr * 2^frac_bits) */
+    int llr_clip;     /* |q| clamp for channel values */
+    int ext_clip;     /* |Le| clamp */
+    int ext_scale_q2; /* extrinsic scale in quarters: 3 = 0.75, 4 = 1.0 */
+    int early_term;   /* 1: stop when hard decisions repeat between two iterations */
+} tdo_fx_params;
+
+/* Returns the number of iterations run.  bits_out[K] final decisions; le_out
+ * (may be NULL) gets the last SISO2 extrinsic in natural order (int).  overflow
+ * (may be NULL) is set to 1 if any state metric left the int16 range. */
+int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
+                  int *bits_out, int *le_out, int *overflow);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,240 @@
+"""ctypes bindings for the parity checkers under oracle/ (TEST INFRASTRUCTURE ONLY).
+
+`Oracle`  -> oracle/_build/libtdoracle.so  (C restatement, oracle/turbo_oracle.c)
+`RefLib`  -> oracle/_ref/libittc_ref.so    (the reference's own ITTC sources compiled in place,
+                                           oracle/ref_harness.cpp); optional.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libtdoracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libittc_ref.so")
+
+ALGO_LOGMAP_LUT = 1
+ALGO_MAXLOG = 2
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build_oracle(force=False):
+    """Compile oracle/'s C restatement (and oracle/_ref when /root/reference is present)."""
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("turbo_oracle.c", "turbo_oracle_fx.c", "turbo_oracle.h")]
+    stale = force or not os.path.exists(ORACLE_SO) or any(
+        os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"], stdout=subprocess.DEVNULL)
+    ref_src = "/root/reference/ITTC/log_map.cpp"
+    harness = os.path.join(ORACLE_DIR, "ref_harness.cpp")
+    if os.path.exists(ref_src) and (force or not os.path.exists(REF_SO)
+                                    or os.path.getmtime(harness) > os.path.getmtime(REF_SO)):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "ref"], stdout=subprocess.DEVNULL)
+
+
+class FxParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "K", "n_iter", "sub_len", "warmup", "frac_bits", "llr_clip", "ext_clip",
+        "ext_scale_q2", "early_term")]
+
+
+def _opt(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    def __init__(self):
+        build_oracle()
+        L = self.lib = C.CDLL(ORACLE_SO)
+        L.tdo_gen_trellis.argtypes = [_ip, _ip, _ip, _ip]
+        L.tdo_qpp_index.argtypes = [C.c_int, C.c_int, C.c_int, _ip]
+        L.tdo_lte_qpp_params.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.tdo_lte_size_at.argtypes = [C.c_int]
+        L.tdo_turbo_encode.argtypes = [_ip, C.c_int, _ip, _ip]
+        L.tdo_channel_llr.argtypes = [_ip, C.c_int, C.c_double, C.c_ulonglong, C.c_ulonglong, _dp]
+        L.tdo_sigma_from_ebn0.argtypes = [C.c_double, C.c_int]
+        L.tdo_sigma_from_ebn0.restype = C.c_double
+        L.tdo_max_star_lut.argtypes = [C.c_double, C.c_double]
+        L.tdo_max_star_lut.restype = C.c_double
+        L.tdo_siso.argtypes = [_dp, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_double]
+        L.tdo_turbo_decode.argtypes = [_dp, C.c_int, _ip, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tdo_turbo_decode_batch.argtypes = [_dp, C.c_int, C.c_int, _ip, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_int]
+        L.tdo_turbo_decode_batch.restype = C.c_double
+        L.tdo_fx_decode.argtypes = [_fp, _ip, C.POINTER(FxParams), _ip, C.c_void_p, C.c_void_p]
+        L.tdo_fx_decode.restype = C.c_int
+
+    # ---- constants
+    def trellis(self):
+        no, ns, lo, ls = (np.zeros(n, np.int32) for n in (32, 16, 32, 16))
+        self.lib.tdo_gen_trellis(no, ns, lo, ls)
+        return no.reshape(8, 4), ns.reshape(8, 2), lo.reshape(8, 4), ls.reshape(8, 2)
+
+    def lte_sizes(self):
+        return [self.lib.tdo_lte_size_at(i) for i in range(self.lib.tdo_lte_num_sizes())]
+
+    def lte_params(self, K):
+        f1, f2 = C.c_int(), C.c_int()
+        if self.lib.tdo_lte_qpp_params(K, C.byref(f1), C.byref(f2)) != 0:
+            raise ValueError(f"K={K} is not an LTE turbo block size")
+        return f1.value, f2.value
+
+    def qpp(self, K, f1=None, f2=None):
+        if f1 is None:
+            f1, f2 = self.lte_params(K)
+        pi = np.zeros(K, np.int32)
+        self.lib.tdo_qpp_index(K, f1, f2, pi)
+        return pi
+
+    # ---- test-vector generation
+    def encode(self, bits, pi):
+        K = len(bits)
+        coded = np.zeros(3 * K + 12, np.int32)
+        self.lib.tdo_turbo_encode(np.ascontiguousarray(bits, np.int32), K, pi, coded)
+        return coded
+
+    def sigma(self, ebn0_db, K):
+        return self.lib.tdo_sigma_from_ebn0(ebn0_db, K)
+
+    def channel(self, coded, sigma, seed, stream=0):
+        llr = np.zeros(len(coded), np.float64)
+        self.lib.tdo_channel_llr(np.ascontiguousarray(coded, np.int32), len(coded), sigma, seed, stream, llr)
+        return llr
+
+    def make_batch(self, K, n_cb, ebn0_db, seed, pi=None):
+        """(bits[n_cb,K] int32, llr[n_cb,3K+12] float64) -- seeded, reproducible."""
+        pi = self.qpp(K) if pi is None else pi
+        rng = np.random.default_rng(seed)
+        bits = rng.integers(0, 2, size=(n_cb, K), dtype=np.int32)
+        sig = self.sigma(ebn0_db, K)
+        llr = np.zeros((n_cb, 3 * K + 12), np.float64)
+        for c in range(n_cb):
+            llr[c] = self.channel(self.encode(bits[c], pi), sig, seed, c)
+        return bits, llr
+
+    # ---- decode
+    def max_star(self, x, y):
+        return self.lib.tdo_max_star_lut(x, y)
+
+    def siso(self, recs, La, algo=ALGO_LOGMAP_LUT, terminated=1, tempmax_floor=math.nan):
+        T = len(La)
+        out = np.zeros(T, np.float64)
+        self.lib.tdo_siso(np.ascontiguousarray(recs, np.float64), np.ascontiguousarray(La, np.float64),
+                          terminated, out, T, algo, tempmax_floor)
+        return out
+
+    def decode(self, llr, pi, n_iter, algo=ALGO_LOGMAP_LUT, want_llr=False):
+        K = len(pi)
+        T = K + 3
+        bits = np.zeros((n_iter, K), np.int32)
+        l1 = np.zeros(T) if want_llr else None
+        l2 = np.zeros(T) if want_llr else None
+        le = np.zeros(T) if want_llr else None
+        self.lib.tdo_turbo_decode(np.ascontiguousarray(llr, np.float64), K, pi, n_iter, algo,
+                                  _opt(bits), _opt(l1), _opt(l2), _opt(le))
+        return (bits, l1, l2, le) if want_llr else bits
+
+    def decode_batch(self, llr, pi, n_iter, algo=ALGO_LOGMAP_LUT, n_threads=1):
+        llr = np.ascontiguousarray(llr, np.float64)
+        n_cb, K = llr.shape[0], len(pi)
+        bits = np.zeros((n_cb, K), np.int32)
+        secs = self.lib.tdo_turbo_decode_batch(llr, n_cb, K, pi, n_iter, algo, _opt(bits), n_threads)
+        return bits, secs
+
+    def fx_decode(self, llr_f32, pi, params, want_le=False):
+        K = len(pi)
+        bits = np.zeros(K, np.int32)
+        le = np.zeros(K, np.int32) if want_le else None
+        ovf = C.c_int(0)
+        it = self.lib.tdo_fx_decode(np.ascontiguousarray(llr_f32, np.float32), pi, C.byref(params),
+                                    bits, _opt(le), C.cast(C.byref(ovf), C.c_void_p))
+        return bits, le, it, ovf.value
+
+
+class RefLib:
+    """The reference's own code (oracle/_ref).  available() is False where it was never built."""
+
+    @staticmethod
+    def available():
+        build_oracle()
+        return os.path.exists(REF_SO)
+
+    def __init__(self, K, f1, f2):
+        build_oracle()
+        L = self.lib = C.CDLL(REF_SO)
+        self.K = K
+        L.ref_init.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.ref_get_qpp.argtypes = [_ip]
+        L.ref_get_trellis.argtypes = [_ip, _ip, _ip, _ip]
+        L.ref_encode.argtypes = [_ip, _ip]
+        L.ref_max_star.argtypes = [C.c_double, C.c_double]
+        L.ref_max_star.restype = C.c_double
+        L.ref_channel.argtypes = [_ip, C.c_double, C.c_uint, _dp]
+        L.ref_turbo_decoding.argtypes = [_dp, _ip]
+        L.ref_siso.argtypes = [_dp, _dp, C.c_int, _dp, C.c_int]
+        L.ref_decode_iters.argtypes = [_dp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_decode_batch.argtypes = [_dp, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.ref_decode_batch.restype = C.c_double
+        L.ref_init(K, f1, f2)
+
+    def qpp(self):
+        pi = np.zeros(self.K, np.int32)
+        self.lib.ref_get_qpp(pi)
+        return pi
+
+    def trellis(self):
+        no, ns, lo, ls = (np.zeros(n, np.int32) for n in (32, 16, 32, 16))
+        self.lib.ref_get_trellis(no, ns, lo, ls)
+        return no.reshape(8, 4), ns.reshape(8, 2), lo.reshape(8, 4), ls.reshape(8, 2)
+
+    def encode(self, bits):
+        coded = np.zeros(3 * self.K + 12, np.int32)
+        self.lib.ref_encode(np.ascontiguousarray(bits, np.int32), coded)
+        return coded
+
+    def max_star(self, x, y):
+        return self.lib.ref_max_star(x, y)
+
+    def channel(self, coded, sigma, seed):
+        llr = np.zeros(3 * self.K + 12, np.float64)
+        self.lib.ref_channel(np.ascontiguousarray(coded, np.int32), sigma, seed, llr)
+        return llr
+
+    def turbo_decoding(self, llr):
+        """The reference's TurboDecoding(): 15 iterations; returns bits[15,K]."""
+        buf = np.array(llr, np.float64, copy=True)
+        out = np.zeros(15 * self.K, np.int32)
+        self.lib.ref_turbo_decoding(buf, out)
+        return out.reshape(15, self.K)
+
+    def siso(self, recs, La, terminated=1):
+        T = len(La)
+        out = np.zeros(T, np.float64)
+        self.lib.ref_siso(np.array(recs, np.float64), np.array(La, np.float64), terminated, out, T)
+        return out
+
+    def decode(self, llr, n_iter, want_llr=False):
+        K, T = self.K, self.K + 3
+        bits = np.zeros((n_iter, K), np.int32)
+        l1 = np.zeros(T) if want_llr else None
+        l2 = np.zeros(T) if want_llr else None
+        le = np.zeros(T) if want_llr else None
+        self.lib.ref_decode_iters(np.ascontiguousarray(llr, np.float64), n_iter,
+                                  _opt(bits), _opt(l1), _opt(l2), _opt(le))
+        return (bits, l1, l2, le) if want_llr else bits
+
+    def decode_batch(self, llr, n_iter, n_threads=1):
+        llr = np.ascontiguousarray(llr, np.float64)
+        n_cb = llr.shape[0]
+        bits = np.zeros((n_cb, self.K), np.int32)
+        secs = self.lib.ref_decode_batch(llr, n_cb, n_iter, _opt(bits), n_threads)
+        return bits, secs
