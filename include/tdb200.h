@@ -1,0 +1,155 @@
+/*
+ * tdb200.h -- C ABI of the B200-native batched LTE turbo decoder.
+ *
+ * This is the drop-in boundary for ONE path of xinxu27/turbo_decoder_cuda: the
+ * iterative PCCC decode
+ *     void TurboDecoding(double *flow_for_decode, int *flow_decoded, int flow_length)
+ *         ITTC/main.h:20, ITTC/log_map.cpp:1146-1280, called from ITTC/main.cpp:221
+ * and its component decoder
+ *     void Log_MAP_decoder(double *recs, double *La, int terminated, double *LLR, int len_total)
+ *         ITTC/log_map.cpp:898-1047
+ * The reference has no FFI layer: its boundary is link-level C++ free functions plus
+ * caller-defined globals (ITTC/main.h:6-11).  The entry points below are what a binding for
+ * that path would bind; turbo_decoder_cuda_b200/compat/ittc_compat.cpp re-exports the
+ * reference's own signatures on top of them.
+ *
+ * Plain pointers and sizes only; no CUDA or torch types.  `stream` is a cudaStream_t passed as
+ * void* (NULL = the legacy default stream).  All functions return a tdb200_status; the text of
+ * the last failure on the calling thread is available from tdb200_last_error().
+ * There is NO CPU fallback: without a CUDA device every entry point fails with
+ * TDB200_ERR_NO_DEVICE.
+ */
+#ifndef TDB200_H
+#define TDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDB200_VERSION 1
+
+typedef enum tdb200_status {
+    TDB200_OK = 0,
+    TDB200_ERR_INVALID_ARG = 1,
+    TDB200_ERR_UNSUPPORTED = 2,
+    TDB200_ERR_NO_DEVICE = 3,
+    TDB200_ERR_CUDA = 4,
+    TDB200_ERR_ALLOC = 5
+} tdb200_status;
+
+/* Component-decoder arithmetic. */
+typedef enum tdb200_algo {
+    /* fp64 Log-MAP with the reference's 16-entry max* LUT, unsegmented recursion, the
+     * reference's operation order (replaces Log_MAP_decoder, log_map.cpp:898-1047, bit for
+     * bit up to its uninitialised tempmax[]).  The LLR-parity mode. */
+    TDB200_ALGO_LOGMAP_F64 = 0,
+    /* max-log-MAP in packed 16-bit fixed point (two codeblocks per 32-bit lane), sub-block
+     * parallel with boundary-state initialisation.  The throughput mode. */
+    TDB200_ALGO_MAXLOG_S16 = 1,
+    /* fp32 Log-MAP (max* with the exact Jacobian correction), sub-block parallel. */
+    TDB200_ALGO_LOGMAP_F32 = 2,
+    /* fp32 max-log-MAP, sub-block parallel. */
+    TDB200_ALGO_MAXLOG_F32 = 3
+} tdb200_algo;
+
+/* Element type of the channel-LLR input. */
+typedef enum tdb200_llr_type {
+    TDB200_LLR_F64 = 0, /* the reference's type (double *flow_for_decode) */
+    TDB200_LLR_F32 = 1,
+    TDB200_LLR_S8 = 2   /* already quantised: q = LLR * 2^frac_bits, saturated to int8 */
+} tdb200_llr_type;
+
+/* Where caller buffers live. */
+typedef enum tdb200_mem {
+    TDB200_MEM_HOST = 0,  /* pageable or pinned host memory; copies are issued on `stream` */
+    TDB200_MEM_DEVICE = 1 /* device memory of the decoder's GPU */
+} tdb200_mem;
+
+typedef struct tdb200_config {
+    int K;          /* information bits per codeblock (source_length, ITTC/main.h:6) */
+    int f1, f2;     /* QPP parameters (ITTC/main.h:9); 0,0 = look K up in TS 36.212 Table 5.1.3-3 */
+    int n_iter;     /* full iterations (N_ITERATION, ITTC/log_map.h:30) */
+    int algo;       /* tdb200_algo */
+    int sub_block;  /* trellis steps per sub-block / window (multiple of 8 dividing K); 0 = auto.
+                       Ignored by TDB200_ALGO_LOGMAP_F64 (always unsegmented). */
+    int warmup;     /* guard steps recomputed from the neighbouring sub-block before each
+                       sub-block boundary; 0 = next-iteration initialisation only */
+    int early_term; /* 1 = stop a codeblock when its hard decisions repeat (min 2 iterations) */
+    int ext_scale_q2; /* extrinsic scaling in quarters for the max-log modes: 3 = 0.75, 4 = 1.0;
+                         0 = default (3 for max-log, 4 for Log-MAP) */
+    int frac_bits;  /* fixed-point fractional bits of TDB200_ALGO_MAXLOG_S16 and of
+                       TDB200_LLR_S8 input; 0 = default (3) */
+    int device;     /* CUDA device ordinal */
+    int max_batch;  /* codeblocks the workspace is sized for per launch; larger batches are
+                       processed in chunks.  0 = default for the algo */
+} tdb200_config;
+
+/* Optional outputs; any pointer may be NULL.  Buffers live in the `mem` space given to the
+ * decode call.  T = K + 3. */
+typedef struct tdb200_outputs {
+    uint8_t *bits;        /* [n_cb][K]  hard decisions after the last iteration run, natural
+                             order, one byte per bit (LLR < 0 -> 0 else 1, log_map.cpp:862-879) */
+    int32_t *bits_iters;  /* [n_cb][n_iter][K] decisions after EVERY iteration, as ints: one
+                             codeblock's slab is exactly TurboDecoding's flow_decoded
+                             (log_map.cpp:1264).  Rows past an early stop repeat the last one. */
+    int32_t *iters_used;  /* [n_cb] iterations actually run */
+    /* a-posteriori / extrinsic LLRs of the LAST iteration, in the algo's native float type
+     * (double for LOGMAP_F64, float otherwise; MAXLOG_S16 writes float = q / 2^frac_bits):     */
+    void *llr_siso1;      /* [n_cb][T] SISO-1 output, natural order   (LLR_all_turbo, :1230) */
+    void *llr_siso2;      /* [n_cb][T] SISO-2 output, interleaved order (:1251)              */
+    void *ext_siso2;      /* [n_cb][T] SISO-2 extrinsic, interleaved order (Le_turbo, :1258) */
+} tdb200_outputs;
+
+typedef struct tdb200_decoder tdb200_decoder;
+
+/* Fill cfg with the defaults for block size K (8 iterations, TDB200_ALGO_MAXLOG_S16). */
+int tdb200_default_config(tdb200_config *cfg, int K);
+
+/* TS 36.212 Table 5.1.3-3.  Returns TDB200_ERR_INVALID_ARG if K is not an LTE block size. */
+int tdb200_lte_qpp_params(int K, int *f1, int *f2);
+
+/* Replaces TurboCodingInit() / TurboCodingRelease() (log_map.cpp:349-434,1330-1345) for the
+ * decode path: builds the QPP tables, uploads constants, allocates the device workspace. */
+int tdb200_create(const tdb200_config *cfg, tdb200_decoder **out);
+void tdb200_destroy(tdb200_decoder *dec);
+
+/* Replaces TurboDecoding() for a batch.  llr is [n_cb][3K+12] channel LLRs (positive = bit 1)
+ * in the reference's multiplex order: [3i]=systematic, [3i+1]=parity 1, [3i+2]=parity 2 for
+ * i<K, then (x,z)x3 tail of encoder 1 and (x',z')x3 tail of encoder 2
+ * (log_map.cpp:566-578,1103-1123).  The input is never modified (the reference halves it in
+ * place, :1202-1205; the compat wrapper reproduces that side effect).
+ * Work is enqueued on `stream`; with TDB200_MEM_DEVICE buffers the call is asynchronous, with
+ * TDB200_MEM_HOST buffers it returns after the results have landed in the caller's memory. */
+int tdb200_decode_batch(tdb200_decoder *dec, const void *llr, int llr_type, int mem, int n_cb,
+                        const tdb200_outputs *out, void *stream);
+
+/* Replaces Log_MAP_decoder() for a batch (TDB200_ALGO_LOGMAP_F64 decoders only): one BCJR pass.
+ * recs [n_cb][2T] interleaved (xs,xp) half-LLRs, La [n_cb][T], LLR out [n_cb][T], doubles. */
+int tdb200_siso_batch(tdb200_decoder *dec, const double *recs, const double *La, int terminated,
+                      double *LLR, int mem, int n_cb, void *stream);
+
+/* Introspection (what the plan resolved to). */
+typedef struct tdb200_plan_info {
+    int K, f1, f2, n_iter, algo;
+    int sub_block;       /* L */
+    int n_sub_blocks;    /* P = K / L */
+    int warmup;
+    int cb_per_cta;      /* codeblocks one CTA decodes concurrently */
+    int threads_per_cta;
+    int smem_bytes;      /* dynamic shared memory per CTA */
+    int max_batch;
+    int sm_count;
+    int kernel_launches_last_call; /* kernels launched by the most recent decode call */
+} tdb200_plan_info;
+int tdb200_get_plan(const tdb200_decoder *dec, tdb200_plan_info *info);
+
+const char *tdb200_last_error(void);
+const char *tdb200_status_string(int status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDB200_H */

@@ -1,0 +1,99 @@
+"""GPU parity of the fp64 reference-order mode (TDB200_ALGO_LOGMAP_F64) against the oracle.
+
+north_star bar: a-posteriori / extrinsic LLRs within 1e-3 absolute of the reference CPU Log-MAP
+on identical channel LLRs, identical hard decisions.  This mode performs the reference's fp64
+operations in the reference's order, so the tolerance used here is far tighter (1e-6).
+All calls go through the C ABI (ctypes).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LLR_TOL = 1e-6  # north_star allows 1e-3
+
+
+def _torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.mark.parametrize("K,ebn0,n_cb,n_iter", [
+    (6144, 1.0, 3, 8),   # BASELINE configs[0]: the reference's own CPU-runnable case
+    (6144, 0.4, 2, 8),   # waterfall: not converged early, LLRs small -> most sensitive to LUT flips
+    (6144, 0.0, 2, 4),
+    (40, 2.0, 9, 6),     # smallest LTE block, ragged batch (not a multiple of 4)
+    (512, 1.5, 5, 5),
+    (1008, 1.0, 4, 3),
+])
+def test_decode_matches_oracle(oracle, K, ebn0, n_cb, n_iter):
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    pi = oracle.qpp(K)
+    bits, llr = oracle.make_batch(K, n_cb, ebn0, seed=1234 + K)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="logmap_f64", max_batch=8)
+    want = ("bits", "bits_iters", "iters_used", "llr_siso1", "llr_siso2", "ext_siso2")
+    # device path (zero-copy torch tensors) and host path (numpy) must agree with each other
+    out_d = dec.decode(torch.from_numpy(llr).cuda(), want=want)
+    torch.cuda.synchronize()
+    out_h = dec.decode(llr, want=want)
+    for c in range(n_cb):
+        ob, o1, o2, ole = oracle.decode(llr[c], pi, n_iter, want_llr=True)
+        for out in (out_h, {k: v.cpu().numpy() for k, v in out_d.items()}):
+            assert np.array_equal(out["bits_iters"][c], ob), "hard decisions differ from the oracle"
+            assert np.array_equal(out["bits"][c], ob[-1].astype(np.uint8))
+            assert out["iters_used"][c] == n_iter
+            assert np.abs(out["llr_siso1"][c] - o1).max() < LLR_TOL
+            assert np.abs(out["llr_siso2"][c] - o2).max() < LLR_TOL
+            assert np.abs(out["ext_siso2"][c] - ole).max() < LLR_TOL
+    assert dec.plan()["kernel_launches_last_call"] >= 1
+
+
+def test_llr_input_types(oracle):
+    """float32 input is widened exactly; the decode of float32-rounded LLRs matches the oracle on them."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_iter = 256, 4
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, 4, 1.0, seed=5)
+    llr32 = llr.astype(np.float32)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="logmap_f64")
+    out = dec.decode(llr32, want=("bits_iters", "llr_siso2"))
+    for c in range(4):
+        ob, _, o2, _ = oracle.decode(llr32[c].astype(np.float64), pi, n_iter, want_llr=True)
+        assert np.array_equal(out["bits_iters"][c], ob)
+        assert np.abs(out["llr_siso2"][c] - o2).max() < LLR_TOL
+
+
+def test_siso_matches_oracle(oracle):
+    """tdb200_siso_batch == Log_MAP_decoder on arbitrary (recs, La), terminated and not."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K = 1024
+    T = K + 3
+    rng = np.random.default_rng(3)
+    n_cb = 5
+    recs = rng.normal(0, 2.0, size=(n_cb, 2 * T))
+    La = rng.normal(0, 3.0, size=(n_cb, T))
+    dec = TurboDecoder(K, n_iter=1, algo="logmap_f64")
+    for term in (1, 0):
+        got = dec.siso(recs, La, terminated=term)
+        for c in range(n_cb):
+            ref = oracle.siso(recs[c], La[c], terminated=term)
+            assert np.abs(got[c] - ref).max() < LLR_TOL
+
+
+def test_empty_batch_and_bad_args():
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TdbError, TurboDecoder
+    dec = TurboDecoder(40, n_iter=2, algo="logmap_f64")
+    out = dec.decode(np.zeros((0, 132)), want=("bits",))
+    assert out["bits"].shape == (0, 40)
+    with pytest.raises(TdbError):
+        TurboDecoder(41, algo="logmap_f64")          # not an LTE size and no f1/f2 given
+    with pytest.raises(TdbError):
+        TurboDecoder(40, f1=4, f2=10, algo="logmap_f64")  # not a permutation
+    with pytest.raises(TdbError):
+        TurboDecoder(40, n_iter=0, algo="logmap_f64")

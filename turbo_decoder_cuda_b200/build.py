@@ -1,0 +1,93 @@
+"""In-tree build of the CUDA library (sm_100a only) with plain nvcc.
+
+    python -m turbo_decoder_cuda_b200.build [--force]
+
+Outputs (git-ignored, shipped to the GPU box by gpurun):
+    turbo_decoder_cuda_b200/lib/libtdb200.so         C ABI (include/tdb200.h) + kernels
+    turbo_decoder_cuda_b200/lib/libtdb200_compat.so  reference-signature C++ wrappers (compat/)
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+COMPAT = os.path.join(PKG, "compat")
+LIB = os.path.join(PKG, "lib")
+OBJ = os.path.join(LIB, "obj")
+INCLUDE = os.path.join(ROOT, "include")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
+
+# (source, extra flags)
+KERNEL_TUS = [
+    ("tdb200_api.cu", []),
+    ("tdb200_ref64.cu", ["-fmad=false"]),
+    ("tdb200_fast.cu", ["-Xptxas", "-v"]),
+]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: the CUDA library cannot be built")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _headers():
+    hs = [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
+    hs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    return hs
+
+
+def build(force=False, verbose=False):
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = _headers()
+    objs = []
+    log = []
+    for src, extra in KERNEL_TUS:
+        s = os.path.join(CSRC, src)
+        if not os.path.exists(s):
+            continue
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + hdrs):
+            cmd = [nvcc] + ARCH + COMMON + extra + ["-c", s, "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            log.append(r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    so = os.path.join(LIB, "libtdb200.so")
+    if force or _stale(so, objs):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", so] + objs + ["-cudart", "static"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    compat_src = os.path.join(COMPAT, "ittc_compat.cpp")
+    compat_so = os.path.join(LIB, "libtdb200_compat.so")
+    if os.path.exists(compat_src) and (force or _stale(compat_so, [compat_src, so] + hdrs)):
+        cmd = ["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-I", INCLUDE, compat_src, "-o", compat_so,
+               "-L", LIB, "-ltdb200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("compat build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    if verbose:
+        sys.stderr.write("".join(log))
+    with open(os.path.join(LIB, "ptxas.log"), "a") as f:
+        f.write("".join(log))
+    return so
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

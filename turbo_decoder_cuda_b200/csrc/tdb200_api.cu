@@ -1,0 +1,404 @@
+// tdb200_api.cu -- the C ABI declared in include/tdb200.h: plan construction (QPP tables,
+// sub-block geometry), device workspace, batch chunking, host<->device staging on streams.
+// No CPU fallback lives here: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "tdb200_internal.h"
+
+namespace tdb200 {
+
+// ---------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+
+static int fail(int status, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+#define TDB_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(e_ == cudaErrorMemoryAllocation ? TDB200_ERR_ALLOC : TDB200_ERR_CUDA,   \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------- constants
+// RSC with feedback 13_8 = 1011 and feed-forward 15_8 = 1101 (ITTC/log_map.h:34-36); state =
+// 4*s0 + 2*s1 + s2 with s0 the newest register, as bin2int does (log_map.cpp:213-231).
+static void rsc_step(int state, int d, int *next, int *parity)
+{
+    const int s0 = (state >> 2) & 1, s1 = (state >> 1) & 1, s2 = state & 1;
+    const int a = (d + s1 + s2) & 1;
+    *parity = (a + s0 + s2) & 1;
+    *next = (a << 2) | (s0 << 1) | s1;
+}
+
+const Trellis &host_trellis()
+{
+    static Trellis t = [] {
+        Trellis r;
+        for (int s = 0; s < kStates; s++) {
+            int n, p;
+            rsc_step(s, 0, &n, &p);
+            r.ns0[s] = n; r.par0[s] = p; r.ls0[n] = s;
+            rsc_step(s, 1, &n, &p);
+            r.ns1[s] = n; r.ls1[n] = s;
+        }
+        return r;
+    }();
+    return t;
+}
+
+static bool trellis_literals_ok()
+{
+    const Trellis &t = host_trellis();
+    for (int s = 0; s < kStates; s++) {
+        if (tb(kNs0, s) != t.ns0[s] || tb(kNs1, s) != t.ns1[s] || tb(kLs0, s) != t.ls0[s] ||
+            tb(kLs1, s) != t.ls1[s] || (int)((kPar0 >> s) & 1) != t.par0[s])
+            return false;
+        int n, p;
+        rsc_step(s, 1, &n, &p);
+        if (p != 1 - t.par0[s]) return false;  // o1 = -o0
+    }
+    return true;
+}
+
+// TS 36.212 Table 5.1.3-3 (K, f1, f2).  Not present in the reference, which hard-codes
+// 6144 -> (263,480) (ITTC/main.cpp:30,36-37) and mentions 2688 -> (127,504) (:17-19).
+static const short kLte[188][3] = {
+    {40,3,10},{48,7,12},{56,19,42},{64,7,16},{72,7,18},{80,11,20},{88,5,22},{96,11,24},{104,7,26},{112,41,84},
+    {120,103,90},{128,15,32},{136,9,34},{144,17,108},{152,9,38},{160,21,120},{168,101,84},{176,21,44},{184,57,46},{192,23,48},
+    {200,13,50},{208,27,52},{216,11,36},{224,27,56},{232,85,58},{240,29,60},{248,33,62},{256,15,32},{264,17,198},{272,33,68},
+    {280,103,210},{288,19,36},{296,19,74},{304,37,76},{312,19,78},{320,21,120},{328,21,82},{336,115,84},{344,193,86},{352,21,44},
+    {360,133,90},{368,81,46},{376,45,94},{384,23,48},{392,243,98},{400,151,40},{408,155,102},{416,25,52},{424,51,106},{432,47,72},
+    {440,91,110},{448,29,168},{456,29,114},{464,247,58},{472,29,118},{480,89,180},{488,91,122},{496,157,62},{504,55,84},{512,31,64},
+    {528,17,66},{544,35,68},{560,227,420},{576,65,96},{592,19,74},{608,37,76},{624,41,234},{640,39,80},{656,185,82},{672,43,252},
+    {688,21,86},{704,155,44},{720,79,120},{736,139,92},{752,23,94},{768,217,48},{784,25,98},{800,17,80},{816,127,102},{832,25,52},
+    {848,239,106},{864,17,48},{880,137,110},{896,215,112},{912,29,114},{928,15,58},{944,147,118},{960,29,60},{976,59,122},{992,65,124},
+    {1008,55,84},{1024,31,64},{1056,17,66},{1088,171,204},{1120,67,140},{1152,35,72},{1184,19,74},{1216,39,76},{1248,19,78},{1280,199,240},
+    {1312,21,82},{1344,211,252},{1376,21,86},{1408,43,88},{1440,149,60},{1472,45,92},{1504,49,846},{1536,71,48},{1568,13,28},{1600,17,80},
+    {1632,25,102},{1664,183,104},{1696,55,954},{1728,127,96},{1760,27,110},{1792,29,112},{1824,29,114},{1856,57,116},{1888,45,354},{1920,31,120},
+    {1952,59,610},{1984,185,124},{2016,113,420},{2048,31,64},{2112,17,66},{2176,171,136},{2240,209,420},{2304,253,216},{2368,367,444},{2432,265,456},
+    {2496,181,468},{2560,39,80},{2624,27,164},{2688,127,504},{2752,143,172},{2816,43,88},{2880,29,300},{2944,45,92},{3008,157,188},{3072,47,96},
+    {3136,13,28},{3200,111,240},{3264,443,204},{3328,51,104},{3392,51,212},{3456,451,192},{3520,257,220},{3584,57,336},{3648,313,228},{3712,271,232},
+    {3776,179,236},{3840,331,120},{3904,363,244},{3968,375,248},{4032,127,168},{4096,31,64},{4160,33,130},{4224,43,264},{4288,33,134},{4352,477,408},
+    {4416,35,138},{4480,233,280},{4544,357,142},{4608,337,480},{4672,37,146},{4736,71,444},{4800,71,120},{4864,37,152},{4928,39,462},{4992,127,234},
+    {5056,39,158},{5120,39,80},{5184,31,96},{5248,113,902},{5312,41,166},{5376,251,336},{5440,43,170},{5504,21,86},{5568,43,174},{5632,45,176},
+    {5696,45,178},{5760,161,120},{5824,89,182},{5888,323,184},{5952,47,186},{6016,23,94},{6080,47,190},{6144,263,480}};
+
+}  // namespace tdb200
+
+using namespace tdb200;
+
+// ---------------------------------------------------------------------------- handle
+struct tdb200_decoder {
+    tdb200_config cfg{};
+    int T = 0, NL = 0;
+    int sm_count = 0;
+    int *d_pi = nullptr, *d_pi_inv = nullptr;
+    std::vector<int> h_pi;
+    Ref64Workspace ws64{};
+    void *ws64_block = nullptr;
+    // staging for TDB200_MEM_HOST callers (one chunk)
+    void *d_in = nullptr;
+    size_t d_in_bytes = 0;
+    uint8_t *d_bits = nullptr;
+    int32_t *d_bits_iters = nullptr;
+    int32_t *d_iters_used = nullptr;
+    void *d_llr1 = nullptr, *d_llr2 = nullptr, *d_ext2 = nullptr;
+    int launches_last = 0;
+};
+
+// Ensure a device staging buffer of at least `bytes`.
+template <typename P>
+static int ensure(P *&p, size_t &have, size_t bytes)
+{
+    if (have >= bytes) return TDB200_OK;
+    cudaFree(p);
+    p = nullptr; have = 0;
+    TDB_CUDA(cudaMalloc(&p, bytes));
+    have = bytes;
+    return TDB200_OK;
+}
+template <typename P>
+static int ensure_once(P *&p, size_t bytes)
+{
+    if (p) return TDB200_OK;
+    TDB_CUDA(cudaMalloc(&p, bytes));
+    return TDB200_OK;
+}
+
+static size_t llr_elem_size(int t) { return t == TDB200_LLR_F64 ? 8 : (t == TDB200_LLR_F32 ? 4 : 1); }
+
+extern "C" {
+
+const char *tdb200_last_error(void) { return g_err; }
+
+const char *tdb200_status_string(int s)
+{
+    switch (s) {
+        case TDB200_OK: return "ok";
+        case TDB200_ERR_INVALID_ARG: return "invalid argument";
+        case TDB200_ERR_UNSUPPORTED: return "unsupported";
+        case TDB200_ERR_NO_DEVICE: return "no CUDA device";
+        case TDB200_ERR_CUDA: return "CUDA error";
+        case TDB200_ERR_ALLOC: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+int tdb200_lte_qpp_params(int K, int *f1, int *f2)
+{
+    for (auto &r : kLte)
+        if (r[0] == K) {
+            if (f1) *f1 = r[1];
+            if (f2) *f2 = r[2];
+            return TDB200_OK;
+        }
+    return fail(TDB200_ERR_INVALID_ARG, "K=%d is not an LTE turbo block size", K);
+}
+
+int tdb200_default_config(tdb200_config *cfg, int K)
+{
+    if (!cfg) return fail(TDB200_ERR_INVALID_ARG, "cfg is NULL");
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->K = K;
+    cfg->n_iter = 8;
+    cfg->algo = TDB200_ALGO_MAXLOG_S16;
+    return TDB200_OK;
+}
+
+void tdb200_destroy(tdb200_decoder *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->cfg.device);
+    cudaFree(d->d_pi); cudaFree(d->d_pi_inv); cudaFree(d->ws64_block); cudaFree(d->d_in);
+    cudaFree(d->d_bits); cudaFree(d->d_bits_iters); cudaFree(d->d_iters_used);
+    cudaFree(d->d_llr1); cudaFree(d->d_llr2); cudaFree(d->d_ext2);
+    delete d;
+}
+
+static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
+{
+    if (!trellis_literals_ok()) return fail(TDB200_ERR_UNSUPPORTED, "internal: trellis literals disagree with the (13,15) generator");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(TDB200_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    }
+    d->cfg = *cfg;
+    tdb200_config &c = d->cfg;
+    if (c.device < 0 || c.device >= ndev) return fail(TDB200_ERR_INVALID_ARG, "device %d out of range (have %d)", c.device, ndev);
+    if (c.K < 8 || c.K > 8192) return fail(TDB200_ERR_INVALID_ARG, "K=%d out of range [8,8192]", c.K);
+    if (c.f1 == 0 && c.f2 == 0) {
+        int s = tdb200_lte_qpp_params(c.K, &c.f1, &c.f2);
+        if (s != TDB200_OK) return s;
+    }
+    if (c.n_iter < 1 || c.n_iter > 64) return fail(TDB200_ERR_INVALID_ARG, "n_iter=%d out of range [1,64]", c.n_iter);
+    d->T = c.K + kTail;
+    d->NL = 3 * c.K + 4 * kTail;
+
+    // QPP permutation pi(i) = (f1*i + f2*i^2) mod K (gen_qpp_index, log_map.cpp:616-624), built
+    // with the second-difference recurrence; must be a bijection.
+    const int K = c.K;
+    d->h_pi.resize(K);
+    std::vector<int> inv(K, -1);
+    {
+        long long p = 0, g = ((long long)c.f1 + c.f2) % K;  // pi(i+1) - pi(i) at i = 0
+        const long long g2 = (2LL * c.f2) % K;
+        for (int i = 0; i < K; i++) {
+            d->h_pi[i] = (int)p;
+            if (inv[p] != -1) return fail(TDB200_ERR_INVALID_ARG, "(f1=%d,f2=%d) is not a permutation for K=%d", c.f1, c.f2, K);
+            inv[p] = i;
+            p = (p + g) % K;
+            g = (g + g2) % K;
+        }
+    }
+    TDB_CUDA(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    TDB_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    d->sm_count = prop.multiProcessorCount;
+    TDB_CUDA(cudaMalloc(&d->d_pi, sizeof(int) * K));
+    TDB_CUDA(cudaMalloc(&d->d_pi_inv, sizeof(int) * K));
+    TDB_CUDA(cudaMemcpy(d->d_pi, d->h_pi.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+    TDB_CUDA(cudaMemcpy(d->d_pi_inv, inv.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+
+    if (c.algo == TDB200_ALGO_LOGMAP_F64) {
+        if (c.early_term) return fail(TDB200_ERR_UNSUPPORTED, "early termination is not part of the reference-order fp64 mode");
+        if (c.max_batch <= 0) c.max_batch = 4096;
+        const size_t nb = (size_t)((c.max_batch + 3) / 4) * 4;  // warps own groups of four
+        const size_t T = d->T;
+        const size_t per_cb = 7 * T + (T + 1) + 2 * 8 * (T + 1);
+        TDB_CUDA(cudaMalloc(&d->ws64_block, sizeof(double) * per_cb * nb));
+        double *p = static_cast<double *>(d->ws64_block);
+        Ref64Workspace &w = d->ws64;
+        w.xs1 = p; p += T * nb;
+        w.xp1 = p; p += T * nb;
+        w.xs2 = p; p += T * nb;
+        w.xp2 = p; p += T * nb;
+        w.La = p; p += T * nb;
+        w.Le = p; p += T * nb;
+        w.LLR = p; p += T * nb;
+        w.tmax = p; p += (T + 1) * nb;
+        w.alpha = p; p += 8 * (T + 1) * nb;
+        w.beta = p; p += 8 * (T + 1) * nb;
+        w.max_batch = c.max_batch;
+    } else {
+        return fail(TDB200_ERR_UNSUPPORTED, "algo %d is not built into this library yet", c.algo);
+    }
+    return TDB200_OK;
+}
+
+int tdb200_create(const tdb200_config *cfg, tdb200_decoder **out)
+{
+    if (!cfg || !out) return fail(TDB200_ERR_INVALID_ARG, "cfg/out is NULL");
+    *out = nullptr;
+    tdb200_decoder *d = new (std::nothrow) tdb200_decoder;
+    if (!d) return fail(TDB200_ERR_ALLOC, "host allocation failed");
+    int s = create_impl(cfg, d);
+    if (s != TDB200_OK) {
+        tdb200_destroy(d);
+        return s;
+    }
+    *out = d;
+    return TDB200_OK;
+}
+
+int tdb200_get_plan(const tdb200_decoder *d, tdb200_plan_info *info)
+{
+    if (!d || !info) return fail(TDB200_ERR_INVALID_ARG, "dec/info is NULL");
+    std::memset(info, 0, sizeof(*info));
+    info->K = d->cfg.K; info->f1 = d->cfg.f1; info->f2 = d->cfg.f2;
+    info->n_iter = d->cfg.n_iter; info->algo = d->cfg.algo;
+    info->max_batch = d->cfg.max_batch; info->sm_count = d->sm_count;
+    info->kernel_launches_last_call = d->launches_last;
+    if (d->cfg.algo == TDB200_ALGO_LOGMAP_F64) {
+        info->sub_block = d->cfg.K; info->n_sub_blocks = 1; info->cb_per_cta = 8; info->threads_per_cta = 64;
+    }
+    return TDB200_OK;
+}
+
+int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int mem, int n_cb,
+                        const tdb200_outputs *out, void *stream)
+{
+    if (!d || !llr || !out) return fail(TDB200_ERR_INVALID_ARG, "dec/llr/out is NULL");
+    if (n_cb < 0) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d", n_cb);
+    if (llr_type < TDB200_LLR_F64 || llr_type > TDB200_LLR_S8) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d", llr_type);
+    if (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE) return fail(TDB200_ERR_INVALID_ARG, "mem=%d", mem);
+    d->launches_last = 0;
+    if (n_cb == 0) return TDB200_OK;
+    const tdb200_config &c = d->cfg;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDB_CUDA(cudaSetDevice(c.device));
+    const int K = c.K, T = d->T, NL = d->NL;
+    const size_t esz = llr_elem_size(llr_type);
+    const bool host = (mem == TDB200_MEM_HOST);
+    const int chunk = c.max_batch;
+
+    if (c.algo != TDB200_ALGO_LOGMAP_F64) return fail(TDB200_ERR_UNSUPPORTED, "algo %d", c.algo);
+    const size_t fsz = sizeof(double);  // native float type of the LLR outputs
+
+    if (host) {
+        int s = ensure(d->d_in, d->d_in_bytes, (size_t)chunk * NL * 8);
+        if (s) return s;
+        if (out->bits && (s = ensure_once(d->d_bits, (size_t)chunk * K))) return s;
+        if (out->bits_iters && (s = ensure_once(d->d_bits_iters, sizeof(int32_t) * (size_t)chunk * c.n_iter * K))) return s;
+        if (out->iters_used && (s = ensure_once(d->d_iters_used, sizeof(int32_t) * (size_t)chunk))) return s;
+        if (out->llr_siso1 && (s = ensure_once(d->d_llr1, 8 * (size_t)chunk * T))) return s;
+        if (out->llr_siso2 && (s = ensure_once(d->d_llr2, 8 * (size_t)chunk * T))) return s;
+        if (out->ext_siso2 && (s = ensure_once(d->d_ext2, 8 * (size_t)chunk * T))) return s;
+    }
+
+    for (int c0 = 0; c0 < n_cb; c0 += chunk) {
+        const int n = std::min(chunk, n_cb - c0);
+        const char *src = static_cast<const char *>(llr) + (size_t)c0 * NL * esz;
+        Ref64Args a{};
+        a.llr_type = llr_type; a.n_cb = n; a.K = K; a.n_iter = c.n_iter;
+        a.pi = d->d_pi; a.pi_inv = d->d_pi_inv; a.ws = d->ws64;
+        if (host) {
+            TDB_CUDA(cudaMemcpyAsync(d->d_in, src, (size_t)n * NL * esz, cudaMemcpyHostToDevice, st));
+            a.llr = d->d_in;
+            a.bits = out->bits ? d->d_bits : nullptr;
+            a.bits_iters = out->bits_iters ? d->d_bits_iters : nullptr;
+            a.llr1 = out->llr_siso1 ? static_cast<double *>(d->d_llr1) : nullptr;
+            a.llr2 = out->llr_siso2 ? static_cast<double *>(d->d_llr2) : nullptr;
+            a.ext2 = out->ext_siso2 ? static_cast<double *>(d->d_ext2) : nullptr;
+        } else {
+            a.llr = src;
+            a.bits = out->bits ? out->bits + (size_t)c0 * K : nullptr;
+            a.bits_iters = out->bits_iters ? out->bits_iters + (size_t)c0 * c.n_iter * K : nullptr;
+            a.llr1 = out->llr_siso1 ? static_cast<double *>(out->llr_siso1) + (size_t)c0 * T : nullptr;
+            a.llr2 = out->llr_siso2 ? static_cast<double *>(out->llr_siso2) + (size_t)c0 * T : nullptr;
+            a.ext2 = out->ext_siso2 ? static_cast<double *>(out->ext_siso2) + (size_t)c0 * T : nullptr;
+        }
+        TDB_CUDA(launch_ref64_decode(a, st, &d->launches_last));
+        if (out->iters_used) {
+            // the fp64 mode always runs every iteration
+            std::vector<int32_t> v(n, c.n_iter);
+            if (host) std::copy(v.begin(), v.end(), out->iters_used + c0);
+            else TDB_CUDA(cudaMemcpyAsync(out->iters_used + c0, v.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+            if (!host) TDB_CUDA(cudaStreamSynchronize(st));  // v goes out of scope
+        }
+        if (host) {
+            if (out->bits) TDB_CUDA(cudaMemcpyAsync(out->bits + (size_t)c0 * K, d->d_bits, (size_t)n * K, cudaMemcpyDeviceToHost, st));
+            if (out->bits_iters) TDB_CUDA(cudaMemcpyAsync(out->bits_iters + (size_t)c0 * c.n_iter * K, d->d_bits_iters, sizeof(int32_t) * (size_t)n * c.n_iter * K, cudaMemcpyDeviceToHost, st));
+            if (out->llr_siso1) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->llr_siso1) + fsz * (size_t)c0 * T, d->d_llr1, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, st));
+            if (out->llr_siso2) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->llr_siso2) + fsz * (size_t)c0 * T, d->d_llr2, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, st));
+            if (out->ext_siso2) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->ext_siso2) + fsz * (size_t)c0 * T, d->d_ext2, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, st));
+            TDB_CUDA(cudaStreamSynchronize(st));  // staging buffers are reused by the next chunk
+        }
+    }
+    return TDB200_OK;
+}
+
+int tdb200_siso_batch(tdb200_decoder *d, const double *recs, const double *La, int terminated,
+                      double *LLR, int mem, int n_cb, void *stream)
+{
+    if (!d || !recs || !La || !LLR) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (d->cfg.algo != TDB200_ALGO_LOGMAP_F64) return fail(TDB200_ERR_UNSUPPORTED, "tdb200_siso_batch needs a TDB200_ALGO_LOGMAP_F64 decoder");
+    if (n_cb < 0) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d", n_cb);
+    d->launches_last = 0;
+    if (n_cb == 0) return TDB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    const int T = d->T, chunk = d->cfg.max_batch;
+    const bool host = (mem == TDB200_MEM_HOST);
+    if (host) {
+        int s = ensure(d->d_in, d->d_in_bytes, (size_t)chunk * d->NL * 8);  // >= 3T doubles per codeblock
+        if (s) return s;
+        if ((s = ensure_once(d->d_llr1, 8 * (size_t)chunk * T))) return s;
+    }
+    for (int c0 = 0; c0 < n_cb; c0 += chunk) {
+        const int n = std::min(chunk, n_cb - c0);
+        Ref64SisoArgs a{};
+        a.terminated = terminated; a.n_cb = n; a.T = T; a.ws = d->ws64;
+        if (host) {
+            double *din = static_cast<double *>(d->d_in);
+            TDB_CUDA(cudaMemcpyAsync(din, recs + (size_t)c0 * 2 * T, 8 * (size_t)n * 2 * T, cudaMemcpyHostToDevice, st));
+            TDB_CUDA(cudaMemcpyAsync(din + (size_t)chunk * 2 * T, La + (size_t)c0 * T, 8 * (size_t)n * T, cudaMemcpyHostToDevice, st));
+            a.recs = din; a.La = din + (size_t)chunk * 2 * T; a.LLR = static_cast<double *>(d->d_llr1);
+        } else {
+            a.recs = recs + (size_t)c0 * 2 * T; a.La = La + (size_t)c0 * T; a.LLR = LLR + (size_t)c0 * T;
+        }
+        TDB_CUDA(launch_ref64_siso(a, st, &d->launches_last));
+        if (host) {
+            TDB_CUDA(cudaMemcpyAsync(LLR + (size_t)c0 * T, d->d_llr1, 8 * (size_t)n * T, cudaMemcpyDeviceToHost, st));
+            TDB_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    return TDB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// tdb200_internal.h -- shared declarations between the C-ABI translation unit and the kernel
+// translation units.  Nothing here is exported.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tdb200.h"
+
+namespace tdb200 {
+
+constexpr int kStates = 8;  // (13,15)_8 RSC, ITTC/log_map.cpp:28-29
+constexpr int kTail = 3;    // M_num_reg
+
+// (13,15)_8 trellis, derived once on the host by rsc_step() in tdb200_api.cu (cf. gen_trellis,
+// ITTC/log_map.cpp:281-337):
+//   next state for input 0 / 1:      ns0 = {0,4,5,1,2,6,7,3}   ns1 = {4,0,1,5,6,2,3,7}
+//   parity bit for input 0 from s:   c0  = {0,0,1,1,1,1,0,0}   (input 1: 1 - c0)
+//   previous state reaching s with input 0 / 1: ls0 = {0,3,4,7,1,2,5,6}  ls1 = {1,2,5,6,0,3,4,7}
+struct Trellis {
+    int ns0[kStates], ns1[kStates], ls0[kStates], ls1[kStates];
+    int par0[kStates];  // parity bit (0/1) leaving state s with input 0
+};
+const Trellis &host_trellis();
+
+// 3-bit packed trellis tables, state 0 in the low bits (checked against the host-derived
+// trellis in tdb200_create()).
+__host__ __device__ constexpr unsigned pack8(int a, int b, int c, int d, int e, int f, int g, int h)
+{
+    return a | (b << 3) | (c << 6) | (d << 9) | (e << 12) | (f << 15) | (g << 18) | (h << 21);
+}
+constexpr unsigned kNs0 = pack8(0, 4, 5, 1, 2, 6, 7, 3);
+constexpr unsigned kNs1 = pack8(4, 0, 1, 5, 6, 2, 3, 7);
+constexpr unsigned kLs0 = pack8(0, 3, 4, 7, 1, 2, 5, 6);
+constexpr unsigned kLs1 = pack8(1, 2, 5, 6, 0, 3, 4, 7);
+constexpr unsigned kPar0 = 0x3C;  // bit s = parity leaving state s with input 0: {0,0,1,1,1,1,0,0}
+
+__host__ __device__ constexpr int tb(unsigned t, int s) { return (t >> (3 * s)) & 7; }
+// parity as +-1 for input 0 / input 1 from state s (mx_nextout[s*4+1], [s*4+3])
+__host__ __device__ constexpr double o0(int s) { return ((kPar0 >> s) & 1) ? 1.0 : -1.0; }
+__host__ __device__ constexpr double o1(int s) { return -o0(s); }
+
+// ------------------------------------------------------------------ fp64 reference-order path
+struct Ref64Workspace {
+    // per codeblock, T = K+3 doubles each unless noted
+    double *xs1, *xp1, *xs2, *xp2;  // half-LLRs after demultiplex (yk_turbo, log_map.cpp:1083-1127)
+    double *La, *Le, *LLR;
+    double *tmax;         // [T+1]
+    double *alpha, *beta; // [T+1][8]
+    int max_batch;
+};
+
+struct Ref64Args {
+    const void *llr;   // [n_cb][3K+12] device, llr_type
+    int llr_type;
+    int n_cb, K, n_iter;
+    const int *pi;     // [K] device
+    const int *pi_inv; // [K] device
+    Ref64Workspace ws;
+    // outputs (device, nullable)
+    uint8_t *bits;
+    int32_t *bits_iters;
+    double *llr1, *llr2, *ext2;
+};
+cudaError_t launch_ref64_decode(const Ref64Args &a, cudaStream_t st, int *n_launches);
+
+struct Ref64SisoArgs {
+    const double *recs, *La;
+    double *LLR;
+    int terminated, n_cb, T;
+    Ref64Workspace ws;
+};
+cudaError_t launch_ref64_siso(const Ref64SisoArgs &a, cudaStream_t st, int *n_launches);
+
+}  // namespace tdb200

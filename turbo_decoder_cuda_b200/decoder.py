@@ -1,0 +1,198 @@
+"""Python mirror of the C ABI in include/tdb200.h (ctypes; no compute happens in Python).
+
+The reference's interface for this path is a pair of C++ free functions
+(`TurboDecoding`, `Log_MAP_decoder`, ITTC/main.h:20, ITTC/log_map.cpp:898,1146) configured by
+globals; `TurboDecoder` keeps their argument meaning (LLR layout 3K+12 in the reference's
+multiplex order, hard decisions per iteration, natural order) for a batch of codeblocks.
+Buffers may be numpy arrays (host) or torch CUDA tensors (device, zero-copy).
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is present, construction
+raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libtdb200.so")
+
+ALGO_LOGMAP_F64 = 0
+ALGO_MAXLOG_S16 = 1
+ALGO_LOGMAP_F32 = 2
+ALGO_MAXLOG_F32 = 3
+ALGO_NAMES = {"logmap_f64": 0, "maxlog_s16": 1, "logmap_f32": 2, "maxlog_f32": 3}
+
+LLR_F64, LLR_F32, LLR_S8 = 0, 1, 2
+MEM_HOST, MEM_DEVICE = 0, 1
+
+
+class TdbError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("tdb200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "K", "f1", "f2", "n_iter", "algo", "sub_block", "warmup", "early_term", "ext_scale_q2",
+        "frac_bits", "device", "max_batch")]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("bits", C.c_void_p), ("bits_iters", C.c_void_p), ("iters_used", C.c_void_p),
+                ("llr_siso1", C.c_void_p), ("llr_siso2", C.c_void_p), ("ext_siso2", C.c_void_p)]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "K", "f1", "f2", "n_iter", "algo", "sub_block", "n_sub_blocks", "warmup", "cb_per_cta",
+        "threads_per_cta", "smem_bytes", "max_batch", "sm_count", "kernel_launches_last_call")]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s is missing: build it with `python -m turbo_decoder_cuda_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.tdb200_last_error.restype = C.c_char_p
+    L.tdb200_status_string.restype = C.c_char_p
+    L.tdb200_status_string.argtypes = [C.c_int]
+    L.tdb200_default_config.argtypes = [C.POINTER(Config), C.c_int]
+    L.tdb200_lte_qpp_params.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.tdb200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.tdb200_destroy.argtypes = [C.c_void_p]
+    L.tdb200_destroy.restype = None
+    L.tdb200_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(Outputs), C.c_void_p]
+    L.tdb200_siso_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_void_p]
+    L.tdb200_get_plan.argtypes = [C.c_void_p, C.POINTER(PlanInfo)]
+    _lib = L
+    return L
+
+
+def _check(status):
+    if status != 0:
+        raise TdbError(status, load_library().tdb200_last_error().decode())
+
+
+def lte_qpp_params(K):
+    f1, f2 = C.c_int(), C.c_int()
+    _check(load_library().tdb200_lte_qpp_params(K, C.byref(f1), C.byref(f2)))
+    return f1.value, f2.value
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr_of(x):
+    """(pointer, mem_space) of a numpy array or a torch tensor."""
+    if x is None:
+        return None, None
+    if _is_torch(x):
+        assert x.is_contiguous()
+        return x.data_ptr(), (MEM_DEVICE if x.is_cuda else MEM_HOST)
+    assert x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data, MEM_HOST
+
+
+_LLR_TYPES = {"float64": LLR_F64, "float32": LLR_F32, "int8": LLR_S8}
+
+
+class TurboDecoder:
+    """Batched iterative PCCC decoder handle (tdb200_create / tdb200_destroy)."""
+
+    def __init__(self, K, n_iter=8, algo="maxlog_s16", f1=0, f2=0, sub_block=0, warmup=0,
+                 early_term=False, ext_scale_q2=0, frac_bits=0, device=0, max_batch=0):
+        L = load_library()
+        cfg = Config()
+        _check(L.tdb200_default_config(C.byref(cfg), K))
+        cfg.f1, cfg.f2, cfg.n_iter = f1, f2, n_iter
+        cfg.algo = ALGO_NAMES[algo] if isinstance(algo, str) else int(algo)
+        cfg.sub_block, cfg.warmup, cfg.early_term = sub_block, warmup, int(early_term)
+        cfg.ext_scale_q2, cfg.frac_bits, cfg.device, cfg.max_batch = ext_scale_q2, frac_bits, device, max_batch
+        h = C.c_void_p()
+        _check(L.tdb200_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._L = L
+        self.K, self.T, self.n_iter, self.algo, self.device = K, K + 3, n_iter, cfg.algo, device
+        self.llr_len = 3 * K + 12
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tdb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def plan(self):
+        info = PlanInfo()
+        _check(self._L.tdb200_get_plan(self._h, C.byref(info)))
+        return {n: getattr(info, n) for n, _ in PlanInfo._fields_}
+
+    @property
+    def float_dtype(self):
+        return np.float64 if self.algo == ALGO_LOGMAP_F64 else np.float32
+
+    def decode_raw(self, llr_ptr, llr_type, mem, n_cb, bits=None, bits_iters=None, iters_used=None,
+                   llr_siso1=None, llr_siso2=None, ext_siso2=None, stream=0):
+        """Thin call-through with raw pointers (used by bench.py's timed loops)."""
+        o = Outputs(bits, bits_iters, iters_used, llr_siso1, llr_siso2, ext_siso2)
+        _check(self._L.tdb200_decode_batch(self._h, llr_ptr, llr_type, mem, n_cb, C.byref(o), stream))
+
+    def decode(self, llr, want=("bits",), stream=0):
+        """Decode llr[n_cb, 3K+12] (numpy -> host path, torch.cuda tensor -> device path).
+
+        `want` selects outputs among bits, bits_iters, iters_used, llr_siso1, llr_siso2, ext_siso2;
+        returns a dict of arrays of the same kind (numpy / torch) as the input.
+        """
+        n_cb = int(llr.shape[0])
+        assert int(llr.shape[1]) == self.llr_len, "llr must be [n_cb, 3K+12]"
+        tname = str(llr.dtype).replace("torch.", "")
+        if tname not in _LLR_TYPES:
+            raise TypeError("llr dtype %s not supported" % tname)
+        ptr, mem = _ptr_of(llr)
+        K, T = self.K, self.T
+        shapes = {"bits": ((n_cb, K), "uint8"), "bits_iters": ((n_cb, self.n_iter, K), "int32"),
+                  "iters_used": ((n_cb,), "int32"),
+                  "llr_siso1": ((n_cb, T), None), "llr_siso2": ((n_cb, T), None), "ext_siso2": ((n_cb, T), None)}
+        outs = {}
+        for name in want:
+            shape, dt = shapes[name]
+            if _is_torch(llr):
+                import torch
+                tdt = getattr(torch, dt) if dt else (torch.float64 if self.algo == ALGO_LOGMAP_F64 else torch.float32)
+                outs[name] = torch.empty(shape, dtype=tdt, device=llr.device)
+            else:
+                outs[name] = np.empty(shape, dtype=dt or self.float_dtype)
+        ptrs = {k: _ptr_of(v)[0] for k, v in outs.items()}
+        self.decode_raw(ptr, _LLR_TYPES[tname], mem, n_cb, stream=stream, **ptrs)
+        return outs
+
+    def siso(self, recs, La, terminated=1, stream=0):
+        """One BCJR pass (tdb200_siso_batch), the Log_MAP_decoder replacement; doubles only."""
+        n_cb = int(La.shape[0])
+        rp, mem = _ptr_of(recs)
+        lp, _ = _ptr_of(La)
+        if _is_torch(La):
+            import torch
+            out = torch.empty_like(La)
+        else:
+            out = np.empty_like(La)
+        op, _ = _ptr_of(out)
+        _check(self._L.tdb200_siso_batch(self._h, rp, lp, terminated, op, mem, n_cb, stream))
+        return out
