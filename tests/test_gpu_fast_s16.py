@@ -1,0 +1,135 @@
+"""GPU parity of the throughput mode (TDB200_ALGO_MAXLOG_S16) through the C ABI.
+
+Integer work -> the bar is BIT-EXACT: hard decisions and extrinsics must equal the int32
+specification oracle/turbo_oracle_fx.c on the same seeded inputs, for every geometry
+(sub-block length L, guard G), fixed-point format and input type, including ragged batches
+(odd n_cb: the second int16 lane of the last CTA is a duplicate whose outputs are dropped).
+The statistical relation of this mode to the reference Log-MAP is tested in test_gpu_ber.py.
+"""
+import numpy as np
+import pytest
+
+from oracle_lib import FxParams
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _fx_params(K, n_iter, L, G, F=3, q2=3):
+    return FxParams(K=K, n_iter=n_iter, sub_len=L, warmup=G, frac_bits=F,
+                    llr_clip=min((1 << (F + 4)) - 1, 127), ext_clip=(1 << (F + 7)) - 1,
+                    ext_scale_q2=q2, early_term=0)
+
+
+def _check(oracle, dec, llr_in, llr_f32, pi, prm, n_cb, K):
+    out = dec.decode(llr_in, want=("bits", "ext_siso2", "llr_siso2", "iters_used"))
+    out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+    scale = float(1 << prm.frac_bits)
+    for c in range(n_cb):
+        bits, le, it, ovf = oracle.fx_decode(llr_f32[c], pi, prm, want_le=True)
+        assert ovf == 0, "int16 range exceeded in the specification model"
+        assert np.array_equal(out["bits"][c], bits.astype(np.uint8)), "hard decisions differ (cb %d)" % c
+        got = np.rint(out["ext_siso2"][c][:K] * scale).astype(np.int32)
+        assert np.array_equal(got, le[pi]), "extrinsics differ (cb %d)" % c
+        # a-posteriori sign must agree with the delivered decision
+        lam = out["llr_siso2"][c][:K]
+        assert np.array_equal((lam >= 0).astype(np.uint8), bits[pi].astype(np.uint8))
+        assert out["iters_used"][c] == prm.n_iter
+
+
+@pytest.mark.parametrize("K,L,G,n_cb,n_iter,ebn0", [
+    (6144, 0, 0, 5, 8, 0.6),     # auto plan (L=48, G=16): BASELINE configs[1] geometry, odd batch
+    (6144, 48, 0, 2, 4, 0.4),    # next-iteration initialisation only
+    (6144, 96, 32, 2, 3, 0.4),
+    (6144, 32, 8, 3, 3, 0.8),
+    (6144, 24, 24, 2, 2, 0.8),   # guard == sub-block length
+    (40, 40, 0, 7, 6, 2.0),      # single sub-block: exact unsegmented max-log
+    (40, 8, 8, 4, 4, 2.0),
+    (512, 16, 16, 4, 5, 1.5),
+    (1008, 0, 0, 3, 4, 1.0),     # P = 21: not a warp multiple
+    (2048, 64, 16, 2, 4, 1.0),
+])
+def test_bit_exact_vs_fixed_point_model(oracle, K, L, G, n_cb, n_iter, ebn0):
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, n_cb, ebn0, seed=77 + K + L)
+    llr32 = llr.astype(np.float32)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16", sub_block=L, warmup=G)
+    plan = dec.plan()
+    prm = _fx_params(K, n_iter, plan["sub_block"], plan["warmup"])
+    _check(oracle, dec, torch.from_numpy(llr32).cuda(), llr32, pi, prm, n_cb, K)   # device path
+    _check(oracle, dec, llr32, llr32, pi, prm, n_cb, K)                             # host path
+
+
+@pytest.mark.parametrize("F,q2", [(4, 3), (3, 4), (2, 3)])
+def test_fixed_point_formats(oracle, F, q2):
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_cb, n_iter = 1024, 4, 5
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, n_cb, 1.0, seed=31)
+    llr32 = llr.astype(np.float32)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16", frac_bits=F, ext_scale_q2=q2)
+    plan = dec.plan()
+    _check(oracle, dec, llr32, llr32, pi, _fx_params(K, n_iter, plan["sub_block"], plan["warmup"], F, q2), n_cb, K)
+
+
+def test_input_types(oracle):
+    """float64 input is rounded to float32 first; int8 input is taken as already quantised."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_cb, n_iter = 768, 3, 4
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, n_cb, 1.2, seed=8)
+    llr32 = llr.astype(np.float32)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16")
+    plan = dec.plan()
+    prm = _fx_params(K, n_iter, plan["sub_block"], plan["warmup"])
+    _check(oracle, dec, llr, llr32, pi, prm, n_cb, K)
+    q = np.clip(np.rint(llr32 * 8.0), -127, 127).astype(np.int8)
+    _check(oracle, dec, q, (q.astype(np.float32) / 8.0), pi, prm, n_cb, K)
+
+
+def test_extreme_llrs_do_not_overflow(oracle):
+    """Saturated, erased (0 / NaN) and sign-alternating inputs stay inside int16 and stay bit-exact."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_iter = 6144, 8
+    pi = oracle.qpp(K)
+    rng = np.random.default_rng(5)
+    bits, llr = oracle.make_batch(K, 4, 3.0, seed=9)
+    llr32 = llr.astype(np.float32)
+    llr32[0] *= 1e4                      # everything saturates at the channel clip
+    llr32[1, ::7] = 0.0                  # erasures
+    llr32[1, 5::11] = np.nan
+    llr32[2] = (rng.integers(0, 2, llr32.shape[1]) * 2 - 1) * 1e3   # saturated garbage: no codeword
+    llr32[3] = 0.0                       # all erased
+    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16")
+    plan = dec.plan()
+    prm = _fx_params(K, n_iter, plan["sub_block"], plan["warmup"])
+    out = dec.decode(llr32, want=("bits", "ext_siso2"))
+    for c in range(4):
+        b, le, it, ovf = oracle.fx_decode(np.nan_to_num(llr32[c], nan=0.0), pi, prm, want_le=True)
+        assert ovf == 0
+        assert np.array_equal(out["bits"][c], b.astype(np.uint8))
+        assert np.array_equal(np.rint(out["ext_siso2"][c][:K] * 8).astype(np.int32), le[pi])
+    assert np.array_equal(out["bits"][0], bits[0].astype(np.uint8))
+
+
+def test_decodes_clean_codewords(oracle):
+    """Size-independent property at the full BASELINE size: at 2 dB every codeblock of a 64-block
+    batch decodes to the transmitted bits."""
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K = 6144
+    bits, llr = oracle.make_batch(K, 64, 2.0, seed=4)
+    dec = TurboDecoder(K, n_iter=8, algo="maxlog_s16")
+    out = dec.decode(torch.from_numpy(llr.astype(np.float32)).cuda(), want=("bits",))
+    assert np.array_equal(out["bits"].cpu().numpy(), bits.astype(np.uint8))

@@ -111,6 +111,8 @@ struct tdb200_decoder {
     std::vector<int> h_pi;
     Ref64Workspace ws64{};
     void *ws64_block = nullptr;
+    FastGeom geom{};
+    uint16_t *d_tab2 = nullptr;
     // staging for TDB200_MEM_HOST callers (one chunk)
     void *d_in = nullptr;
     size_t d_in_bytes = 0;
@@ -184,7 +186,7 @@ void tdb200_destroy(tdb200_decoder *d)
 {
     if (!d) return;
     cudaSetDevice(d->cfg.device);
-    cudaFree(d->d_pi); cudaFree(d->d_pi_inv); cudaFree(d->ws64_block); cudaFree(d->d_in);
+    cudaFree(d->d_pi); cudaFree(d->d_pi_inv); cudaFree(d->ws64_block); cudaFree(d->d_tab2); cudaFree(d->d_in);
     cudaFree(d->d_bits); cudaFree(d->d_bits_iters); cudaFree(d->d_iters_used);
     cudaFree(d->d_llr1); cudaFree(d->d_llr2); cudaFree(d->d_ext2);
     delete d;
@@ -255,6 +257,46 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         w.alpha = p; p += 8 * (T + 1) * nb;
         w.beta = p; p += 8 * (T + 1) * nb;
         w.max_batch = c.max_batch;
+    } else if (c.algo == TDB200_ALGO_MAXLOG_S16) {
+        if (c.early_term) return fail(TDB200_ERR_UNSUPPORTED, "early termination is not built into this library yet");
+        if (c.max_batch <= 0) c.max_batch = 16384;
+        if (c.frac_bits == 0) c.frac_bits = 3;
+        if (c.frac_bits < 1 || c.frac_bits > 4) return fail(TDB200_ERR_INVALID_ARG, "frac_bits=%d out of range [1,4]", c.frac_bits);
+        if (c.ext_scale_q2 == 0) c.ext_scale_q2 = 3;
+        if (c.ext_scale_q2 != 3 && c.ext_scale_q2 != 4) return fail(TDB200_ERR_INVALID_ARG, "ext_scale_q2=%d (3 or 4)", c.ext_scale_q2);
+        // ---- sub-block geometry: K = P * L, L = 8 * NW, P <= 256 threads
+        FastGeom &g = d->geom;
+        int L = c.sub_block;
+        if (L == 0) {
+            static const int pref[] = {48, 40, 56, 32, 64, 24, 72, 80, 96, 16, 128, 8};
+            for (int cand : pref)
+                if (K % cand == 0 && K / cand <= 256) { L = cand; break; }
+            if (L == 0)
+                for (int cand = 8; cand <= K; cand += 8)
+                    if (K % cand == 0 && K / cand <= 256) { L = cand; break; }
+        }
+        if (L < 8 || L % 8 || K % L || K / L > 256)
+            return fail(TDB200_ERR_INVALID_ARG, "sub_block=%d must be a multiple of 8 dividing K=%d with K/sub_block <= 256", L, K);
+        int G = c.warmup;
+        if (G < 0 || G % 8) return fail(TDB200_ERR_INVALID_ARG, "warmup=%d must be a non-negative multiple of 8", G);
+        if (c.warmup == 0 && c.sub_block == 0) G = 16;  // auto plan: guard of 16 (BER vs (L,G))
+        if (G > L) G = L;
+        g.K = K; g.L = L; g.P = K / L; g.NW = L / 8; g.G = (g.P == 1) ? 0 : G;
+        g.threads = ((g.P + 31) / 32) * 32;
+        g.n_ckpt = std::max(g.NW - 2, 0);
+        g.smem_bytes = fast_s16_smem_bytes(g);
+        if ((size_t)g.smem_bytes > prop.sharedMemPerBlockOptin)
+            return fail(TDB200_ERR_UNSUPPORTED, "plan needs %d B of shared memory per CTA, device allows %zu", g.smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
+        c.sub_block = L; c.warmup = g.G;
+        TDB_CUDA(fast_s16_configure(g));
+        // word address of element pi(tL+j), stored at j*P+t
+        std::vector<uint16_t> tab(K);
+        for (int i = 0; i < K; i++) {
+            const int t = i / L, j = i % L, n = d->h_pi[i];
+            tab[j * g.P + t] = (uint16_t)((n % L) * g.P + n / L);
+        }
+        TDB_CUDA(cudaMalloc(&d->d_tab2, sizeof(uint16_t) * K));
+        TDB_CUDA(cudaMemcpy(d->d_tab2, tab.data(), sizeof(uint16_t) * K, cudaMemcpyHostToDevice));
     } else {
         return fail(TDB200_ERR_UNSUPPORTED, "algo %d is not built into this library yet", c.algo);
     }
@@ -286,6 +328,9 @@ int tdb200_get_plan(const tdb200_decoder *d, tdb200_plan_info *info)
     info->kernel_launches_last_call = d->launches_last;
     if (d->cfg.algo == TDB200_ALGO_LOGMAP_F64) {
         info->sub_block = d->cfg.K; info->n_sub_blocks = 1; info->cb_per_cta = 8; info->threads_per_cta = 64;
+    } else {
+        info->sub_block = d->geom.L; info->n_sub_blocks = d->geom.P; info->warmup = d->geom.G;
+        info->cb_per_cta = 2; info->threads_per_cta = d->geom.threads; info->smem_bytes = d->geom.smem_bytes;
     }
     return TDB200_OK;
 }
@@ -307,11 +352,13 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
     const bool host = (mem == TDB200_MEM_HOST);
     const int chunk = c.max_batch;
 
-    if (c.algo != TDB200_ALGO_LOGMAP_F64) return fail(TDB200_ERR_UNSUPPORTED, "algo %d", c.algo);
-    const size_t fsz = sizeof(double);  // native float type of the LLR outputs
+    const bool f64 = (c.algo == TDB200_ALGO_LOGMAP_F64);
+    const size_t fsz = f64 ? sizeof(double) : sizeof(float);  // native float type of the LLR outputs
+    if (!f64 && (out->bits_iters || out->llr_siso1))
+        return fail(TDB200_ERR_UNSUPPORTED, "bits_iters / llr_siso1 are produced by TDB200_ALGO_LOGMAP_F64 only");
 
     if (host) {
-        int s = ensure(d->d_in, d->d_in_bytes, (size_t)chunk * NL * 8);
+        int s = ensure(d->d_in, d->d_in_bytes, (size_t)chunk * NL * esz);
         if (s) return s;
         if (out->bits && (s = ensure_once(d->d_bits, (size_t)chunk * K))) return s;
         if (out->bits_iters && (s = ensure_once(d->d_bits_iters, sizeof(int32_t) * (size_t)chunk * c.n_iter * K))) return s;
@@ -324,36 +371,53 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
     for (int c0 = 0; c0 < n_cb; c0 += chunk) {
         const int n = std::min(chunk, n_cb - c0);
         const char *src = static_cast<const char *>(llr) + (size_t)c0 * NL * esz;
-        Ref64Args a{};
-        a.llr_type = llr_type; a.n_cb = n; a.K = K; a.n_iter = c.n_iter;
-        a.pi = d->d_pi; a.pi_inv = d->d_pi_inv; a.ws = d->ws64;
+        // device-side views of this chunk
+        const void *v_llr = src;
+        uint8_t *v_bits = out->bits ? out->bits + (size_t)c0 * K : nullptr;
+        int32_t *v_bits_iters = out->bits_iters ? out->bits_iters + (size_t)c0 * c.n_iter * K : nullptr;
+        int32_t *v_iters = out->iters_used ? out->iters_used + c0 : nullptr;
+        char *v_llr1 = out->llr_siso1 ? static_cast<char *>(out->llr_siso1) + fsz * (size_t)c0 * T : nullptr;
+        char *v_llr2 = out->llr_siso2 ? static_cast<char *>(out->llr_siso2) + fsz * (size_t)c0 * T : nullptr;
+        char *v_ext2 = out->ext_siso2 ? static_cast<char *>(out->ext_siso2) + fsz * (size_t)c0 * T : nullptr;
         if (host) {
             TDB_CUDA(cudaMemcpyAsync(d->d_in, src, (size_t)n * NL * esz, cudaMemcpyHostToDevice, st));
-            a.llr = d->d_in;
-            a.bits = out->bits ? d->d_bits : nullptr;
-            a.bits_iters = out->bits_iters ? d->d_bits_iters : nullptr;
-            a.llr1 = out->llr_siso1 ? static_cast<double *>(d->d_llr1) : nullptr;
-            a.llr2 = out->llr_siso2 ? static_cast<double *>(d->d_llr2) : nullptr;
-            a.ext2 = out->ext_siso2 ? static_cast<double *>(d->d_ext2) : nullptr;
-        } else {
-            a.llr = src;
-            a.bits = out->bits ? out->bits + (size_t)c0 * K : nullptr;
-            a.bits_iters = out->bits_iters ? out->bits_iters + (size_t)c0 * c.n_iter * K : nullptr;
-            a.llr1 = out->llr_siso1 ? static_cast<double *>(out->llr_siso1) + (size_t)c0 * T : nullptr;
-            a.llr2 = out->llr_siso2 ? static_cast<double *>(out->llr_siso2) + (size_t)c0 * T : nullptr;
-            a.ext2 = out->ext_siso2 ? static_cast<double *>(out->ext_siso2) + (size_t)c0 * T : nullptr;
+            v_llr = d->d_in;
+            if (v_bits) v_bits = d->d_bits;
+            if (v_bits_iters) v_bits_iters = d->d_bits_iters;
+            if (v_iters) v_iters = d->d_iters_used;
+            if (v_llr1) v_llr1 = static_cast<char *>(d->d_llr1);
+            if (v_llr2) v_llr2 = static_cast<char *>(d->d_llr2);
+            if (v_ext2) v_ext2 = static_cast<char *>(d->d_ext2);
         }
-        TDB_CUDA(launch_ref64_decode(a, st, &d->launches_last));
-        if (out->iters_used) {
-            // the fp64 mode always runs every iteration
-            std::vector<int32_t> v(n, c.n_iter);
-            if (host) std::copy(v.begin(), v.end(), out->iters_used + c0);
-            else TDB_CUDA(cudaMemcpyAsync(out->iters_used + c0, v.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-            if (!host) TDB_CUDA(cudaStreamSynchronize(st));  // v goes out of scope
+        if (f64) {
+            Ref64Args a{};
+            a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.K = K; a.n_iter = c.n_iter;
+            a.pi = d->d_pi; a.pi_inv = d->d_pi_inv; a.ws = d->ws64;
+            a.bits = v_bits; a.bits_iters = v_bits_iters;
+            a.llr1 = reinterpret_cast<double *>(v_llr1); a.llr2 = reinterpret_cast<double *>(v_llr2);
+            a.ext2 = reinterpret_cast<double *>(v_ext2);
+            TDB_CUDA(launch_ref64_decode(a, st, &d->launches_last));
+            if (v_iters) {  // the fp64 mode always runs every iteration
+                std::vector<int32_t> v(n, c.n_iter);
+                TDB_CUDA(cudaMemcpyAsync(v_iters, v.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+                TDB_CUDA(cudaStreamSynchronize(st));  // v goes out of scope
+            }
+        } else {
+            FastArgs a{};
+            a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.g = d->geom; a.n_iter = c.n_iter;
+            a.frac_bits = c.frac_bits;
+            a.llr_clip = std::min((1 << (c.frac_bits + 4)) - 1, 127);  // systematic values are kept as int8 pairs in shared memory
+            a.ext_lim = 1 << (c.frac_bits + 7);
+            a.q2 = c.ext_scale_q2; a.early_term = c.early_term;
+            a.tab2 = d->d_tab2;
+            a.bits = v_bits; a.iters_used = v_iters;
+            a.llr2 = reinterpret_cast<float *>(v_llr2); a.ext2 = reinterpret_cast<float *>(v_ext2);
+            TDB_CUDA(launch_fast_s16(a, st, &d->launches_last));
         }
         if (host) {
             if (out->bits) TDB_CUDA(cudaMemcpyAsync(out->bits + (size_t)c0 * K, d->d_bits, (size_t)n * K, cudaMemcpyDeviceToHost, st));
             if (out->bits_iters) TDB_CUDA(cudaMemcpyAsync(out->bits_iters + (size_t)c0 * c.n_iter * K, d->d_bits_iters, sizeof(int32_t) * (size_t)n * c.n_iter * K, cudaMemcpyDeviceToHost, st));
+            if (out->iters_used) TDB_CUDA(cudaMemcpyAsync(out->iters_used + c0, d->d_iters_used, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
             if (out->llr_siso1) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->llr_siso1) + fsz * (size_t)c0 * T, d->d_llr1, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, st));
             if (out->llr_siso2) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->llr_siso2) + fsz * (size_t)c0 * T, d->d_llr2, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, st));
             if (out->ext_siso2) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->ext_siso2) + fsz * (size_t)c0 * T, d->d_ext2, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, st));

@@ -72,4 +72,37 @@ struct Ref64SisoArgs {
 };
 cudaError_t launch_ref64_siso(const Ref64SisoArgs &a, cudaStream_t st, int *n_launches);
 
+// ------------------------------------------------------------------ sub-block-parallel fast path
+// Geometry of one codeblock: K = P * L, L = 8 * NW.  Sub-block t in [0,P) owns trellis steps
+// [tL, (t+1)L); element n = tL + j lives at shared-memory word  j*P + t  ("step-major"), which
+// makes both the natural walk (consecutive t -> consecutive banks) and the QPP walk
+// (pi(tL+j) = r_j + L*((q_j + A_t + j*B_t) mod P): same row r_j for all t, column a permutation
+// polynomial in t) bank-conflict free when 32 | P.
+constexpr int kFxNeg = -14000;  // metric of an impossible state (range analysis in DESIGN.md)
+
+struct FastGeom {
+    int K, L, P, NW, G;
+    int threads;     // CTA size: P rounded up to a warp multiple
+    int n_ckpt;      // alpha checkpoints kept in shared memory per thread: max(NW-2, 0)
+    int smem_bytes;
+};
+
+struct FastArgs {
+    const void *llr;  // [n_cb][3K+12] device
+    int llr_type;
+    int n_cb;
+    FastGeom g;
+    int n_iter;
+    int frac_bits, llr_clip, ext_lim /* Ce+1, multiple of 4 */, q2;
+    int early_term;
+    const uint16_t *tab2;  // [K] device: smem word of element pi(tL+j), stored at index j*P+t
+    // outputs (device, nullable)
+    uint8_t *bits;
+    int32_t *iters_used;
+    float *llr2, *ext2;  // [n_cb][K+3]
+};
+cudaError_t fast_s16_configure(const FastGeom &g);  // opt in to the dynamic shared memory size
+cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches);
+int fast_s16_smem_bytes(const FastGeom &g);
+
 }  // namespace tdb200
