@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the turbo-decode hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU decoder on host cores
+
+Metric: decoded information Gbit/s, K=6144, 8 iterations (BASELINE.json `metric`), on
+BASELINE configs[1]: LTE K=6144 QPP(263,480), max-log-MAP, 8 iterations, 4096 codeblocks per GPU.
+A "step" is one decode of one batch of synthetic channel LLRs (random bits -> (13,15) PCCC ->
+BPSK/AWGN at --ebn0 -> LLR = 2r/sigma^2, made by turbo_decoder_cuda_b200/synth.py before timing).
+
+  value  : whole-job Gbit/s with the LLR batch already resident in HBM (device pointers through
+           the C ABI), timed with CUDA events on the launching stream, max over ranks.
+  e2e    : the same metric through the same C-ABI call with HOST buffers (pinned): H2D of the LLRs
+           and D2H of the hard decisions inside the timed region.
+Codeblocks are independent: ranks decode disjoint shards, no collective on the data path ("weak").
+Only the cpu_baseline leg and --impl reference touch oracle/ (as the thing timed there, per the
+tier contract); the CUDA arm fails loudly if the CUDA library is missing.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 6144
+N_ITER = 8
+OPS_PER_INFO_BIT = 2 * N_ITER * 101 * (K + 3) / K  # ~101 add/max ops per trellis step per SISO
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), float(d.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_reference_decoder():
+    """(decode_batch(llr_f64, n_threads) -> (bits, seconds), kind) from oracle/ -- the reference's own
+    code compiled in place when oracle/_ref exists, else the C restatement."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle, RefLib
+    o = Oracle()
+    f1, f2 = o.lte_params(K)
+    if RefLib.available():
+        r = RefLib(K, f1, f2)
+        return (lambda llr, nt: r.decode_batch(llr, N_ITER, nt)), "reference"
+    pi = o.qpp(K)
+    return (lambda llr, nt: o.decode_batch(llr, pi, N_ITER, 1, nt)), "port"
+
+
+def run_reference(args):
+    """--impl reference: the reference CPU Log-MAP (fp64, 8 iterations) on all host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from turbo_decoder_cuda_b200 import synth
+    cores = host_cores()
+    decode, kind = cpu_reference_decoder()
+    n_sample = args.ref_sample or max(4 * cores, 8)
+    bits, llr = synth.make_batch(K, n_sample, args.ebn0, seed=1000, device="cpu", dtype=torch.float64)
+    llr = llr.numpy()
+    for _ in range(args.warmup):
+        decode(llr[:max(cores, 1)], cores)
+    t = 0.0
+    errs = 0
+    for _ in range(args.steps):
+        out, secs = decode(llr, cores)
+        t += secs
+        errs += int((out != bits.numpy()).sum())
+    value = n_sample * K * args.steps / t / 1e9
+    line = {
+        "impl": "reference", "metric": "decoded info Gbit/s, K=6144, 8 iterations", "value": value, "unit": "Gbit/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.batch, None),
+        "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": kind,
+                         "sample": "%d codeblocks per step (K=6144, fp64 LUT Log-MAP, 8 iterations, one codeword per thread)" % n_sample},
+        "e2e": {"value": value, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "ber": errs / float(n_sample * K * args.steps),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch, plan):
+    cfg = {"workload": "BASELINE configs[1]: LTE turbo K=6144 QPP(263,480), max-log-MAP, 8 iterations, "
+                       "batch of %d codeblocks per GPU" % args.batch,
+           "K": K, "n_iter": N_ITER, "batch_per_gpu": batch, "ebn0_db": args.ebn0, "algo": args.algo,
+           "llr_input": "float32 [n_cb, 3K+12], reference multiplex order",
+           "l2_policy": "inputs larger than L2 (%.0f MB of LLRs per step vs 126 MB)" % (batch * (3 * K + 12) * 4 / 1e6),
+           "parallelism": "codeblock-sharded, no collective"}
+    if plan:
+        cfg.update({"sub_block": plan["sub_block"], "n_sub_blocks": plan["n_sub_blocks"], "guard": plan["warmup"],
+                    "cb_per_cta": plan["cb_per_cta"], "smem_bytes_per_cta": plan["smem_bytes"]})
+    return cfg
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from turbo_decoder_cuda_b200 import TurboDecoder, decoder as tdb, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    batch = args.batch
+    # synthetic traffic is made on the host (keeps the GPU launch list down to the decoder itself)
+    bits, llr = synth.make_batch(K, batch, args.ebn0, seed=1000 + rank, device="cpu")
+    bits, llr = bits.to(dev), llr.to(dev)
+    dec = TurboDecoder(K, n_iter=N_ITER, algo=args.algo, device=local, max_batch=batch)
+    plan = dec.plan()
+    out_bits = torch.empty((batch, K), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def step_dev():
+        dec.decode_raw(llr.data_ptr(), tdb.LLR_F32, tdb.MEM_DEVICE, batch, bits=out_bits.data_ptr(), stream=sp)
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize()
+    launches_per_step = dec.plan()["kernel_launches_last_call"]
+    sampler = ClockSampler(local)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    ber = float((out_bits != bits).sum().item()) / (batch * K)
+
+    # ---- end to end through host buffers (pinned): H2D + decode + D2H inside the timed region
+    h_llr = torch.empty(llr.shape, dtype=llr.dtype, pin_memory=True)
+    h_llr.copy_(llr)
+    h_bits = torch.empty((batch, K), dtype=torch.uint8, pin_memory=True)
+
+    def step_host():
+        dec.decode_raw(h_llr.data_ptr(), tdb.LLR_F32, tdb.MEM_HOST, batch, bits=h_bits.data_ptr(), stream=sp)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_host()
+    torch.cuda.synchronize()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    f0.record(stream)
+    for _ in range(args.steps):
+        step_host()
+    f1.record(stream)
+    torch.cuda.synchronize()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), wall_ms)  # the host-buffer call blocks, so wall time is the honest clock
+    e2e_ok = bool((h_bits.to(dev) == out_bits).all().item())
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        b = torch.tensor([ber], device=dev, dtype=torch.float64)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        ber = float(b[0]) / world
+
+    if rank == 0:
+        total_bits = float(world) * batch * K * args.steps
+        value = total_bits / (ms * 1e-3) / 1e9
+        e2e = total_bits / (ms_e2e * 1e-3) / 1e9
+        hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+        kernel_ms = ms / args.steps / max(launches_per_step, 1)
+        alg_bytes = batch * ((3 * K + 12) * 4 + K)  # LLRs read once + one byte per decision written
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        alu_peak = 148 * 128 * sm_max_mhz * 1e6 * 2  # packed 16-bit lane-ops/s
+        alu_ach = (batch * K / (kernel_ms * 1e-3)) * OPS_PER_INFO_BIT
+        line = {
+            "metric": "decoded info Gbit/s, K=6144, 8 iterations", "value": value, "unit": "Gbit/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16",
+            "data": "synthetic", "config": workload_config(args, batch, plan),
+            "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": batch * (3 * K + 12) * 4,
+                    "d2h_bytes_per_step": batch * K, "matches_device_path": e2e_ok},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel": "fast_s16_kernel", "kernel_ms": kernel_ms,
+                         "note": "secondary bound: the path is ALU-bound by design (SURVEY.md 8d); see roofline.alu",
+                         "alu": {"achieved": alu_ach / 1e12, "peak": alu_peak / 1e12, "unit": "Tlane-op/s (packed 16-bit)",
+                                 "frac": alu_ach / alu_peak, "ops_per_info_bit": OPS_PER_INFO_BIT}},
+            "ber": ber,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            decode, kind = cpu_reference_decoder()
+            n_sample = args.ref_sample or max(4 * cores, 8)
+            sample = llr[:n_sample].double().cpu().numpy()
+            out, secs = decode(sample, cores)
+            line["cpu_baseline"] = {
+                "value": n_sample * K / secs / 1e9, "unit": "Gbit/s", "cores": cores, "kind": kind,
+                "sample": "first %d codeblocks of the batch, fp64 LUT Log-MAP, 8 iterations, one codeword per thread, %.1f s" % (n_sample, secs),
+                "ber": float((out != bits[:n_sample].cpu().numpy()).sum()) / (n_sample * K)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="codeblocks per GPU per step")
+    ap.add_argument("--ebn0", type=float, default=1.0)
+    ap.add_argument("--algo", default="maxlog_s16")
+    ap.add_argument("--ref-sample", type=int, default=0, help="codeblocks per CPU-baseline step (0 = 4 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

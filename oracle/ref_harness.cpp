@@ -11,6 +11,8 @@
  */
 #include "main.h" /* -I/root/reference/ITTC */
 
+#include <malloc.h>
+
 #include <chrono>
 #include <cstring>
 #include <mutex>
@@ -38,9 +40,27 @@ extern "C" {
 
 int ref_n_iteration_macro(void) { return 15; } /* N_ITERATION, ITTC/log_map.h:30 */
 
+/* The reference reads tempmax[] before writing it (log_map.cpp:925,989).  In its own process the
+ * heap is clean and the value is 0 or an earlier, benign tempmax; inside a Python process the
+ * recycled chunk can hold anything (1e300, NaN) and wreck a decode.  M_PERTURB = 0xFF makes glibc
+ * fill every malloc'd block with 0x00, i.e. the reference behaves as on a fresh heap:
+ * tempmax[i] = max(0, max_j alpha_j).  No reference source is touched. */
+void ref_heap_zeroing(int on) { mallopt(M_PERTURB, on ? 0xFF : 0); }
+
+/* M_PERTURB does not reach glibc's per-thread cache (blocks <= ~1 KB, i.e. tempmax[] for K <= 125):
+ * park zero-filled blocks of that size in the cache so the next malloc returns one of them. */
+static void scrub_small_blocks(size_t bytes)
+{
+    if (bytes > 1040) return;
+    void *p[8];
+    for (int i = 0; i < 8; i++) p[i] = calloc(1, bytes);
+    for (int i = 0; i < 8; i++) free(p[i]);
+}
+
 /* main.cpp:29-37,106 */
 void ref_init(int K, int qf1, int qf2)
 {
+    ref_heap_zeroing(1);
     if (g_ready) {
         TurboCodingRelease();
         g_ready = false;
@@ -90,11 +110,13 @@ void ref_channel(int *coded, double sigma, unsigned seed, double *llr)
 /* The reference's own TurboDecoding(): N_ITERATION = 15 iterations, mutates llr (x0.5). */
 void ref_turbo_decoding(double *llr, int *flow_decoded)
 {
+    scrub_small_blocks(sizeof(double) * (source_length + M_num_reg + 1));
     TurboDecoding(llr, flow_decoded, 3 * source_length + 4 * M_num_reg);
 }
 
 void ref_siso(double *recs, double *La, int terminated, double *LLR, int T)
 {
+    scrub_small_blocks(sizeof(double) * (T + 1));
     Log_MAP_decoder(recs, La, terminated, LLR, T);
 }
 
@@ -109,6 +131,7 @@ void ref_decode_iters(const double *llr, int n_iter, int *bits_out, double *llr1
     std::vector<double> h(n), yk(4 * T), La(T, 0.0), Le(T, 0.0), LLR(T, 0.0);
     std::vector<int> tmp(T);
     for (int i = 0; i < n; i++) h[i] = llr[i] * 0.5;
+    scrub_small_blocks(sizeof(double) * (T + 1));
     demultiplex(h.data(), K, yk.data());
     for (int it = 0; it < n_iter; it++) {
         random_deinterlvr_double(La.data(), Le.data(), index_randomintlvr, K);
@@ -152,11 +175,15 @@ double ref_decode_batch(const double *llrs, int n_cb, int n_iter, int *bits_last
         }
     };
     if (n_threads < 1) n_threads = 1;
+    /* timing leg: run the allocator natively (no zero-fill, ~7 % faster); each worker thread gets
+     * its own fresh glibc arena, so the uninitialised tempmax[] reads zero pages anyway */
+    ref_heap_zeroing(0);
     auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> th;
     for (int i = 0; i < n_threads; i++) th.emplace_back(worker);
     for (auto &t : th) t.join();
     auto t1 = std::chrono::steady_clock::now();
+    ref_heap_zeroing(1);
     return std::chrono::duration<double>(t1 - t0).count();
 }
 

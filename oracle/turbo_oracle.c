@@ -338,12 +338,13 @@ void tdo_turbo_decode(const double *llr_in, int K, const int *pi, int n_iter, in
     for (int it = 0; it < n_iter; it++) { /* :1217-1265 */
         for (int i = 0; i < K; i++) La[pi[i]] = Le[i]; /* random_deinterlvr_double, :87-96,1221 */
         for (int i = K; i < T; i++) La[i] = 0;
-        tdo_siso(yk, La, 1, LLR, T, algo, NAN);
+        /* tempmax floor 0.0: the reference on a clean (zero-filled) heap, see tdo_siso */
+        tdo_siso(yk, La, 1, LLR, T, algo, 0.0);
         if (llr1_out && it == n_iter - 1) memcpy(llr1_out, LLR, sizeof(double) * T);
         for (int i = 0; i < T; i++) Le[i] = LLR[i] - La[i] - 2 * yk[2 * i]; /* :1234-1238 */
         for (int i = 0; i < K; i++) La[i] = Le[pi[i]]; /* randominterleaver_double, :76-85,1242 */
         for (int i = K; i < T; i++) La[i] = 0;
-        tdo_siso(yk + 2 * T, La, 1, LLR, T, algo, NAN);
+        tdo_siso(yk + 2 * T, La, 1, LLR, T, algo, 0.0);
         for (int i = 0; i < T; i++) Le[i] = LLR[i] - La[i] - 2 * yk[2 * T + 2 * i]; /* :1255-1259 */
         if (bits_out)
             for (int i = 0; i < K; i++) /* decision :862-879 + random_deinterlvr_int :1264 */

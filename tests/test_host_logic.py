@@ -1,0 +1,171 @@
+"""CPU tests of the host side: the C-ABI library loads and exports everything include/tdb200.h
+declares (no compute without a GPU), the synthetic-traffic generator equals the oracle encoder,
+the fixed-point specification model relates to the reference-derived max-log oracle, and the
+codeblock sharding used by bench.py --gpus N works under a 2-rank gloo group."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle_lib import ALGO_MAXLOG, FxParams
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from turbo_decoder_cuda_b200 import build
+    build.build()
+    from turbo_decoder_cuda_b200 import load_library
+    return load_library()
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "tdb200.h")).read()
+    declared = set(re.findall(r"\b(tdb200_[a-z0-9_]+)\s*\(", hdr))
+    assert {"tdb200_create", "tdb200_destroy", "tdb200_decode_batch", "tdb200_siso_batch",
+            "tdb200_default_config", "tdb200_lte_qpp_params", "tdb200_get_plan",
+            "tdb200_last_error", "tdb200_status_string"} <= declared
+    for name in declared:
+        assert hasattr(lib, name), "libtdb200.so does not export %s" % name
+
+
+def test_compat_exports_reference_signatures(lib):
+    """compat/ re-exports the reference's C++ entry points (mangled exactly as g++ mangles ITTC/main.h)."""
+    so = os.path.join(ROOT, "turbo_decoder_cuda_b200", "lib", "libtdb200_compat.so")
+    if not os.path.exists(so):
+        pytest.skip("compat library not built")
+    c = ctypes.CDLL(so)
+    for sym in ("_Z13TurboDecodingPdPii", "_Z15Log_MAP_decoderPdS_iS_i", "_Z15TurboCodingInitv", "_Z18TurboCodingReleasev"):
+        assert hasattr(c, sym), sym
+
+
+def test_lte_table_matches_oracle(lib, oracle):
+    from turbo_decoder_cuda_b200 import TdbError, lte_qpp_params
+    for K in oracle.lte_sizes():
+        assert lte_qpp_params(K) == oracle.lte_params(K)
+    with pytest.raises(TdbError):
+        lte_qpp_params(6145)
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device creation fails loudly (status NO_DEVICE); with one this test is moot."""
+    import torch
+    from turbo_decoder_cuda_b200 import TdbError, TurboDecoder
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(TdbError) as e:
+        TurboDecoder(6144)
+    assert e.value.status == 3 and "no CPU path" in str(e.value)
+
+
+def test_synth_matches_oracle_encoder(oracle):
+    import torch
+    from turbo_decoder_cuda_b200 import synth
+    for K in (40, 1008, 6144):
+        pi = oracle.qpp(K)
+        assert np.array_equal(synth.qpp_permutation(K).numpy(), pi)
+        bits, llr = synth.make_batch(K, 3, 1.0, seed=5)
+        coded = synth.turbo_encode(bits, torch.from_numpy(pi).long())
+        for c in range(3):
+            assert np.array_equal(coded[c].numpy(), oracle.encode(bits[c].numpy().astype(np.int32), pi).astype(np.uint8))
+        assert abs(synth.sigma_from_ebn0(1.0, K) - oracle.sigma(1.0, K)) < 1e-12
+        assert llr.shape == (3, 3 * K + 12) and llr.dtype == torch.float32
+    # LLR sign convention: positive = bit 1; at high SNR the hard slice of the systematic LLRs is the data
+    bits, llr = synth.make_batch(512, 2, 20.0, seed=1)
+    assert np.array_equal((llr[:, 0:3 * 512:3] > 0).numpy().astype(np.uint8), bits.numpy())
+
+
+def _fx(K, n_iter, L, G, q2=3, F=3):
+    return FxParams(K=K, n_iter=n_iter, sub_len=L, warmup=G, frac_bits=F, llr_clip=127,
+                    ext_clip=(1 << (F + 7)) - 1, ext_scale_q2=q2, early_term=0)
+
+
+def test_fixed_point_model_is_exact_maxlog_when_unsegmented(oracle):
+    """One sub-block, no scaling: the int model must reproduce the fp64 max-log oracle (reference
+    Log_MAP_decoder with max* -> max) exactly on LLRs that are multiples of 1/8 -- every add/max is
+    exact in both.  This ties the GPU specification to the reference-derived oracle."""
+    K, n_iter = 512, 2
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, 4, 0.0, seed=17)
+    q = np.clip(np.rint(llr * 8), -127, 127) / 8.0
+    for c in range(4):
+        bits, le, it, ovf = oracle.fx_decode(q[c].astype(np.float32), pi, _fx(K, n_iter, K, 0, q2=4), want_le=True)
+        ob, _, o2, ole = oracle.decode(q[c], pi, n_iter, algo=ALGO_MAXLOG, want_llr=True)
+        assert ovf == 0 and it == n_iter
+        assert np.abs(ole[:K]).max() < 127.0           # no clamp active, else the comparison is void
+        assert np.array_equal(bits, ob[-1])
+        assert np.array_equal(le[pi], np.rint(ole[:K] * 8).astype(np.int32))
+
+
+def test_fixed_point_model_subblocks_and_guard(oracle):
+    """Segmentation only perturbs boundary metrics: at 1.5 dB every geometry decodes the block, and a
+    guard of 16 steps restores what pure next-iteration initialisation loses in the waterfall."""
+    K = 6144
+    pi = oracle.qpp(K)
+    bits, llr = oracle.make_batch(K, 2, 1.5, seed=3)
+    for L, G in ((6144, 0), (48, 16), (48, 0), (96, 32), (24, 24)):
+        for c in range(2):
+            b, _, _, ovf = oracle.fx_decode(llr[c].astype(np.float32), pi, _fx(K, 8, L, G))
+            assert ovf == 0 and np.array_equal(b, bits[c]), (L, G)
+    # L must be a multiple of 8 dividing K: the model rejects any other plan
+    assert oracle.fx_decode(llr[0].astype(np.float32), pi, _fx(K, 8, 50, 0))[2] == -1
+
+
+def test_early_termination_model(oracle):
+    K = 1024
+    pi = oracle.qpp(K)
+    bits, llr = oracle.make_batch(K, 3, 2.5, seed=9)
+    p = _fx(K, 8, 32, 16)
+    p.early_term = 1
+    for c in range(3):
+        b, _, it, _ = oracle.fx_decode(llr[c].astype(np.float32), pi, p)
+        assert 2 <= it < 8 and np.array_equal(b, bits[c])
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from turbo_decoder_cuda_b200 import shard
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    n = 1000003
+    lo, hi = shard.shard_range(n, world, rank)
+    got = [None] * world
+    dist.all_gather_object(got, (lo, hi))
+    t = shard.max_over_ranks(float(rank + 1) * 1.5, dist if world > 1 else None)
+    total = shard.sum_over_ranks(hi - lo, dist if world > 1 else None)
+    q.put((rank, got, t, total))
+    dist.destroy_process_group()
+
+
+def test_codeblock_sharding_two_ranks_gloo():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    for rank, got, t, total in res:
+        assert got[0] == (0, 500002) and got[1] == (500002, 1000003)   # disjoint, covering, balanced
+        assert t == 3.0 and total == 1000003
+
+
+def test_shard_range_properties():
+    from turbo_decoder_cuda_b200 import shard
+    for n in (0, 1, 7, 4096, 1000000):
+        for w in (1, 2, 4, 8):
+            r = [shard.shard_range(n, w, k) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1

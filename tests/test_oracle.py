@@ -1,0 +1,138 @@
+"""CPU tests of the oracle (oracle/turbo_oracle.c): pinned against the golden vectors generated
+from the reference's own code (tests/golden/make_golden.py), against known answers of the code
+(SURVEY.md 4 / Appendix B), and -- where oracle/_ref was built -- against the reference live."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import ALGO_MAXLOG, RefLib
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ------------------------------------------------------------------ constants
+def test_trellis_literals(oracle):
+    # dumped from the running reference == turboDecoderBianJieZhi.cu:208-226
+    no, ns, lo, ls = oracle.trellis()
+    assert ns[:, 0].tolist() == [0, 4, 5, 1, 2, 6, 7, 3]
+    assert ns[:, 1].tolist() == [4, 0, 1, 5, 6, 2, 3, 7]
+    assert ls[:, 0].tolist() == [0, 3, 4, 7, 1, 2, 5, 6]
+    assert ls[:, 1].tolist() == [1, 2, 5, 6, 0, 3, 4, 7]
+    assert no[:, 1].tolist() == [-1, -1, 1, 1, 1, 1, -1, -1]
+    assert (no[:, 3] == -no[:, 1]).all() and (no[:, 0] == -1).all() and (no[:, 2] == 1).all()
+
+
+def test_qpp_known_values_and_table(oracle):
+    pi = oracle.qpp(6144)
+    assert pi[:8].tolist() == [0, 743, 2446, 5109, 2588, 1027, 426, 785]  # TurboDecoder.cu:60
+    assert oracle.lte_params(6144) == (263, 480) and oracle.lte_params(2688) == (127, 504)  # main.cpp:17-19,36-37
+    sizes = oracle.lte_sizes()
+    expect = list(range(40, 512, 8)) + list(range(512, 1024, 16)) + list(range(1024, 2048, 32)) + list(range(2048, 6145, 64))
+    assert sizes == expect and len(sizes) == 188
+    for K in sizes:
+        assert np.array_equal(np.sort(oracle.qpp(K)), np.arange(K)), "pi not a bijection for K=%d" % K
+
+
+def test_impulse_encode(oracle):
+    K = 6144
+    bits = np.zeros(K, np.int32)
+    bits[0] = 1
+    c = oracle.encode(bits, oracle.qpp(K))
+    assert "".join(map(str, c[:12])) == "111011011011"
+    assert "".join(map(str, c[-12:])) == "000111000111"
+    z = oracle.encode(np.zeros(K, np.int32), oracle.qpp(K))
+    assert not z.any()
+
+
+# ------------------------------------------------------------------ golden vectors from the reference
+def test_max_star_lut_golden(oracle):
+    g = np.load(os.path.join(GOLD, "max_star_lut.npz"))
+    for x, y in zip(g["x"], g["y"]):
+        assert oracle.max_star(0.0, float(x)) == y
+        assert oracle.max_star(float(x), 0.0) == y        # symmetric
+    assert oracle.max_star(1.0, 1.0) == 1.0 + 0.69315
+    assert oracle.max_star(-3.0, 5.0) == 5.0              # |d| >= 4.3758 -> no correction
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "k*.npz"))))
+def test_decode_matches_reference_golden(oracle, path):
+    g = np.load(path)
+    K, n_iter = int(g["K"]), int(g["n_iter"])
+    pi = oracle.qpp(K, int(g["f1"]), int(g["f2"]))
+    llr = g["llr"].astype(np.float64)
+    bits, l1, l2, le = oracle.decode(llr, pi, n_iter, want_llr=True)
+    ref_bits = np.unpackbits(g["bits"], axis=1)[:, :K]
+    assert np.array_equal(bits, ref_bits)
+    # identical operation order -> rounding-noise agreement (exactly 0 for the large blocks; the
+    # reference's uninitialised tempmax[] leaves ~1e-13 on K=40, see oracle/ref_harness.cpp)
+    for a, b in ((l1, g["llr1"]), (l2, g["llr2"]), (le, g["le"])):
+        assert np.abs(a - b).max() < 1e-9
+    tx = np.unpackbits(g["tx_bits"])[:K]
+    assert np.array_equal(bits[-1], tx), "fixture decodes cleanly by the last iteration"
+
+
+# ------------------------------------------------------------------ live reference (dev container only)
+@pytest.mark.skipif(not RefLib.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_vs_live_reference(oracle):
+    K = 1024
+    f1, f2 = oracle.lte_params(K)
+    r = RefLib(K, f1, f2)
+    pi = oracle.qpp(K)
+    assert np.array_equal(pi, r.qpp())
+    for a, b in zip(oracle.trellis(), r.trellis()):
+        assert np.array_equal(a, b)
+    bits_tx, llr = oracle.make_batch(K, 3, 0.8, seed=21)
+    for c in range(3):
+        assert np.array_equal(oracle.encode(bits_tx[c], pi), r.encode(bits_tx[c]))
+        rb, r1, r2, rle = r.decode(llr[c], 6, want_llr=True)
+        ob, o1, o2, ole = oracle.decode(llr[c], pi, 6, want_llr=True)
+        assert np.array_equal(rb, ob)
+        assert max(np.abs(r1 - o1).max(), np.abs(r2 - o2).max(), np.abs(rle - ole).max()) < 1e-9
+        assert np.array_equal(r.turbo_decoding(llr[c])[:6], rb)   # the reference's own 15-iteration entry point
+    rng = np.random.default_rng(0)
+    T = K + 3
+    recs, La = rng.normal(0, 2, 2 * T), rng.normal(0, 3, T)
+    for term in (1, 0):
+        assert np.abs(r.siso(recs, La, term) - oracle.siso(recs, La, terminated=term, tempmax_floor=0.0)).max() < 1e-9
+
+
+# ------------------------------------------------------------------ properties
+def test_noiseless_and_erasure_properties(oracle):
+    K = 512
+    pi = oracle.qpp(K)
+    rng = np.random.default_rng(1)
+    bits = rng.integers(0, 2, K, dtype=np.int32)
+    coded = oracle.encode(bits, pi)
+    llr = (2.0 * coded - 1.0) * 4.0
+    out = oracle.decode(llr, pi, 2)
+    assert np.array_equal(out[0], bits) and np.array_equal(out[1], bits)
+    # erase every parity-2 value and 10 % of the rest: the code still recovers the block
+    llr[2:3 * K:3] = 0.0
+    llr[rng.random(llr.size) < 0.1] = 0.0
+    assert np.array_equal(oracle.decode(llr, pi, 8)[-1], bits)
+    # all-zero input: LLR == 0 everywhere -> every decision is 1 (decision(): LLR<0 -> 0 else 1, :869-877)
+    assert oracle.decode(np.zeros(3 * K + 12), pi, 1)[0].all()
+
+
+def test_maxlog_is_logmap_without_correction(oracle):
+    """max-log SISO output differs from the LUT Log-MAP by a bounded amount (|corr| <= 0.69315 per max*)."""
+    rng = np.random.default_rng(2)
+    T = 259
+    recs, La = rng.normal(0, 1.5, 2 * T), rng.normal(0, 1.0, T)
+    a = oracle.siso(recs, La)
+    b = oracle.siso(recs, La, algo=ALGO_MAXLOG)
+    assert 0 < np.abs(a - b).max() < 8.0
+    assert (np.sign(a) == np.sign(b)).mean() > 0.9
+
+
+def test_batch_threads_agree(oracle):
+    K = 256
+    pi = oracle.qpp(K)
+    bits, llr = oracle.make_batch(K, 6, 1.5, seed=3)
+    b1, _ = oracle.decode_batch(llr, pi, 4, n_threads=1)
+    b4, _ = oracle.decode_batch(llr, pi, 4, n_threads=4)
+    assert np.array_equal(b1, b4)
+    for c in range(6):
+        assert np.array_equal(oracle.decode(llr[c], pi, 4)[-1], b1[c])

@@ -97,6 +97,9 @@ __device__ void siso_pass(const SisoPtrs &p, int T, int terminated, int lane)
                 const double t = __shfl_xor_sync(0xffffffffu, m, o, 8);
                 m = (m < t) ? t : m;
             }
+            // the reference compares against an uninitialised tempmax[] (:925,:989); on a clean
+            // (zero-filled) heap that is max(0, max_j alpha_j), which is what oracle/ pins
+            m = (m < 0.0) ? 0.0 : m;
             al = v - m;  // :996-999
             alpha[(size_t)(i + 1) * 8 + j] = al;
             if (j == 0) tmax[i + 1] = m;
