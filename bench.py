@@ -54,7 +54,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -73,7 +73,7 @@ class ClockSampler(threading.Thread):
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -82,10 +82,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._halt.wait(0.02)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
