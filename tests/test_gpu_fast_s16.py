@@ -123,6 +123,32 @@ def test_extreme_llrs_do_not_overflow(oracle):
     assert np.array_equal(out["bits"][0], bits[0].astype(np.uint8))
 
 
+@pytest.mark.parametrize("K,ebn0", [(6144, 1.2), (6144, 0.5), (1024, 2.0), (40, 3.0)])
+def test_early_termination(oracle, K, ebn0):
+    """Hard-decision-aided stop: iters_used equals the model's stopping iteration for every
+    codeblock; the two codeblocks of a CTA stop together, so the delivered bits are the model's
+    bits after max(iterations of the pair)."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    n_cb, n_iter = 7, 8
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, n_cb, ebn0, seed=91 + K)
+    llr32 = llr.astype(np.float32)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16", early_term=True)
+    plan = dec.plan()
+    out = dec.decode(llr32, want=("bits", "iters_used"))
+    prm = _fx_params(K, n_iter, plan["sub_block"], plan["warmup"])
+    prm.early_term = 1
+    its = [oracle.fx_decode(llr32[c], pi, prm)[2] for c in range(n_cb)]
+    assert out["iters_used"].tolist() == its
+    for c in range(n_cb):
+        mate = c ^ 1 if (c ^ 1) < n_cb else c
+        ran = max(its[c], its[mate])
+        b = oracle.fx_decode(llr32[c], pi, _fx_params(K, ran, plan["sub_block"], plan["warmup"]))[0]
+        assert np.array_equal(out["bits"][c], b.astype(np.uint8))
+    assert min(its) >= 2
+
+
 def test_decodes_clean_codewords(oracle):
     """Size-independent property at the full BASELINE size: at 2 dB every codeblock of a 64-block
     batch decodes to the transmitted bits."""

@@ -258,7 +258,6 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         w.beta = p; p += 8 * (T + 1) * nb;
         w.max_batch = c.max_batch;
     } else if (c.algo == TDB200_ALGO_MAXLOG_S16) {
-        if (c.early_term) return fail(TDB200_ERR_UNSUPPORTED, "early termination is not built into this library yet");
         if (c.max_batch <= 0) c.max_batch = 16384;
         if (c.frac_bits == 0) c.frac_bits = 3;
         if (c.frac_bits < 1 || c.frac_bits > 4) return fail(TDB200_ERR_INVALID_ARG, "frac_bits=%d out of range [1,4]", c.frac_bits);
@@ -282,6 +281,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         if (c.warmup == 0 && c.sub_block == 0) G = 16;  // auto plan: guard of 16 (BER vs (L,G))
         if (G > L) G = L;
         g.K = K; g.L = L; g.P = K / L; g.NW = L / 8; g.G = (g.P == 1) ? 0 : G;
+        g.PP = g.P | 1;  // odd row pitch: de-multiplex stores spread over the banks, walks stay conflict-free
         g.threads = ((g.P + 31) / 32) * 32;
         g.n_ckpt = std::max(g.NW - 2, 0);
         g.smem_bytes = fast_s16_smem_bytes(g);
@@ -289,14 +289,14 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
             return fail(TDB200_ERR_UNSUPPORTED, "plan needs %d B of shared memory per CTA, device allows %zu", g.smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
         c.sub_block = L; c.warmup = g.G;
         TDB_CUDA(fast_s16_configure(g));
-        // word address of element pi(tL+j), stored at j*P+t
-        std::vector<uint16_t> tab(K);
+        // word address of element pi(tL+j), stored at j*PP+t
+        std::vector<uint16_t> tab((size_t)L * g.PP, 0);
         for (int i = 0; i < K; i++) {
             const int t = i / L, j = i % L, n = d->h_pi[i];
-            tab[j * g.P + t] = (uint16_t)((n % L) * g.P + n / L);
+            tab[j * g.PP + t] = (uint16_t)((n % L) * g.PP + n / L);
         }
-        TDB_CUDA(cudaMalloc(&d->d_tab2, sizeof(uint16_t) * K));
-        TDB_CUDA(cudaMemcpy(d->d_tab2, tab.data(), sizeof(uint16_t) * K, cudaMemcpyHostToDevice));
+        TDB_CUDA(cudaMalloc(&d->d_tab2, sizeof(uint16_t) * tab.size()));
+        TDB_CUDA(cudaMemcpy(d->d_tab2, tab.data(), sizeof(uint16_t) * tab.size(), cudaMemcpyHostToDevice));
     } else {
         return fail(TDB200_ERR_UNSUPPORTED, "algo %d is not built into this library yet", c.algo);
     }

@@ -29,6 +29,13 @@
 //    step-major layout (tdb200_internal.h).
 //  * Tail bits only shape the beta vector at step K (La is zero there, :1224-1227), so they are
 //    folded into a constant start vector once per decode.
+//  * EARLY TERMINATION (new functionality; the reference only has a placeholder,
+//    previous/Decoder.cc:1098-1099): every thread keeps the hard decisions of its own steps as a
+//    bit mask; when a whole iteration changes none of them for either codeblock the CTA stops.
+//
+// The kernel is a template over the geometry: the BASELINE block size K=6144 (P=128 sub-blocks of
+// L=48 steps, guard 16) gets compile-time constants -- every shared-memory address becomes
+// base+immediate -- and every other LTE size runs the same code with run-time geometry.
 #include <cuda_runtime.h>
 
 #include "tdb200_internal.h"
@@ -38,8 +45,8 @@ namespace {
 
 typedef uint32_t w32;  // two int16 lanes: codeblock A in bits 0-15, codeblock B in bits 16-31
 
-__device__ __forceinline__ w32 vadd(w32 a, w32 b) { return __vadd2(a, b); }                    // VIADD.16x2  (fma pipe)
-__device__ __forceinline__ w32 vaddmax(w32 a, w32 b, w32 c) { return __viaddmax_s16x2(a, b, c); }  // VIADDMNMX.S16x2: max(a+b,c)
+__device__ __forceinline__ w32 vadd(w32 a, w32 b) { return __vadd2(a, b); }                        // VIADD.16x2      (fma-heavy pipe)
+__device__ __forceinline__ w32 vaddmax(w32 a, w32 b, w32 c) { return __viaddmax_s16x2(a, b, c); }  // VIADDMNMX.S16x2 (alu pipe): max(a+b,c)
 __device__ __forceinline__ w32 vneg(w32 a) { return __vadd2(~a, 0x00010001u); }
 __device__ __forceinline__ w32 pack2(int lo, int hi) { return (w32)(lo & 0xffff) | ((w32)hi << 16); }
 __device__ __forceinline__ w32 dup2(int v) { return pack2(v, v); }
@@ -52,8 +59,8 @@ __device__ __forceinline__ void norm8(w32 (&m)[8])
     for (int s = 1; s < 8; s++) m[s] = vadd(m[s], nz);
 }
 
-// alpha(i+1) from alpha(i); u = U_i, v = V_i   (restates the max-log form of :975-1001)
-__device__ __forceinline__ void alpha_step(w32 (&a)[8], w32 u, w32 v)
+// alpha(i+1) from alpha(i); u = U_i, v = V_i   (the max-log form of :975-1001)
+__device__ __forceinline__ void alpha_step_to(const w32 (&a)[8], w32 u, w32 v, w32 (&o)[8])
 {
     const w32 w = vadd(u, v);
     const w32 t5 = vadd(a[2], v), t1 = vadd(a[3], v), t2 = vadd(a[4], v), t6 = vadd(a[5], v);
@@ -61,8 +68,9 @@ __device__ __forceinline__ void alpha_step(w32 (&a)[8], w32 u, w32 v)
     const w32 o5 = vaddmax(a[3], u, t5), o1 = vaddmax(a[2], u, t1);
     const w32 o2 = vaddmax(a[5], u, t2), o6 = vaddmax(a[4], u, t6);
     const w32 o7 = vaddmax(a[7], w, a[6]), o3 = vaddmax(a[6], w, a[7]);
-    a[0] = o0; a[1] = o1; a[2] = o2; a[3] = o3; a[4] = o4; a[5] = o5; a[6] = o6; a[7] = o7;
+    o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3; o[4] = o4; o[5] = o5; o[6] = o6; o[7] = o7;
 }
+__device__ __forceinline__ void alpha_step(w32 (&a)[8], w32 u, w32 v) { alpha_step_to(a, u, v, a); }
 
 // beta(i) from beta(i+1)   (:1004-1021)
 __device__ __forceinline__ void beta_step(w32 (&b)[8], w32 u, w32 v)
@@ -100,22 +108,27 @@ __device__ __forceinline__ int quant(float x, float scale, int clip)
 }
 
 // 12 consecutive input values (4 systematic/parity1/parity2 triplets) starting at element 12*q
-__device__ __forceinline__ void load12(const void *base, int type, size_t row_elems, int cb, int q, float scale, int clip, int (&out)[12])
+template <int LLR_T>
+__device__ __forceinline__ void load12(const void *base, size_t row_elems, int cb, int q, float scale, int clip, int (&out)[12])
 {
-    if (type == TDB200_LLR_F32) {
+    if (LLR_T == TDB200_LLR_F32) {
         const float4 *p = reinterpret_cast<const float4 *>(static_cast<const float *>(base) + (size_t)cb * row_elems) + 3 * q;
+        float4 f[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) f[k] = __ldg(p + k);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const float4 f = __ldg(p + k);
-            out[4 * k] = quant(f.x, scale, clip); out[4 * k + 1] = quant(f.y, scale, clip);
-            out[4 * k + 2] = quant(f.z, scale, clip); out[4 * k + 3] = quant(f.w, scale, clip);
+            out[4 * k] = quant(f[k].x, scale, clip); out[4 * k + 1] = quant(f[k].y, scale, clip);
+            out[4 * k + 2] = quant(f[k].z, scale, clip); out[4 * k + 3] = quant(f[k].w, scale, clip);
         }
-    } else if (type == TDB200_LLR_F64) {
+    } else if (LLR_T == TDB200_LLR_F64) {
         const double2 *p = reinterpret_cast<const double2 *>(static_cast<const double *>(base) + (size_t)cb * row_elems) + 6 * q;
+        double2 f[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) f[k] = __ldg(p + k);
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            const double2 f = __ldg(p + k);
-            out[2 * k] = quant((float)f.x, scale, clip); out[2 * k + 1] = quant((float)f.y, scale, clip);
+            out[2 * k] = quant((float)f[k].x, scale, clip); out[2 * k + 1] = quant((float)f[k].y, scale, clip);
         }
     } else {
         const int *p = reinterpret_cast<const int *>(static_cast<const int8_t *>(base) + (size_t)cb * row_elems) + 3 * q;
@@ -131,10 +144,11 @@ __device__ __forceinline__ void load12(const void *base, int type, size_t row_el
     }
 }
 
-__device__ __forceinline__ int load1(const void *base, int type, size_t idx, float scale, int clip)
+template <int LLR_T>
+__device__ __forceinline__ int load1(const void *base, size_t idx, float scale, int clip)
 {
-    if (type == TDB200_LLR_F32) return quant(__ldg(static_cast<const float *>(base) + idx), scale, clip);
-    if (type == TDB200_LLR_F64) return quant((float)__ldg(static_cast<const double *>(base) + idx), scale, clip);
+    if (LLR_T == TDB200_LLR_F32) return quant(__ldg(static_cast<const float *>(base) + idx), scale, clip);
+    if (LLR_T == TDB200_LLR_F64) return quant((float)__ldg(static_cast<const double *>(base) + idx), scale, clip);
     const int v = (int)__ldg(static_cast<const int8_t *>(base) + idx);
     return max(min(v, clip), -clip);
 }
@@ -142,21 +156,8 @@ __device__ __forceinline__ int load1(const void *base, int type, size_t idx, flo
 struct Smem {
     w32 *X, *par1, *par2;
     uint16_t *sys8, *tab;
-    w32 *ckpt, *edge;
+    w32 *ckpt, *dec, *edge;
 };
-
-__device__ __forceinline__ Smem carve(unsigned char *base, int K, int P, int n_ckpt)
-{
-    Smem s;
-    s.X = reinterpret_cast<w32 *>(base);
-    s.par1 = s.X + K;
-    s.par2 = s.par1 + K;
-    s.sys8 = reinterpret_cast<uint16_t *>(s.par2 + K);
-    s.tab = s.sys8 + K;
-    s.ckpt = reinterpret_cast<w32 *>(s.tab + K);
-    s.edge = s.ckpt + (size_t)n_ckpt * 7 * P;
-    return s;
-}
 
 // sign-extend the two int8 of a 16-bit word into an s16x2
 __device__ __forceinline__ w32 sext8x2(unsigned v)
@@ -167,24 +168,28 @@ __device__ __forceinline__ w32 sext8x2(unsigned v)
 }
 
 struct PassCfg {
-    int t, P, L, NW, G, n_ckpt;
     int q2;
-    w32 lim;       // dup2(ext_lim)
-    w32 limmax;    // dup2(2*ext_lim - 1)
-    w32 unbias;    // dup2(-(3*ext_lim/4)) or dup2(-ext_lim)
+    w32 lim;     // dup2(ext_lim)
+    w32 limmax;  // dup2(2*ext_lim - 1)
+    w32 unbias;  // dup2(-(3*ext_lim/4)) or dup2(-ext_lim)
 };
 
 // One SISO pass of one sub-block.  IL = false: SISO-1 (natural order), true: SISO-2 (through tab).
 // na/nb: boundary vectors (alpha G steps before the sub-block, beta G steps after it); on return
-// they hold the vectors for the next iteration of this SISO.
-template <bool IL>
-__device__ __forceinline__ void siso_pass(const PassCfg &c, const Smem &sm, const w32 *par, w32 (&na)[8], w32 (&nb)[8],
-                                          const bool first_fixed, const bool last_fixed, w32 *stage)
+// they hold the vectors for the next iteration of this SISO.  With want_bits the hard decisions
+// of this pass go to sm.dec (one word per two windows) and the return value has bits 0-15 / 16-31
+// set where a decision of codeblock A / B differs from what sm.dec held before.
+template <bool IL, int KP, int KNW, int KG>
+__device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, const Smem &sm, const w32 *par, w32 (&na)[8], w32 (&nb)[8],
+                                         const bool first_fixed, const bool last_fixed, const bool want_bits, w32 *stage)
 {
-    const int t = c.t, P = c.P, NW = c.NW, G = c.G;
+    const int P = KP ? KP : g.P, PP = KP ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW, G = KP ? KG : g.G;
+    const int L = 8 * NW;
+    const int t = threadIdx.x;
     const bool active = t < P;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     w32 a[8], b[8], a0[8], sa[8], sb[8];
+    w32 changed = 0;
 #pragma unroll
     for (int s = 0; s < 8; s++) { a[s] = na[s]; b[s] = nb[s]; sa[s] = 0; sb[s] = 0; }
 
@@ -193,9 +198,10 @@ __device__ __forceinline__ void siso_pass(const PassCfg &c, const Smem &sm, cons
         if (!first_fixed)
             for (int g0 = 0; g0 < G; g0 += 8) {
                 norm8(a);
+                const int base = (L - G + g0) * PP + (t - 1);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const int idx = (c.L - G + g0 + k) * P + (t - 1);
+                    const int idx = base + k * PP;
                     const int e = IL ? sm.tab[idx] : idx;
                     alpha_step(a, sm.X[e], par[idx]);
                 }
@@ -204,14 +210,15 @@ __device__ __forceinline__ void siso_pass(const PassCfg &c, const Smem &sm, cons
         if (!last_fixed)
             for (int g0 = G - 8; g0 >= 0; g0 -= 8) {
                 norm8(b);
+                const int base = g0 * PP + (t + 1);
 #pragma unroll
                 for (int k = 7; k >= 0; k--) {
-                    const int idx = (g0 + k) * P + (t + 1);
+                    const int idx = base + k * PP;
                     const int e = IL ? sm.tab[idx] : idx;
                     beta_step(b, sm.X[e], par[idx]);
                 }
             }
-        if (G == c.L) {
+        if (G == L) {
 #pragma unroll
             for (int s = 0; s < 8; s++) sb[s] = b[s];
         }
@@ -224,9 +231,10 @@ __device__ __forceinline__ void siso_pass(const PassCfg &c, const Smem &sm, cons
 #pragma unroll
                 for (int s = 1; s < 8; s++) sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t] = a[s];
             }
+            const int base = 8 * w * PP + t;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const int idx = (8 * w + k) * P + t;
+                const int idx = base + k * PP;
                 const int e = IL ? sm.tab[idx] : idx;
                 alpha_step(a, sm.X[e], par[idx]);
             }
@@ -234,46 +242,50 @@ __device__ __forceinline__ void siso_pass(const PassCfg &c, const Smem &sm, cons
     }
     __syncthreads();  // every warm-up read of X precedes every in-place update below
     if (active) {
-        const int w_sa = (c.L - G) >> 3, w_sb = G >> 3;
+        const int w_sa = (L - G) >> 3, w_sb = G >> 3;
+        w32 hold = 0;  // decision bits of the odd window waiting for its even partner
         for (int w = NW - 1; w >= 0; w--) {
-            if (w < NW - 1) {
-                if (w == 0) {
-#pragma unroll
-                    for (int s = 0; s < 8; s++) a[s] = a0[s];
-                } else {
-                    a[0] = 0;
-#pragma unroll
-                    for (int s = 1; s < 8; s++) a[s] = sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t];
-                }
-            }
-            // ---- re-create the 8 alpha vectors of this window in registers
+            // ---- re-create the alpha vectors of this window in registers
             w32 aw[8][8], u[8], v[8];
             int e[8];
-            norm8(a);
+            if (w == NW - 1) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) aw[0][s] = a[s];
+                norm8(aw[0]);
+            } else if (w == 0) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) aw[0][s] = a0[s];
+                norm8(aw[0]);
+            } else {  // checkpoints were stored normalised
+                aw[0][0] = 0;
+#pragma unroll
+                for (int s = 1; s < 8; s++) aw[0][s] = sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t];
+            }
+            const int base = 8 * w * PP + t;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const int idx = (8 * w + k) * P + t;
+                const int idx = base + k * PP;
                 e[k] = IL ? sm.tab[idx] : idx;
                 u[k] = sm.X[e[k]];
                 v[k] = par[idx];
-#pragma unroll
-                for (int s = 0; s < 8; s++) aw[k][s] = a[s];
-                alpha_step(a, u[k], v[k]);
+                if (k < 7) alpha_step_to(aw[k], u[k], v[k], aw[k + 1]);
             }
             if (w == w_sa) {
 #pragma unroll
                 for (int s = 0; s < 8; s++) sa[s] = aw[0][s];
             }
-            if (G == 0 && w == NW - 1) {
-#pragma unroll
-                for (int s = 0; s < 8; s++) sa[s] = a[s];
-            }
+            if (G == 0 && w == NW - 1) alpha_step_to(aw[7], u[7], v[7], sa);  // alpha at the sub-block end
             // ---- beta, extrinsic, in-place update of X
             norm8(b);
+            w32 acc = 0;
 #pragma unroll
             for (int k = 7; k >= 0; k--) {
                 const w32 ex = extrinsic(aw[k], b, v[k]);
-                if (stage) stage[e[k]] = vadd(u[k], ex);  // a-posteriori, :1038 (+ the dropped U)
+                if (want_bits) {
+                    const w32 lam = vadd(u[k], ex);  // a-posteriori, :1038 (+ the dropped U)
+                    acc = (acc >> 1) | (lam & 0x80008000u);
+                    if (stage) stage[e[k]] = lam;
+                }
                 // clamp to [-lim, lim-1], bias to [0, 2lim-1]
                 const w32 y = __viaddmin_s16x2_relu(ex, c.lim, c.limmax);
                 w32 es;
@@ -286,6 +298,16 @@ __device__ __forceinline__ void siso_pass(const PassCfg &c, const Smem &sm, cons
             if (w == w_sb) {
 #pragma unroll
                 for (int s = 0; s < 8; s++) sb[s] = b[s];
+            }
+            if (want_bits) {
+                // acc: sign of step k in bit 15-k (A) / 31-k (B).  Two windows share one word.
+                if (w & 1) hold = acc;
+                else {
+                    const w32 word = (acc >> 8) | hold;
+                    changed |= word ^ sm.dec[(w >> 1) * P + t];
+                    sm.dec[(w >> 1) * P + t] = word;
+                    hold = 0;
+                }
             }
         }
         norm8(sa);
@@ -308,14 +330,26 @@ __device__ __forceinline__ void siso_pass(const PassCfg &c, const Smem &sm, cons
         if (!first_fixed) na[s] = up[s];
         if (!last_fixed) nb[s] = dn[s];
     }
+    return changed;
 }
 
-__global__ void __launch_bounds__(256) fast_s16_kernel(FastArgs A)
+template <int LLR_T, int KP, int KNW, int KG>
+__global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) fast_s16_kernel(FastArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FastGeom &g = A.g;
-    const int K = g.K, L = g.L, P = g.P;
-    const Smem sm = carve(smem_raw, K, P, g.n_ckpt);
+    const int P = KP ? KP : g.P, PP = KP ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW;
+    const int L = 8 * NW, K = P * L;
+    const int W = L * PP;  // words per array
+    Smem sm;
+    sm.X = reinterpret_cast<w32 *>(smem_raw);
+    sm.par1 = sm.X + W;
+    sm.par2 = sm.par1 + W;
+    sm.sys8 = reinterpret_cast<uint16_t *>(sm.par2 + W);
+    sm.tab = sm.sys8 + W + (W & 1);
+    sm.ckpt = reinterpret_cast<w32 *>(sm.tab + W + (W & 1));
+    sm.dec = sm.ckpt + (size_t)g.n_ckpt * 7 * P;
+    sm.edge = sm.dec + (size_t)((NW + 1) / 2) * P;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int cbA = 2 * blockIdx.x;
     const bool hasB = cbA + 1 < A.n_cb;
@@ -324,30 +358,26 @@ __global__ void __launch_bounds__(256) fast_s16_kernel(FastArgs A)
     const float scale = (float)(1 << A.frac_bits);
     const int clip = A.llr_clip;
 
-    // ---- load + quantise + de-multiplex (once per decode)
+    // ---- load + quantise + de-multiplex (once per decode); element n = tt*L + j -> word j*PP + tt
     for (int q = tid; q < K / 4; q += nthr) {
         int va[12], vb[12];
-        load12(A.llr, A.llr_type, row, cbA, q, scale, clip, va);
-        load12(A.llr, A.llr_type, row, cbB, q, scale, clip, vb);
+        load12<LLR_T>(A.llr, row, cbA, q, scale, clip, va);
+        load12<LLR_T>(A.llr, row, cbB, q, scale, clip, vb);
 #pragma unroll
         for (int m = 0; m < 4; m++) {
             const int n = 4 * q + m;
             const int tt = n / L, j = n - tt * L;
-            const int ad = j * P + tt;
+            const int ad = j * PP + tt;
             sm.X[ad] = pack2(va[3 * m], vb[3 * m]);
             sm.sys8[ad] = (uint16_t)((va[3 * m] & 0xff) | ((vb[3 * m] & 0xff) << 8));
             sm.par1[ad] = pack2(va[3 * m + 1], vb[3 * m + 1]);
             sm.par2[ad] = pack2(va[3 * m + 2], vb[3 * m + 2]);
         }
     }
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.tab2);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(sm.tab);
-        for (int i = tid; i < K / 2; i += nthr) dst[i] = __ldg(src + i);
-    }
+    for (int i = tid; i < W; i += nthr) sm.tab[i] = __ldg(A.tab2 + i);
 
     PassCfg c;
-    c.t = tid; c.P = P; c.L = L; c.NW = g.NW; c.G = g.G; c.n_ckpt = g.n_ckpt; c.q2 = A.q2;
+    c.q2 = A.q2;
     c.lim = dup2(A.ext_lim);
     c.limmax = dup2(2 * A.ext_lim - 1);
     c.unbias = dup2(A.q2 == 3 ? -(3 * A.ext_lim / 4) : -A.ext_lim);
@@ -369,8 +399,8 @@ __global__ void __launch_bounds__(256) fast_s16_kernel(FastArgs A)
             for (int j = 0; j < 8; j++) bt[j] = j ? dup2(kFxNeg) : 0u;
             for (int m = 2; m >= 0; m--) {
                 const size_t o = (size_t)3 * K + 6 * s + 2 * m;
-                const w32 u = pack2(load1(A.llr, A.llr_type, cbA * row + o, scale, clip), load1(A.llr, A.llr_type, cbB * row + o, scale, clip));
-                const w32 v = pack2(load1(A.llr, A.llr_type, cbA * row + o + 1, scale, clip), load1(A.llr, A.llr_type, cbB * row + o + 1, scale, clip));
+                const w32 u = pack2(load1<LLR_T>(A.llr, cbA * row + o, scale, clip), load1<LLR_T>(A.llr, cbB * row + o, scale, clip));
+                const w32 v = pack2(load1<LLR_T>(A.llr, cbA * row + o + 1, scale, clip), load1<LLR_T>(A.llr, cbB * row + o + 1, scale, clip));
                 beta_step(bt, u, v);
             }
             norm8(bt);
@@ -381,33 +411,60 @@ __global__ void __launch_bounds__(256) fast_s16_kernel(FastArgs A)
     __syncthreads();
 
     const bool want_soft = (A.llr2 != nullptr);
+    int used = A.n_iter, usedA = 0, usedB = 0;
     for (int it = 0; it < A.n_iter; it++) {
         const bool last = (it == A.n_iter - 1);
-        siso_pass<false>(c, sm, sm.par1, na[0], nb[0], first_fixed, last_fixed, nullptr);
-        // the last SISO-2 pass parks the a-posteriori values in the (now dead) parity-1 array
-        siso_pass<true>(c, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed, last ? sm.par1 : nullptr);
-    }
-
-    // ---- hard decisions, natural order (decision() :862-879 + random_deinterlvr_int :1264 are
-    //      the sign bit of the parked value at the bit's own word)
-    if (A.bits) {
-        for (int q = tid; q < K / 4; q += nthr) {
-            uint32_t ba = 0, bb = 0;
-#pragma unroll
-            for (int m = 0; m < 4; m++) {
-                const int n = 4 * q + m;
-                const int tt = n / L, j = n - tt * L;
-                const w32 lam = sm.par1[j * P + tt];
-                ba |= ((lam & 0x8000u) ? 0u : 1u) << (8 * m);
-                bb |= ((lam & 0x80000000u) ? 0u : 1u) << (8 * m);
+        siso_pass<false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], first_fixed, last_fixed, false, nullptr);
+        // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
+        // (by then dead) parity-1 array
+        const w32 chg = siso_pass<true, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed,
+                                                     A.early_term || last, (want_soft && (last || A.early_term)) ? sm.par1 : nullptr);
+        if (A.early_term) {
+            // hard-decision-aided stop: no decision of an iteration differs from the previous one
+            const int chA = __syncthreads_or((int)(chg & 0xffffu));
+            const int chB = __syncthreads_or((int)(chg >> 16));
+            if (it >= 1) {
+                if (!chA && !usedA) usedA = it + 1;
+                if (!chB && !usedB) usedB = it + 1;
+                if (usedA && usedB) { used = it + 1; break; }
             }
-            reinterpret_cast<uint32_t *>(A.bits + (size_t)cbA * K)[q] = ba;
-            if (hasB) reinterpret_cast<uint32_t *>(A.bits + (size_t)cbB * K)[q] = bb;
+        }
+    }
+    if (!usedA) usedA = used;
+    if (!usedB) usedB = used;
+
+    // ---- hard decisions, natural order: decision() :862-879 is the sign bit kept in sm.dec,
+    //      random_deinterlvr_int :1264 is the scatter of those bits to byte n = pi(i) of a staging
+    //      array (the dead parity-2 region), which then leaves with coalesced 32-bit stores
+    if (A.bits) {
+        uint8_t *byA = reinterpret_cast<uint8_t *>(sm.par2), *byB = byA + K;
+        if (tid < P) {
+            for (int w2 = 0; w2 < (NW + 1) / 2; w2++) {
+                const w32 word = sm.dec[w2 * P + tid];
+#pragma unroll
+                for (int kk = 0; kk < 16; kk++) {
+                    const int j = 16 * w2 + (kk & 8) + 7 - (kk & 7);  // step k of a window sits in bit 7-k of its byte
+                    if (j < L) {
+                        const int e = sm.tab[j * PP + tid];
+                        const int jj = e / PP, tt = e - jj * PP;
+                        const int n = tt * L + jj;
+                        byA[n] = (uint8_t)(((word >> kk) & 1u) ^ 1u);
+                        byB[n] = (uint8_t)(((word >> (16 + kk)) & 1u) ^ 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t *wa = reinterpret_cast<const uint32_t *>(byA), *wb = reinterpret_cast<const uint32_t *>(byB);
+        uint32_t *oa = reinterpret_cast<uint32_t *>(A.bits + (size_t)cbA * K), *ob = reinterpret_cast<uint32_t *>(A.bits + (size_t)cbB * K);
+        for (int q = tid; q < K / 4; q += nthr) {
+            oa[q] = wa[q];
+            if (hasB) ob[q] = wb[q];
         }
     }
     if (A.iters_used && tid == 0) {
-        A.iters_used[cbA] = A.n_iter;
-        if (hasB) A.iters_used[cbB] = A.n_iter;
+        A.iters_used[cbA] = usedA;
+        if (hasB) A.iters_used[cbB] = usedB;
     }
     if (want_soft || A.ext2) {
         const float inv = 1.0f / scale;
@@ -416,7 +473,7 @@ __global__ void __launch_bounds__(256) fast_s16_kernel(FastArgs A)
             float la = 0.f, lb = 0.f, ea = 0.f, eb = 0.f;
             if (i < K) {
                 const int tt = i / L, j = i - tt * L;
-                const int e = sm.tab[j * P + tt];
+                const int e = sm.tab[j * PP + tt];
                 const w32 lam = sm.par1[e];
                 const w32 ex = vadd(sm.X[e], vneg(sext8x2(sm.sys8[e])));
                 la = (float)(int16_t)(lam & 0xffff) * inv; lb = (float)(int16_t)(lam >> 16) * inv;
@@ -428,23 +485,41 @@ __global__ void __launch_bounds__(256) fast_s16_kernel(FastArgs A)
     }
 }
 
+typedef void (*kernel_fn)(FastArgs);
+
+// The specialised instance exists for the BASELINE geometry only (K=6144: P=128, NW=6, G=16).
+kernel_fn pick_kernel(const FastGeom &g, int llr_type)
+{
+    const bool spec = (g.P == 128 && g.NW == 6 && g.G == 16 && g.PP == 129);
+    switch (llr_type) {
+        case TDB200_LLR_F32: return spec ? fast_s16_kernel<TDB200_LLR_F32, 128, 6, 16> : fast_s16_kernel<TDB200_LLR_F32, 0, 0, 0>;
+        case TDB200_LLR_F64: return spec ? fast_s16_kernel<TDB200_LLR_F64, 128, 6, 16> : fast_s16_kernel<TDB200_LLR_F64, 0, 0, 0>;
+        default: return spec ? fast_s16_kernel<TDB200_LLR_S8, 128, 6, 16> : fast_s16_kernel<TDB200_LLR_S8, 0, 0, 0>;
+    }
+}
+
 }  // namespace
 
 int fast_s16_smem_bytes(const FastGeom &g)
 {
     const int nwarps = g.threads / 32;
-    return 3 * 4 * g.K + 2 * 2 * g.K + 4 * g.n_ckpt * 7 * g.P + 4 * 16 * nwarps;
+    const int W = g.L * g.PP, W2 = W + (W & 1);
+    return 3 * 4 * W + 2 * 2 * W2 + 4 * g.n_ckpt * 7 * g.P + 4 * ((g.NW + 1) / 2) * g.P + 4 * 16 * nwarps;
 }
 
 cudaError_t fast_s16_configure(const FastGeom &g)
 {
-    return cudaFuncSetAttribute(fast_s16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
+    for (int t = TDB200_LLR_F64; t <= TDB200_LLR_S8; t++) {
+        cudaError_t e = cudaFuncSetAttribute(pick_kernel(g, t), cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches)
 {
     const int pairs = (a.n_cb + 1) / 2;
-    fast_s16_kernel<<<pairs, a.g.threads, a.g.smem_bytes, st>>>(a);
+    pick_kernel(a.g, a.llr_type)<<<pairs, a.g.threads, a.g.smem_bytes, st>>>(a);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

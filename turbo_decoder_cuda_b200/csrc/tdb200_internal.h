@@ -82,6 +82,7 @@ constexpr int kFxNeg = -14000;  // metric of an impossible state (range analysis
 
 struct FastGeom {
     int K, L, P, NW, G;
+    int PP;          // row pitch of the step-major arrays in words (P | 1)
     int threads;     // CTA size: P rounded up to a warp multiple
     int n_ckpt;      // alpha checkpoints kept in shared memory per thread: max(NW-2, 0)
     int smem_bytes;
