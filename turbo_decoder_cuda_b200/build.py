@@ -84,8 +84,9 @@ def build(force=False, verbose=False):
             raise RuntimeError("compat build failed:\n%s\n%s" % (r.stdout, r.stderr))
     if verbose:
         sys.stderr.write("".join(log))
-    with open(os.path.join(LIB, "ptxas.log"), "a") as f:
-        f.write("".join(log))
+    if any(log):
+        with open(os.path.join(LIB, "ptxas.log"), "w") as f:
+            f.write("".join(log))
     return so
 
 

@@ -356,6 +356,8 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
     const size_t fsz = f64 ? sizeof(double) : sizeof(float);  // native float type of the LLR outputs
     if (!f64 && (out->bits_iters || out->llr_siso1))
         return fail(TDB200_ERR_UNSUPPORTED, "bits_iters / llr_siso1 are produced by TDB200_ALGO_LOGMAP_F64 only");
+    if (!f64 && c.early_term && out->llr_siso2)
+        return fail(TDB200_ERR_UNSUPPORTED, "llr_siso2 is not available with early termination (the stopping iteration is not known in advance)");
 
     if (host) {
         int s = ensure(d->d_in, d->d_in_bytes, (size_t)chunk * NL * esz);

@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
         // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
         // (by then dead) parity-1 array
         const w32 chg = siso_pass<true, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed,
-                                                     A.early_term || last, (want_soft && (last || A.early_term)) ? sm.par1 : nullptr);
+                                                     A.early_term || last, (want_soft && last) ? sm.par1 : nullptr);
         if (A.early_term) {
             // hard-decision-aided stop: no decision of an iteration differs from the previous one
             const int chA = __syncthreads_or((int)(chg & 0xffffu));
