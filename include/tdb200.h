@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TDB200_VERSION 1
+#define TDB200_VERSION 2
 
 typedef enum tdb200_status {
     TDB200_OK = 0,
@@ -82,6 +82,8 @@ typedef struct tdb200_config {
                          0 = default (3 for max-log, 4 for Log-MAP) */
     int frac_bits;  /* fixed-point fractional bits of TDB200_ALGO_MAXLOG_S16 and of
                        TDB200_LLR_S8 input; 0 = default (3) */
+    int ext_clip;   /* TDB200_ALGO_MAXLOG_S16: extrinsic values are clamped to [-(ext_clip+1), ext_clip]
+                       (fixed-point units); ext_clip+1 must be a multiple of 4.  0 = default */
     int device;     /* CUDA device ordinal */
     int max_batch;  /* codeblocks the workspace is sized for per launch; larger batches are
                        processed in chunks.  0 = default for the algo */

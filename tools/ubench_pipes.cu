@@ -19,16 +19,19 @@ enum Op {
     OP_VIADD16, OP_VIMNMX16, OP_VIMNMX3_16, OP_VIADDMNMX16, OP_VIADDMNMX32, OP_HADD2, OP_HMNMX2, OP_HFMA2,
     OP_MIX_VIADDMNMX16_HADD2, OP_MIX_VIADDMNMX16_IMAD, OP_MIX_VIADD16_VIMNMX16, OP_MIX_FADD_FMNMX,
     OP_MIX_VIADDMNMX16_VIADD16, OP_MIX_VIMNMX16_IMAD, OP_MIX_VIADDMNMX16_LOP3, OP_MIX_HADD2_HMNMX2,
+    OP_IMADHI, OP_IMADWIDE, OP_MIX_VIADDMNMX16_IMADHI, OP_MIX_VIADDMNMX16_IADD3, OP_MIX_VIADD16_IMAD, OP_MIX_VIADD16_HADD2, OP_MIX_VIADD16_FADD,
     OP_COUNT
 };
 static const char *op_name[OP_COUNT] = {
     "FADD", "FMNMX", "FFMA", "FMNMX3", "IADD3", "IMNMX(s32)", "IMAD", "LOP3", "PRMT", "SHF",
     "VIADD.16x2", "VIMNMX.S16x2", "VIMNMX3.S16x2", "VIADDMNMX.S16x2", "VIADDMNMX(s32)", "HADD2", "HMNMX2", "HFMA2",
     "mix VIADDMNMX.S16x2+HADD2", "mix VIADDMNMX.S16x2+IMAD", "mix VIADD.16x2+VIMNMX.S16x2", "mix FADD+FMNMX",
-    "mix VIADDMNMX.S16x2+VIADD.16x2", "mix VIMNMX.S16x2+IMAD", "mix VIADDMNMX.S16x2+LOP3", "mix HADD2+HMNMX2"};
+    "mix VIADDMNMX.S16x2+VIADD.16x2", "mix VIMNMX.S16x2+IMAD", "mix VIADDMNMX.S16x2+LOP3", "mix HADD2+HMNMX2",
+    "IMAD.HI.U32", "IMAD.WIDE.U32", "mix VIADDMNMX.S16x2+IMAD.HI", "mix VIADDMNMX.S16x2+IADD3", "mix VIADD.16x2+IMAD", "mix VIADD.16x2+HADD2", "mix VIADD.16x2+FADD"};
 // thread-ops counted per step() call
 static const int op_per_step[OP_COUNT] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
-                                          2, 2, 2, 2, 2, 2, 2, 2};
+                                          2, 2, 2, 2, 2, 2, 2, 2,
+                                          1, 1, 2, 2, 2, 2, 2};
 
 __device__ __forceinline__ unsigned h2u(__half2 h) { return *reinterpret_cast<unsigned *>(&h); }
 __device__ __forceinline__ __half2 u2h(unsigned u) { return *reinterpret_cast<__half2 *>(&u); }
@@ -62,6 +65,13 @@ __device__ __forceinline__ void step(unsigned &x, unsigned &w, unsigned y, unsig
     if (OP == OP_MIX_VIADDMNMX16_VIADD16) { x = __viaddmax_s16x2(x, y, z); w = __vadd2(w, y); }
     if (OP == OP_MIX_VIMNMX16_IMAD) { x = __vmaxs2(x, y); x = __vmins2(x, z); asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(w) : "r"(y), "r"(z)); asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(w) : "r"(z), "r"(y)); }
     if (OP == OP_MIX_VIADDMNMX16_LOP3) { x = __viaddmax_s16x2(x, y, z); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(w) : "r"(y), "r"(z)); }
+    if (OP == OP_IMADHI) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z));
+    if (OP == OP_IMADWIDE) { unsigned long long r; asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(x), "r"(y), "l"((unsigned long long)z << 30)); x = (unsigned)(r >> 32); }
+    if (OP == OP_MIX_VIADDMNMX16_IMADHI) { x = __viaddmax_s16x2(x, y, z); asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(w) : "r"(y), "r"(z)); }
+    if (OP == OP_MIX_VIADDMNMX16_IADD3) { x = __viaddmax_s16x2(x, y, z); asm volatile("add.s32 %0, %0, %1;" : "+r"(w) : "r"(y)); asm volatile("add.s32 %0, %0, %1;" : "+r"(w) : "r"(z)); }
+    if (OP == OP_MIX_VIADD16_IMAD) { x = __vadd2(x, y); asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(w) : "r"(y), "r"(z)); }
+    if (OP == OP_MIX_VIADD16_HADD2) { x = __vadd2(x, y); w = h2u(__hadd2(u2h(w), u2h(y))); }
+    if (OP == OP_MIX_VIADD16_FADD) { x = __vadd2(x, y); w = __float_as_uint(__uint_as_float(w) + __uint_as_float(y)); }
     if (OP == OP_MIX_HADD2_HMNMX2) { x = h2u(__hadd2(u2h(x), u2h(y))); w = h2u(__hmax2(u2h(w), u2h(x))); }
 }
 

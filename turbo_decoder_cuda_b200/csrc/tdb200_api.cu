@@ -263,6 +263,9 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         if (c.frac_bits < 1 || c.frac_bits > 4) return fail(TDB200_ERR_INVALID_ARG, "frac_bits=%d out of range [1,4]", c.frac_bits);
         if (c.ext_scale_q2 == 0) c.ext_scale_q2 = 3;
         if (c.ext_scale_q2 != 3 && c.ext_scale_q2 != 4) return fail(TDB200_ERR_INVALID_ARG, "ext_scale_q2=%d (3 or 4)", c.ext_scale_q2);
+        if (c.ext_clip == 0) c.ext_clip = (1 << (c.frac_bits + 7)) - 1;
+        if (c.ext_clip < 63 || c.ext_clip > 2047 || ((c.ext_clip + 1) & 3))
+            return fail(TDB200_ERR_INVALID_ARG, "ext_clip=%d: need 63 <= ext_clip <= 2047 and ext_clip+1 a multiple of 4", c.ext_clip);
         // ---- sub-block geometry: K = P * L, L = 8 * NW, P <= 256 threads
         FastGeom &g = d->geom;
         int L = c.sub_block;
@@ -288,12 +291,12 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         if ((size_t)g.smem_bytes > prop.sharedMemPerBlockOptin)
             return fail(TDB200_ERR_UNSUPPORTED, "plan needs %d B of shared memory per CTA, device allows %zu", g.smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
         c.sub_block = L; c.warmup = g.G;
-        TDB_CUDA(fast_s16_configure(g));
+        TDB_CUDA(fast_s16_configure(g, d->sm_count));
         // word address of element pi(tL+j), stored at j*PP+t
         std::vector<uint16_t> tab((size_t)L * g.PP, 0);
         for (int i = 0; i < K; i++) {
             const int t = i / L, j = i % L, n = d->h_pi[i];
-            tab[j * g.PP + t] = (uint16_t)((n % L) * g.PP + n / L);
+            tab[j * g.PP + t] = (uint16_t)(4 * ((n % L) * g.PP + n / L));
         }
         TDB_CUDA(cudaMalloc(&d->d_tab2, sizeof(uint16_t) * tab.size()));
         TDB_CUDA(cudaMemcpy(d->d_tab2, tab.data(), sizeof(uint16_t) * tab.size(), cudaMemcpyHostToDevice));
@@ -409,9 +412,11 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
             a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.g = d->geom; a.n_iter = c.n_iter;
             a.frac_bits = c.frac_bits;
             a.llr_clip = std::min((1 << (c.frac_bits + 4)) - 1, 127);  // systematic values are kept as int8 pairs in shared memory
-            a.ext_lim = 1 << (c.frac_bits + 7);
+            a.ext_lim = c.ext_clip + 1;
             a.q2 = c.ext_scale_q2; a.early_term = c.early_term;
             a.tab2 = d->d_tab2;
+            a.neg1 = 0xffffffffu;
+            a.prefetch_stride = d->geom.resident_ctas;
             a.bits = v_bits; a.iters_used = v_iters;
             a.llr2 = reinterpret_cast<float *>(v_llr2); a.ext2 = reinterpret_cast<float *>(v_ext2);
             TDB_CUDA(launch_fast_s16(a, st, &d->launches_last));

@@ -84,19 +84,6 @@ __device__ __forceinline__ void beta_step(w32 (&b)[8], w32 u, w32 v)
     b[0] = o0; b[1] = o1; b[2] = o2; b[3] = o3; b[4] = o4; b[5] = o5; b[6] = o6; b[7] = o7;
 }
 
-// e = max_{input 1}(alpha + c*V + beta') - max_{input 0}(alpha + c*V + beta')   (:1024-1039 as
-// max-log; the +U common to all input-1 branches is left out, so e IS the extrinsic :1234-1238)
-__device__ __forceinline__ w32 extrinsic(const w32 (&a)[8], const w32 (&b)[8], w32 v)
-{
-    w32 m0a = vadd(a[0], b[0]); m0a = vaddmax(a[1], b[4], m0a); m0a = vaddmax(a[6], b[7], m0a); m0a = vaddmax(a[7], b[3], m0a);
-    w32 m0b = vadd(a[2], b[5]); m0b = vaddmax(a[3], b[1], m0b); m0b = vaddmax(a[4], b[2], m0b); m0b = vaddmax(a[5], b[6], m0b);
-    w32 m1a = vadd(a[0], b[4]); m1a = vaddmax(a[1], b[0], m1a); m1a = vaddmax(a[6], b[3], m1a); m1a = vaddmax(a[7], b[7], m1a);
-    w32 m1b = vadd(a[2], b[1]); m1b = vaddmax(a[3], b[5], m1b); m1b = vaddmax(a[4], b[6], m1b); m1b = vaddmax(a[5], b[2], m1b);
-    const w32 m0 = vaddmax(m0b, v, m0a);
-    const w32 m1 = vaddmax(m1a, v, m1b);
-    return vadd(m1, vneg(m0));
-}
-
 // ---- channel-LLR load + quantisation (q = clamp(rint(x * 2^F), +-clip), oracle: quant())
 __device__ __forceinline__ int quant(float x, float scale, int clip)
 {
@@ -169,25 +156,105 @@ __device__ __forceinline__ w32 sext8x2(unsigned v)
 
 struct PassCfg {
     int q2;
-    w32 lim;     // dup2(ext_lim)
+    w32 lim1;    // dup2(ext_lim + 1): the +1 completes m1 + ~m0 = m1 - m0 - 1
     w32 limmax;  // dup2(2*ext_lim - 1)
     w32 unbias;  // dup2(-(3*ext_lim/4)) or dup2(-ext_lim)
+    w32 neg1;    // 0xffffffff, opaque to the compiler
 };
+
+// ~x on the fma-heavy pipe (x * -1 + -1); LOP3 would take an ALU-pipe slot, and that pipe is the
+// one the add-compare-select instructions saturate.  neg1 = 0xffffffff comes in as a kernel argument:
+// with a literal ptxas turns the product back into an ALU-pipe IADD3.
+__device__ __forceinline__ w32 vnot_fma(w32 x, w32 neg1) { return x * neg1 + neg1; }
+
+// e - 1, where e = max_{input 1}(alpha + c*V + beta') - max_{input 0}(alpha + c*V + beta')
+// (:1024-1039 as max-log; the +U common to all input-1 branches is left out, so e IS the extrinsic
+// of :1234-1238).  The -1 is absorbed by the clamp constant.
+__device__ __forceinline__ w32 extrinsic_m1(const w32 (&a)[8], const w32 (&b)[8], w32 v, w32 neg1)
+{
+    w32 m0a = vadd(a[0], b[0]); m0a = vaddmax(a[1], b[4], m0a); m0a = vaddmax(a[6], b[7], m0a); m0a = vaddmax(a[7], b[3], m0a);
+    w32 m0b = vadd(a[2], b[5]); m0b = vaddmax(a[3], b[1], m0b); m0b = vaddmax(a[4], b[2], m0b); m0b = vaddmax(a[5], b[6], m0b);
+    w32 m1a = vadd(a[0], b[4]); m1a = vaddmax(a[1], b[0], m1a); m1a = vaddmax(a[6], b[3], m1a); m1a = vaddmax(a[7], b[7], m1a);
+    w32 m1b = vadd(a[2], b[1]); m1b = vaddmax(a[3], b[5], m1b); m1b = vaddmax(a[4], b[6], m1b); m1b = vaddmax(a[5], b[2], m1b);
+    const w32 m0 = vaddmax(m0b, v, m0a);
+    const w32 m1 = vaddmax(m1a, v, m1b);
+    return vadd(m1, vnot_fma(m0, neg1));
+}
+
+// Shared-memory accessors.  Interleaved passes go through tab, which holds the BYTE offset 4e of
+// element e inside X (so the X access needs no address arithmetic); sys8 sits at half of it.
+template <bool IL>
+__device__ __forceinline__ unsigned elem_off(const Smem &sm, int idx)
+{
+    return IL ? (unsigned)sm.tab[idx] : 4u * (unsigned)idx;
+}
+__device__ __forceinline__ w32 &word_at(w32 *base, unsigned off4)
+{
+    return *reinterpret_cast<w32 *>(reinterpret_cast<unsigned char *>(base) + off4);
+}
+__device__ __forceinline__ w32 &x_at(const Smem &sm, unsigned off4) { return word_at(sm.X, off4); }
+__device__ __forceinline__ unsigned sys_at(const Smem &sm, unsigned off4)
+{
+    return *reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(sm.sys8) + (off4 >> 1));
+}
+
+// Backward sweep over one 8-step window whose first alpha vector is a0 (normalised): re-create
+// the window's alpha vectors in registers, then run beta, the extrinsic output and the in-place
+// update of X over it.  Returns the decision bits of the window (WANT only): sign of step k in
+// bit 15-k (codeblock A) / 31-k (codeblock B).
+template <bool IL, bool WANT>
+__device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, const w32 *par, const int base, const int PP,
+                                          const w32 (&a0)[8], w32 (&b)[8], w32 *stage)
+{
+    w32 aw[8][8], u[8], v[8];
+    unsigned off[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) aw[0][s] = a0[s];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int idx = base + k * PP;
+        off[k] = elem_off<IL>(sm, idx);
+        u[k] = x_at(sm, off[k]);
+        v[k] = par[idx];
+        if (k < 7) alpha_step_to(aw[k], u[k], v[k], aw[k + 1]);
+    }
+    norm8(b);
+    w32 acc = 0;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+        const w32 exm1 = extrinsic_m1(aw[k], b, v[k], c.neg1);
+        // clamp to [-lim, lim-1], bias to [0, 2lim-1]
+        const w32 y = __viaddmin_s16x2_relu(exm1, c.lim1, c.limmax);
+        w32 es;
+        if (c.q2 == 3) es = ((y * 3u) >> 2) & 0x3fff3fffu;  // floor(3(ec+lim)/4), no cross-lane carry
+        else es = y;
+        const w32 ys = sext8x2(sys_at(sm, off[k]));
+        x_at(sm, off[k]) = vadd(vadd(ys, es), c.unbias);
+        if (WANT) {
+            const w32 lam = vadd(vadd(u[k], exm1), 0x00010001u);  // a-posteriori, :1038 (+ the dropped U)
+            acc = (acc >> 1) | (lam & 0x80008000u);
+            if (stage) word_at(stage, off[k]) = lam;
+        }
+        beta_step(b, u[k], v[k]);
+    }
+    return acc;
+}
 
 // One SISO pass of one sub-block.  IL = false: SISO-1 (natural order), true: SISO-2 (through tab).
 // na/nb: boundary vectors (alpha G steps before the sub-block, beta G steps after it); on return
-// they hold the vectors for the next iteration of this SISO.  With want_bits the hard decisions
-// of this pass go to sm.dec (one word per two windows) and the return value has bits 0-15 / 16-31
-// set where a decision of codeblock A / B differs from what sm.dec held before.
-template <bool IL, int KP, int KNW, int KG>
+// they hold the vectors for the next iteration of this SISO.  With WANT the hard decisions of this
+// pass go to sm.dec (one word per two windows) and the return value has bits 0-15 / 16-31 set
+// where a decision of codeblock A / B differs from what sm.dec held before.
+template <bool IL, bool WANT, int KP, int KNW, int KG>
 __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, const Smem &sm, const w32 *par, w32 (&na)[8], w32 (&nb)[8],
-                                         const bool first_fixed, const bool last_fixed, const bool want_bits, w32 *stage)
+                                         const bool first_fixed, const bool last_fixed, w32 *stage)
 {
     const int P = KP ? KP : g.P, PP = KP ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW, G = KP ? KG : g.G;
     const int L = 8 * NW;
     const int t = threadIdx.x;
-    const bool active = t < P;
+    const bool active = KP ? true : (t < P);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int w_sa = (L - G) >> 3, w_sb = G >> 3;
     w32 a[8], b[8], a0[8], sa[8], sb[8];
     w32 changed = 0;
 #pragma unroll
@@ -202,8 +269,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const int idx = base + k * PP;
-                    const int e = IL ? sm.tab[idx] : idx;
-                    alpha_step(a, sm.X[e], par[idx]);
+                    alpha_step(a, x_at(sm, elem_off<IL>(sm, idx)), par[idx]);
                 }
             }
         // ---- beta warm-up over the first G steps of sub-block t+1
@@ -214,20 +280,21 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
                 for (int k = 7; k >= 0; k--) {
                     const int idx = base + k * PP;
-                    const int e = IL ? sm.tab[idx] : idx;
-                    beta_step(b, sm.X[e], par[idx]);
+                    beta_step(b, x_at(sm, elem_off<IL>(sm, idx)), par[idx]);
                 }
             }
         if (G == L) {
 #pragma unroll
             for (int s = 0; s < 8; s++) sb[s] = b[s];
         }
+        norm8(a);
 #pragma unroll
         for (int s = 0; s < 8; s++) a0[s] = a[s];
-        // ---- forward sweep over windows 0..NW-2, leaving a checkpoint at the start of windows 1..NW-2
+        // ---- forward sweep over windows 0..NW-2, leaving a (normalised) checkpoint at the start of
+        //      windows 1..NW-2; the start of window NW-1 stays in registers
         for (int w = 0; w < NW - 1; w++) {
-            norm8(a);
             if (w > 0) {
+                norm8(a);
 #pragma unroll
                 for (int s = 1; s < 8; s++) sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t] = a[s];
             }
@@ -235,72 +302,67 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int idx = base + k * PP;
-                const int e = IL ? sm.tab[idx] : idx;
-                alpha_step(a, sm.X[e], par[idx]);
+                alpha_step(a, x_at(sm, elem_off<IL>(sm, idx)), par[idx]);
             }
         }
+        if (NW > 1) norm8(a);
     }
     __syncthreads();  // every warm-up read of X precedes every in-place update below
     if (active) {
-        const int w_sa = (L - G) >> 3, w_sb = G >> 3;
-        w32 hold = 0;  // decision bits of the odd window waiting for its even partner
-        for (int w = NW - 1; w >= 0; w--) {
-            // ---- re-create the alpha vectors of this window in registers
-            w32 aw[8][8], u[8], v[8];
-            int e[8];
-            if (w == NW - 1) {
+        // alpha at local step L-G, for the right-hand neighbour's next iteration: the start vector
+        // of window w_sa -- live in registers for the first and last window, a checkpoint otherwise
+        if (G > 0) {
+            if (w_sa == NW - 1) {
 #pragma unroll
-                for (int s = 0; s < 8; s++) aw[0][s] = a[s];
-                norm8(aw[0]);
-            } else if (w == 0) {
+                for (int s = 0; s < 8; s++) sa[s] = a[s];
+            } else if (w_sa == 0) {
 #pragma unroll
-                for (int s = 0; s < 8; s++) aw[0][s] = a0[s];
-                norm8(aw[0]);
-            } else {  // checkpoints were stored normalised
-                aw[0][0] = 0;
-#pragma unroll
-                for (int s = 1; s < 8; s++) aw[0][s] = sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t];
+                for (int s = 0; s < 8; s++) sa[s] = a0[s];
             }
-            const int base = 8 * w * PP + t;
+        }
+        w32 hold = 0;  // decision bits of an odd window waiting for its even partner
+        // ---- last window: alpha from the forward sweep's registers
+        {
+            const int w = NW - 1;
+            if (G == 0) {  // alpha at the sub-block end
+                w32 tmp[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int idx = base + k * PP;
-                e[k] = IL ? sm.tab[idx] : idx;
-                u[k] = sm.X[e[k]];
-                v[k] = par[idx];
-                if (k < 7) alpha_step_to(aw[k], u[k], v[k], aw[k + 1]);
-            }
-            if (w == w_sa) {
+                for (int s = 0; s < 8; s++) tmp[s] = a[s];
+                const int base = 8 * w * PP + t;
 #pragma unroll
-                for (int s = 0; s < 8; s++) sa[s] = aw[0][s];
-            }
-            if (G == 0 && w == NW - 1) alpha_step_to(aw[7], u[7], v[7], sa);  // alpha at the sub-block end
-            // ---- beta, extrinsic, in-place update of X
-            norm8(b);
-            w32 acc = 0;
-#pragma unroll
-            for (int k = 7; k >= 0; k--) {
-                const w32 ex = extrinsic(aw[k], b, v[k]);
-                if (want_bits) {
-                    const w32 lam = vadd(u[k], ex);  // a-posteriori, :1038 (+ the dropped U)
-                    acc = (acc >> 1) | (lam & 0x80008000u);
-                    if (stage) stage[e[k]] = lam;
+                for (int k = 0; k < 8; k++) {
+                    const int idx = base + k * PP;
+                    alpha_step(tmp, x_at(sm, elem_off<IL>(sm, idx)), par[idx]);
                 }
-                // clamp to [-lim, lim-1], bias to [0, 2lim-1]
-                const w32 y = __viaddmin_s16x2_relu(ex, c.lim, c.limmax);
-                w32 es;
-                if (c.q2 == 3) es = ((y * 3u) >> 2) & 0x3fff3fffu;  // floor(3(ec+lim)/4), no cross-lane carry
-                else es = y;
-                const w32 ys = sext8x2(sm.sys8[e[k]]);
-                sm.X[e[k]] = vadd(vadd(ys, es), c.unbias);
-                beta_step(b, u[k], v[k]);
+#pragma unroll
+                for (int s = 0; s < 8; s++) sa[s] = tmp[s];
             }
+            const w32 acc = bwd_window<IL, WANT>(c, sm, par, 8 * w * PP + t, PP, a, b, stage);
             if (w == w_sb) {
 #pragma unroll
                 for (int s = 0; s < 8; s++) sb[s] = b[s];
             }
-            if (want_bits) {
-                // acc: sign of step k in bit 15-k (A) / 31-k (B).  Two windows share one word.
+            if (WANT) {
+                if (w & 1) hold = acc;
+                else {
+                    const w32 word = acc >> 8;
+                    changed |= word ^ sm.dec[(w >> 1) * P + t];
+                    sm.dec[(w >> 1) * P + t] = word;
+                }
+            }
+        }
+        // ---- middle windows: alpha from the checkpoints
+        for (int w = NW - 2; w >= 1; w--) {
+            w32 aw0[8];
+            aw0[0] = 0;
+#pragma unroll
+            for (int s = 1; s < 8; s++) aw0[s] = sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t];
+            const w32 acc = bwd_window<IL, WANT>(c, sm, par, 8 * w * PP + t, PP, aw0, b, stage);
+            if (w == w_sb) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) sb[s] = b[s];
+            }
+            if (WANT) {
                 if (w & 1) hold = acc;
                 else {
                     const w32 word = (acc >> 8) | hold;
@@ -310,27 +372,72 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
                 }
             }
         }
+        // ---- first window: alpha from the saved start vector
+        if (NW > 1) {
+            const w32 acc = bwd_window<IL, WANT>(c, sm, par, t, PP, a0, b, stage);
+            if (w_sb == 0) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) sb[s] = b[s];
+            }
+            if (WANT) {
+                const w32 word = (acc >> 8) | hold;
+                changed |= word ^ sm.dec[t];
+                sm.dec[t] = word;
+            }
+        }
+        if (G > 0 && w_sa > 0 && w_sa < NW - 1) {
+#pragma unroll
+            for (int s = 1; s < 8; s++) sa[s] = sm.ckpt[((w_sa - 1) * 7 + (s - 1)) * P + t];
+        }
         norm8(sa);
         norm8(sb);
     }
-    // ---- hand the boundary vectors to the neighbours (they use them in the next iteration)
+    // ---- hand the boundary vectors to the neighbours (they use them in the next iteration):
+    //      warp shuffles inside a warp, one shared-memory word per state across warp edges
     w32 up[8], dn[8];
 #pragma unroll
     for (int s = 0; s < 8; s++) {
         up[s] = __shfl_up_sync(0xffffffffu, sa[s], 1);
         dn[s] = __shfl_down_sync(0xffffffffu, sb[s], 1);
-        if (lane == 31) sm.edge[s * nwarps + warp] = sa[s];
-        if (lane == 0) sm.edge[(8 + s) * nwarps + warp] = sb[s];
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) sm.edge[s * nwarps + warp] = sa[s];
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) sm.edge[(8 + s) * nwarps + warp] = sb[s];
     }
     __syncthreads();  // also orders this pass's X updates before the next pass's reads
+    if (lane == 0 && warp > 0) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) up[s] = sm.edge[s * nwarps + warp - 1];
+    }
+    if (lane == 31 && warp + 1 < nwarps) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) dn[s] = sm.edge[(8 + s) * nwarps + warp + 1];
+    }
 #pragma unroll
     for (int s = 0; s < 8; s++) {
-        if (lane == 0 && warp > 0) up[s] = sm.edge[s * nwarps + warp - 1];
-        if (lane == 31 && warp + 1 < nwarps) dn[s] = sm.edge[(8 + s) * nwarps + warp + 1];
         if (!first_fixed) na[s] = up[s];
         if (!last_fixed) nb[s] = dn[s];
     }
     return changed;
+}
+
+// ---- de-multiplex + quantise one group of four trellis steps of both codeblocks into shared memory
+__device__ __forceinline__ void put4(const Smem &sm, int q, int L, int PP, const int (&va)[12], const int (&vb)[12])
+{
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int n = 4 * q + m;
+        const int tt = n / L, j = n - tt * L;
+        const int ad = j * PP + tt;
+        sm.X[ad] = pack2(va[3 * m], vb[3 * m]);
+        sm.sys8[ad] = (uint16_t)((va[3 * m] & 0xff) | ((vb[3 * m] & 0xff) << 8));
+        sm.par1[ad] = pack2(va[3 * m + 1], vb[3 * m + 1]);
+        sm.par2[ad] = pack2(va[3 * m + 2], vb[3 * m + 2]);
+    }
 }
 
 template <int LLR_T, int KP, int KNW, int KG>
@@ -358,29 +465,46 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     const float scale = (float)(1 << A.frac_bits);
     const int clip = A.llr_clip;
 
-    // ---- load + quantise + de-multiplex (once per decode); element n = tt*L + j -> word j*PP + tt
-    for (int q = tid; q < K / 4; q += nthr) {
-        int va[12], vb[12];
-        load12<LLR_T>(A.llr, row, cbA, q, scale, clip, va);
-        load12<LLR_T>(A.llr, row, cbB, q, scale, clip, vb);
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-            const int n = 4 * q + m;
-            const int tt = n / L, j = n - tt * L;
-            const int ad = j * PP + tt;
-            sm.X[ad] = pack2(va[3 * m], vb[3 * m]);
-            sm.sys8[ad] = (uint16_t)((va[3 * m] & 0xff) | ((vb[3 * m] & 0xff) << 8));
-            sm.par1[ad] = pack2(va[3 * m + 1], vb[3 * m + 1]);
-            sm.par2[ad] = pack2(va[3 * m + 2], vb[3 * m + 2]);
+    // ---- load + quantise + de-multiplex (once per decode); element n = tt*L + j -> word j*PP + tt.
+    //      Two groups of loads are in flight per thread before the first is consumed.
+    {
+        const int nq = K / 4;
+        int q = tid;
+        for (; q + nthr < nq; q += 2 * nthr) {
+            int va0[12], vb0[12], va1[12], vb1[12];
+            load12<LLR_T>(A.llr, row, cbA, q, scale, clip, va0);
+            load12<LLR_T>(A.llr, row, cbB, q, scale, clip, vb0);
+            load12<LLR_T>(A.llr, row, cbA, q + nthr, scale, clip, va1);
+            load12<LLR_T>(A.llr, row, cbB, q + nthr, scale, clip, vb1);
+            put4(sm, q, L, PP, va0, vb0);
+            put4(sm, q + nthr, L, PP, va1, vb1);
+        }
+        if (q < nq) {
+            int va[12], vb[12];
+            load12<LLR_T>(A.llr, row, cbA, q, scale, clip, va);
+            load12<LLR_T>(A.llr, row, cbB, q, scale, clip, vb);
+            put4(sm, q, L, PP, va, vb);
         }
     }
     for (int i = tid; i < W; i += nthr) sm.tab[i] = __ldg(A.tab2 + i);
+    // ---- pull the rows of the codeblock pair that will run on this SM slot next into L2
+    if (A.prefetch_stride > 0) {
+        const long long nxt = (long long)2 * (blockIdx.x + A.prefetch_stride);
+        if (nxt < A.n_cb) {
+            const size_t esz = LLR_T == TDB200_LLR_F64 ? 8 : (LLR_T == TDB200_LLR_F32 ? 4 : 1);
+            const char *p = static_cast<const char *>(A.llr) + (size_t)nxt * row * esz;
+            const size_t nbytes = (nxt + 1 < A.n_cb ? 2 : 1) * row * esz;
+            for (size_t o = (size_t)tid * 128; o < nbytes; o += (size_t)nthr * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+        }
+    }
 
     PassCfg c;
     c.q2 = A.q2;
-    c.lim = dup2(A.ext_lim);
+    c.lim1 = dup2(A.ext_lim + 1);
     c.limmax = dup2(2 * A.ext_lim - 1);
     c.unbias = dup2(A.q2 == 3 ? -(3 * A.ext_lim / 4) : -A.ext_lim);
+    c.neg1 = A.neg1;
     const bool first_fixed = (tid == 0), last_fixed = (tid == P - 1);
 
     // ---- boundary vectors.  [s][0..7]: s = SISO
@@ -414,20 +538,24 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     int used = A.n_iter, usedA = 0, usedB = 0;
     for (int it = 0; it < A.n_iter; it++) {
         const bool last = (it == A.n_iter - 1);
-        siso_pass<false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], first_fixed, last_fixed, false, nullptr);
-        // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
-        // (by then dead) parity-1 array
-        const w32 chg = siso_pass<true, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed,
-                                                     A.early_term || last, (want_soft && last) ? sm.par1 : nullptr);
-        if (A.early_term) {
-            // hard-decision-aided stop: no decision of an iteration differs from the previous one
-            const int chA = __syncthreads_or((int)(chg & 0xffffu));
-            const int chB = __syncthreads_or((int)(chg >> 16));
-            if (it >= 1) {
-                if (!chA && !usedA) usedA = it + 1;
-                if (!chB && !usedB) usedB = it + 1;
-                if (usedA && usedB) { used = it + 1; break; }
+        siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], first_fixed, last_fixed, nullptr);
+        if (A.early_term || last) {
+            // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
+            // (by then dead) parity-1 array
+            const w32 chg = siso_pass<true, true, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed,
+                                                               (want_soft && last) ? sm.par1 : nullptr);
+            if (A.early_term) {
+                // hard-decision-aided stop: no decision of an iteration differs from the previous one
+                const int chA = __syncthreads_or((int)(chg & 0xffffu));
+                const int chB = __syncthreads_or((int)(chg >> 16));
+                if (it >= 1) {
+                    if (!chA && !usedA) usedA = it + 1;
+                    if (!chB && !usedB) usedB = it + 1;
+                    if (usedA && usedB) { used = it + 1; break; }
+                }
             }
+        } else {
+            siso_pass<true, false, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed, nullptr);
         }
     }
     if (!usedA) usedA = used;
@@ -445,7 +573,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
                 for (int kk = 0; kk < 16; kk++) {
                     const int j = 16 * w2 + (kk & 8) + 7 - (kk & 7);  // step k of a window sits in bit 7-k of its byte
                     if (j < L) {
-                        const int e = sm.tab[j * PP + tid];
+                        const int e = sm.tab[j * PP + tid] >> 2;
                         const int jj = e / PP, tt = e - jj * PP;
                         const int n = tt * L + jj;
                         byA[n] = (uint8_t)(((word >> kk) & 1u) ^ 1u);
@@ -473,7 +601,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
             float la = 0.f, lb = 0.f, ea = 0.f, eb = 0.f;
             if (i < K) {
                 const int tt = i / L, j = i - tt * L;
-                const int e = sm.tab[j * PP + tt];
+                const int e = sm.tab[j * PP + tt] >> 2;
                 const w32 lam = sm.par1[e];
                 const w32 ex = vadd(sm.X[e], vneg(sext8x2(sm.sys8[e])));
                 la = (float)(int16_t)(lam & 0xffff) * inv; lb = (float)(int16_t)(lam >> 16) * inv;
@@ -507,12 +635,22 @@ int fast_s16_smem_bytes(const FastGeom &g)
     return 3 * 4 * W + 2 * 2 * W2 + 4 * g.n_ckpt * 7 * g.P + 4 * ((g.NW + 1) / 2) * g.P + 4 * 16 * nwarps;
 }
 
-cudaError_t fast_s16_configure(const FastGeom &g)
+cudaError_t fast_s16_configure(FastGeom &g, int sm_count)
 {
+    // The attribute belongs to the kernel, not to a decoder handle: several handles with
+    // different geometries share one instantiation, so always opt in to the device maximum.
+    int dev = 0, optin = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e0 != cudaSuccess) return e0;
     for (int t = TDB200_LLR_F64; t <= TDB200_LLR_S8; t++) {
-        cudaError_t e = cudaFuncSetAttribute(pick_kernel(g, t), cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(pick_kernel(g, t), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
         if (e != cudaSuccess) return e;
     }
+    int per_sm = 0;
+    e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(g, TDB200_LLR_F32), g.threads, g.smem_bytes);
+    if (e0 != cudaSuccess) return e0;
+    g.resident_ctas = per_sm * sm_count;
     return cudaSuccess;
 }
 

@@ -86,6 +86,7 @@ struct FastGeom {
     int threads;     // CTA size: P rounded up to a warp multiple
     int n_ckpt;      // alpha checkpoints kept in shared memory per thread: max(NW-2, 0)
     int smem_bytes;
+    int resident_ctas;  // CTAs of this geometry the whole device holds at once
 };
 
 struct FastArgs {
@@ -96,13 +97,15 @@ struct FastArgs {
     int n_iter;
     int frac_bits, llr_clip, ext_lim /* Ce+1, multiple of 4 */, q2;
     int early_term;
-    const uint16_t *tab2;  // [K] device: smem word of element pi(tL+j), stored at index j*P+t
+    uint32_t neg1;  // 0xffffffff (see vnot_fma)
+    const uint16_t *tab2;  // [L*PP] device: 4 * (smem word of element pi(tL+j)), stored at index j*PP+t
+    int prefetch_stride;   // CTAs resident on the device at once (0 = no L2 prefetch of the next pair)
     // outputs (device, nullable)
     uint8_t *bits;
     int32_t *iters_used;
     float *llr2, *ext2;  // [n_cb][K+3]
 };
-cudaError_t fast_s16_configure(const FastGeom &g);  // opt in to the dynamic shared memory size
+cudaError_t fast_s16_configure(FastGeom &g, int sm_count);  // opt in to the dynamic shared memory size
 cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches);
 int fast_s16_smem_bytes(const FastGeom &g);
 
