@@ -261,28 +261,29 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
     for (int s = 0; s < 8; s++) { a[s] = na[s]; b[s] = nb[s]; sa[s] = 0; sb[s] = 0; }
 
     if (active) {
-        // ---- alpha warm-up over the last G steps of sub-block t-1
-        if (!first_fixed)
-            for (int g0 = 0; g0 < G; g0 += 8) {
-                norm8(a);
-                const int base = (L - G + g0) * PP + (t - 1);
+        // ---- warm-up: alpha over the last G steps of sub-block t-1 and beta over the first G steps
+        //      of sub-block t+1, advanced together (two independent dependency chains).  The two
+        //      edge threads run it on their own sub-block and throw the result away, which keeps the
+        //      loop free of divergence.
+        const int ta = first_fixed ? t : t - 1, tb = last_fixed ? t : t + 1;
+#pragma unroll 1
+        for (int g0 = 0; g0 < G; g0 += 8) {
+            const int base_a = (L - G + g0) * PP + ta;
+            const int base_b = (G - 8 - g0) * PP + tb;
+            norm8(a);
+            norm8(b);
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int idx = base + k * PP;
-                    alpha_step(a, x_at(sm, elem_off<IL>(sm, idx)), par[idx]);
-                }
+            for (int k = 0; k < 8; k++) {
+                const int ia = base_a + k * PP, ib = base_b + (7 - k) * PP;
+                alpha_step(a, x_at(sm, elem_off<IL>(sm, ia)), par[ia]);
+                beta_step(b, x_at(sm, elem_off<IL>(sm, ib)), par[ib]);
             }
-        // ---- beta warm-up over the first G steps of sub-block t+1
-        if (!last_fixed)
-            for (int g0 = G - 8; g0 >= 0; g0 -= 8) {
-                norm8(b);
-                const int base = g0 * PP + (t + 1);
+        }
 #pragma unroll
-                for (int k = 7; k >= 0; k--) {
-                    const int idx = base + k * PP;
-                    beta_step(b, x_at(sm, elem_off<IL>(sm, idx)), par[idx]);
-                }
-            }
+        for (int s = 0; s < 8; s++) {
+            if (first_fixed) a[s] = na[s];
+            if (last_fixed) b[s] = nb[s];
+        }
         if (G == L) {
 #pragma unroll
             for (int s = 0; s < 8; s++) sb[s] = b[s];
@@ -292,6 +293,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
         for (int s = 0; s < 8; s++) a0[s] = a[s];
         // ---- forward sweep over windows 0..NW-2, leaving a (normalised) checkpoint at the start of
         //      windows 1..NW-2; the start of window NW-1 stays in registers
+#pragma unroll 1
         for (int w = 0; w < NW - 1; w++) {
             if (w > 0) {
                 norm8(a);
@@ -319,44 +321,37 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
                 for (int s = 0; s < 8; s++) sa[s] = a0[s];
             }
+        } else {  // alpha at the sub-block end
+            w32 tmp[8];
+#pragma unroll
+            for (int s = 0; s < 8; s++) tmp[s] = a[s];
+            const int base = 8 * (NW - 1) * PP + t;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int idx = base + k * PP;
+                alpha_step(tmp, x_at(sm, elem_off<IL>(sm, idx)), par[idx]);
+            }
+#pragma unroll
+            for (int s = 0; s < 8; s++) sa[s] = tmp[s];
         }
+        // ---- backward sweep, ONE window body for all windows (instruction-cache footprint): the
+        //      start vector of a window comes from `spec` for the last and the first window (the
+        //      forward sweep's registers, then the saved a0) and from the checkpoints otherwise.
+        //      Every start vector is normalised, so component 0 is always 0.
+        w32 spec[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) spec[s] = a[s];
         w32 hold = 0;  // decision bits of an odd window waiting for its even partner
-        // ---- last window: alpha from the forward sweep's registers
-        {
-            const int w = NW - 1;
-            if (G == 0) {  // alpha at the sub-block end
-                w32 tmp[8];
-#pragma unroll
-                for (int s = 0; s < 8; s++) tmp[s] = a[s];
-                const int base = 8 * w * PP + t;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int idx = base + k * PP;
-                    alpha_step(tmp, x_at(sm, elem_off<IL>(sm, idx)), par[idx]);
-                }
-#pragma unroll
-                for (int s = 0; s < 8; s++) sa[s] = tmp[s];
-            }
-            const w32 acc = bwd_window<IL, WANT>(c, sm, par, 8 * w * PP + t, PP, a, b, stage);
-            if (w == w_sb) {
-#pragma unroll
-                for (int s = 0; s < 8; s++) sb[s] = b[s];
-            }
-            if (WANT) {
-                if (w & 1) hold = acc;
-                else {
-                    const w32 word = acc >> 8;
-                    changed |= word ^ sm.dec[(w >> 1) * P + t];
-                    sm.dec[(w >> 1) * P + t] = word;
-                }
-            }
-        }
-        // ---- middle windows: alpha from the checkpoints
-        for (int w = NW - 2; w >= 1; w--) {
+#pragma unroll 1
+        for (int w = NW - 1; w >= 0; w--) {
+            const bool mid = (w > 0) && (w < NW - 1);
             w32 aw0[8];
             aw0[0] = 0;
 #pragma unroll
-            for (int s = 1; s < 8; s++) aw0[s] = sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t];
+            for (int s = 1; s < 8; s++) {
+                aw0[s] = spec[s];
+                if (mid) aw0[s] = sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t];
+            }
             const w32 acc = bwd_window<IL, WANT>(c, sm, par, 8 * w * PP + t, PP, aw0, b, stage);
             if (w == w_sb) {
 #pragma unroll
@@ -371,19 +366,8 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
                     hold = 0;
                 }
             }
-        }
-        // ---- first window: alpha from the saved start vector
-        if (NW > 1) {
-            const w32 acc = bwd_window<IL, WANT>(c, sm, par, t, PP, a0, b, stage);
-            if (w_sb == 0) {
 #pragma unroll
-                for (int s = 0; s < 8; s++) sb[s] = b[s];
-            }
-            if (WANT) {
-                const w32 word = (acc >> 8) | hold;
-                changed |= word ^ sm.dec[t];
-                sm.dec[t] = word;
-            }
+            for (int s = 0; s < 8; s++) spec[s] = a0[s];
         }
         if (G > 0 && w_sa > 0 && w_sa < NW - 1) {
 #pragma unroll
