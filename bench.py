@@ -176,7 +176,8 @@ def run_ours(args):
     # synthetic traffic is made on the host (keeps the GPU launch list down to the decoder itself)
     bits, llr = synth.make_batch(K, batch, args.ebn0, seed=1000 + rank, device="cpu")
     bits, llr = bits.to(dev), llr.to(dev)
-    dec = TurboDecoder(K, n_iter=N_ITER, algo=args.algo, device=local, max_batch=batch)
+    dec = TurboDecoder(K, n_iter=N_ITER, algo=args.algo, device=local, max_batch=batch, sub_block=args.sub_block,
+                       warmup=args.guard)
     plan = dec.plan()
     out_bits = torch.empty((batch, K), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
@@ -294,6 +295,8 @@ def main():
     ap.add_argument("--algo", default="maxlog_s16")
     ap.add_argument("--ref-sample", type=int, default=0, help="codeblocks per CPU-baseline step (0 = 4 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sub-block", type=int, default=0, help="trellis steps per sub-block (0 = the library's plan)")
+    ap.add_argument("--guard", type=int, default=0, help="warm-up steps across sub-block boundaries (with --sub-block)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -296,7 +296,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         std::vector<uint16_t> tab((size_t)L * g.PP, 0);
         for (int i = 0; i < K; i++) {
             const int t = i / L, j = i % L, n = d->h_pi[i];
-            tab[j * g.PP + t] = (uint16_t)(4 * ((n % L) * g.PP + n / L));
+            tab[j * g.PP + t] = (uint16_t)((n % L) * g.PP + n / L);
         }
         TDB_CUDA(cudaMalloc(&d->d_tab2, sizeof(uint16_t) * tab.size()));
         TDB_CUDA(cudaMemcpy(d->d_tab2, tab.data(), sizeof(uint16_t) * tab.size(), cudaMemcpyHostToDevice));
@@ -415,7 +415,7 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
             a.ext_lim = c.ext_clip + 1;
             a.q2 = c.ext_scale_q2; a.early_term = c.early_term;
             a.tab2 = d->d_tab2;
-            a.neg1 = 0xffffffffu;
+            a.opaque[0] = 0xffffffffu; a.opaque[1] = 4u; a.opaque[2] = 65536u; a.opaque[3] = 0xC0000000u;
             a.prefetch_stride = d->geom.resident_ctas;
             a.bits = v_bits; a.iters_used = v_iters;
             a.llr2 = reinterpret_cast<float *>(v_llr2); a.ext2 = reinterpret_cast<float *>(v_ext2);

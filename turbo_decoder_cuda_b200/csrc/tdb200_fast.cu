@@ -94,39 +94,77 @@ __device__ __forceinline__ int quant(float x, float scale, int clip)
     return max(min(q, clip), -clip);
 }
 
-// 12 consecutive input values (4 systematic/parity1/parity2 triplets) starting at element 12*q
+// Two channel values (codeblock A, codeblock B) -> one clipped s16x2.  cvt.rni.sat.s16.f32 rounds
+// to nearest even, saturates and maps NaN to 0, exactly like quant() above for |clip| <= 32767.
+__device__ __forceinline__ w32 quant2(float a, float b, float scale, w32 clipv, w32 nclipv)
+{
+    short qa, qb;
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(qa) : "f"(a * scale));
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(qb) : "f"(b * scale));
+    w32 p;
+    asm("mov.b32 %0, {%1, %2};" : "=r"(p) : "h"(qa), "h"(qb));
+    return __vmins2(__vmaxs2(p, nclipv), clipv);
+}
+
+// 12 consecutive input values (4 systematic/parity1/parity2 triplets) of one codeblock, starting at
+// element 12*q, as loaded (128-bit loads for the float types)
 template <int LLR_T>
-__device__ __forceinline__ void load12(const void *base, size_t row_elems, int cb, int q, float scale, int clip, int (&out)[12])
+struct Raw12 {
+    float4 f[LLR_T == TDB200_LLR_F32 ? 3 : 1];
+    double2 d[LLR_T == TDB200_LLR_F64 ? 6 : 1];
+    int w[LLR_T == TDB200_LLR_S8 ? 3 : 1];
+};
+
+template <int LLR_T>
+__device__ __forceinline__ void load12(const void *base, size_t row_elems, int cb, int q, Raw12<LLR_T> &r)
 {
     if (LLR_T == TDB200_LLR_F32) {
         const float4 *p = reinterpret_cast<const float4 *>(static_cast<const float *>(base) + (size_t)cb * row_elems) + 3 * q;
-        float4 f[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) f[k] = __ldg(p + k);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            out[4 * k] = quant(f[k].x, scale, clip); out[4 * k + 1] = quant(f[k].y, scale, clip);
-            out[4 * k + 2] = quant(f[k].z, scale, clip); out[4 * k + 3] = quant(f[k].w, scale, clip);
-        }
+        for (int k = 0; k < 3; k++) r.f[k] = __ldg(p + k);
     } else if (LLR_T == TDB200_LLR_F64) {
         const double2 *p = reinterpret_cast<const double2 *>(static_cast<const double *>(base) + (size_t)cb * row_elems) + 6 * q;
-        double2 f[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) f[k] = __ldg(p + k);
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            out[2 * k] = quant((float)f[k].x, scale, clip); out[2 * k + 1] = quant((float)f[k].y, scale, clip);
-        }
+        for (int k = 0; k < 6; k++) r.d[k] = __ldg(p + k);
     } else {
         const int *p = reinterpret_cast<const int *>(static_cast<const int8_t *>(base) + (size_t)cb * row_elems) + 3 * q;
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int wv = __ldg(p + k);
+        for (int k = 0; k < 3; k++) r.w[k] = __ldg(p + k);
+    }
+}
+
+// quantise + pack the 12 values of codeblocks A and B into 12 s16x2 words
+template <int LLR_T>
+__device__ __forceinline__ void pack12(const Raw12<LLR_T> &a, const Raw12<LLR_T> &b, float scale, w32 clipv, w32 nclipv, w32 (&out)[12])
+{
+    if (LLR_T == TDB200_LLR_F32) {
 #pragma unroll
-            for (int m = 0; m < 4; m++) {
-                const int v = (int)(int8_t)((wv >> (8 * m)) & 0xff);
-                out[4 * k + m] = max(min(v, clip), -clip);
-            }
+        for (int k = 0; k < 3; k++) {
+            out[4 * k] = quant2(a.f[k].x, b.f[k].x, scale, clipv, nclipv);
+            out[4 * k + 1] = quant2(a.f[k].y, b.f[k].y, scale, clipv, nclipv);
+            out[4 * k + 2] = quant2(a.f[k].z, b.f[k].z, scale, clipv, nclipv);
+            out[4 * k + 3] = quant2(a.f[k].w, b.f[k].w, scale, clipv, nclipv);
+        }
+    } else if (LLR_T == TDB200_LLR_F64) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            out[2 * k] = quant2((float)a.d[k].x, (float)b.d[k].x, scale, clipv, nclipv);
+            out[2 * k + 1] = quant2((float)a.d[k].y, (float)b.d[k].y, scale, clipv, nclipv);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            // bytes {a_m, sign(a_m), b_m, sign(b_m)}; prmt, not __byte_perm: the intrinsic drops the
+            // sign-replication bit of the selector
+            w32 p0, p1, p2, p3;
+            asm("prmt.b32 %0, %1, %2, 0xc480;" : "=r"(p0) : "r"(a.w[k]), "r"(b.w[k]));
+            asm("prmt.b32 %0, %1, %2, 0xd591;" : "=r"(p1) : "r"(a.w[k]), "r"(b.w[k]));
+            asm("prmt.b32 %0, %1, %2, 0xe6a2;" : "=r"(p2) : "r"(a.w[k]), "r"(b.w[k]));
+            asm("prmt.b32 %0, %1, %2, 0xf7b3;" : "=r"(p3) : "r"(a.w[k]), "r"(b.w[k]));
+            out[4 * k] = __vmins2(__vmaxs2(p0, nclipv), clipv);
+            out[4 * k + 1] = __vmins2(__vmaxs2(p1, nclipv), clipv);
+            out[4 * k + 2] = __vmins2(__vmaxs2(p2, nclipv), clipv);
+            out[4 * k + 3] = __vmins2(__vmaxs2(p3, nclipv), clipv);
         }
     }
 }
@@ -142,79 +180,105 @@ __device__ __forceinline__ int load1(const void *base, size_t idx, float scale, 
 
 struct Smem {
     w32 *X, *par1, *par2;
-    uint16_t *sys8, *tab;
+    uint8_t *sysA, *sysB;  // systematic value + 128 of codeblock A / B, one byte per trellis step
+    uint16_t *tab;
     w32 *ckpt, *dec, *edge;
 };
 
-// sign-extend the two int8 of a 16-bit word into an s16x2
-__device__ __forceinline__ w32 sext8x2(unsigned v)
-{
-    w32 r;  // prmt default mode: selector nibble bit 3 replicates the sign of the selected byte
-    asm("prmt.b32 %0, %1, 0, 0x9180;" : "=r"(r) : "r"(v));
-    return r;
-}
-
+// Constants the compiler must not see through: ptxas strength-reduces x*-1-1, x*2, x*65536 and
+// mulhi(x, 3<<30) into ALU-pipe instructions (IADD3 / LEA / PRMT / SHF), and the ALU pipe is the one
+// the add-compare-select instructions saturate.  Passed as kernel arguments they stay IMADs on the
+// fma-heavy pipe, which has slack.
 struct PassCfg {
     int q2;
     w32 lim1;    // dup2(ext_lim + 1): the +1 completes m1 + ~m0 = m1 - m0 - 1
     w32 limmax;  // dup2(2*ext_lim - 1)
-    w32 unbias;  // dup2(-(3*ext_lim/4)) or dup2(-ext_lim)
-    w32 neg1;    // 0xffffffff, opaque to the compiler
+    w32 unbias;  // dup2(-(3*ext_lim/4) - 128) or dup2(-ext_lim - 128): extrinsic bias and systematic-byte bias
+    w32 neg1;    // 0xffffffff
+    w32 four;    // 4
+    w32 k64k;    // 65536
+    w32 k3q;     // 0xC0000000: mulhi(y, k3q) = (3*y) >> 2
 };
 
-// ~x on the fma-heavy pipe (x * -1 + -1); LOP3 would take an ALU-pipe slot, and that pipe is the
-// one the add-compare-select instructions saturate.  neg1 = 0xffffffff comes in as a kernel argument:
-// with a literal ptxas turns the product back into an ALU-pipe IADD3.
-__device__ __forceinline__ w32 vnot_fma(w32 x, w32 neg1) { return x * neg1 + neg1; }
+__device__ __forceinline__ w32 vnot_fma(w32 x, w32 neg1) { return x * neg1 + neg1; }  // ~x
+
+#ifndef TDB_LAMBDA_V3
+#define TDB_LAMBDA_V3 2
+#endif
+
+// max of four (alpha + beta') sums.  Form A: 1 fma-pipe + 3 ALU-pipe instructions; form B (three-input
+// maximum): 3 fma-pipe + 2 ALU-pipe.  TDB_LAMBDA_V3 of the four groups per step use form B, which is
+// what balances the two pipes in the backward window.
+template <bool V3>
+__device__ __forceinline__ w32 max4sum(w32 a0, w32 b0, w32 a1, w32 b1, w32 a2, w32 b2, w32 a3, w32 b3)
+{
+    if (V3) return vaddmax(a3, b3, __vimax3_s16x2(vadd(a0, b0), vadd(a1, b1), vadd(a2, b2)));
+    return vaddmax(a3, b3, vaddmax(a2, b2, vaddmax(a1, b1, vadd(a0, b0))));
+}
 
 // e - 1, where e = max_{input 1}(alpha + c*V + beta') - max_{input 0}(alpha + c*V + beta')
 // (:1024-1039 as max-log; the +U common to all input-1 branches is left out, so e IS the extrinsic
 // of :1234-1238).  The -1 is absorbed by the clamp constant.
 __device__ __forceinline__ w32 extrinsic_m1(const w32 (&a)[8], const w32 (&b)[8], w32 v, w32 neg1)
 {
-    w32 m0a = vadd(a[0], b[0]); m0a = vaddmax(a[1], b[4], m0a); m0a = vaddmax(a[6], b[7], m0a); m0a = vaddmax(a[7], b[3], m0a);
-    w32 m0b = vadd(a[2], b[5]); m0b = vaddmax(a[3], b[1], m0b); m0b = vaddmax(a[4], b[2], m0b); m0b = vaddmax(a[5], b[6], m0b);
-    w32 m1a = vadd(a[0], b[4]); m1a = vaddmax(a[1], b[0], m1a); m1a = vaddmax(a[6], b[3], m1a); m1a = vaddmax(a[7], b[7], m1a);
-    w32 m1b = vadd(a[2], b[1]); m1b = vaddmax(a[3], b[5], m1b); m1b = vaddmax(a[4], b[6], m1b); m1b = vaddmax(a[5], b[2], m1b);
+    const w32 m0a = max4sum<(TDB_LAMBDA_V3 > 0)>(a[0], b[0], a[1], b[4], a[6], b[7], a[7], b[3]);
+    const w32 m0b = max4sum<(TDB_LAMBDA_V3 > 2)>(a[2], b[5], a[3], b[1], a[4], b[2], a[5], b[6]);
+    const w32 m1a = max4sum<(TDB_LAMBDA_V3 > 3)>(a[0], b[4], a[1], b[0], a[6], b[3], a[7], b[7]);
+    const w32 m1b = max4sum<(TDB_LAMBDA_V3 > 1)>(a[2], b[1], a[3], b[5], a[4], b[6], a[5], b[2]);
     const w32 m0 = vaddmax(m0b, v, m0a);
     const w32 m1 = vaddmax(m1a, v, m1b);
     return vadd(m1, vnot_fma(m0, neg1));
 }
 
-// Shared-memory accessors.  Interleaved passes go through tab, which holds the BYTE offset 4e of
-// element e inside X (so the X access needs no address arithmetic); sys8 sits at half of it.
+// Where a trellis step's a-priori word X and systematic byte pair live.  Natural-order passes
+// address them by step index (base + immediate); interleaved passes go through tab, which holds the
+// word index e of the element: its byte offset in the systematic planes, a quarter of the one in X.
+struct Elem {
+    unsigned xoff, soff;  // byte offsets into X / the systematic byte planes
+};
 template <bool IL>
-__device__ __forceinline__ unsigned elem_off(const Smem &sm, int idx)
+__device__ __forceinline__ Elem elem_of(const PassCfg &c, unsigned tabval, int idx)
 {
-    return IL ? (unsigned)sm.tab[idx] : 4u * (unsigned)idx;
+    Elem e;
+    e.soff = IL ? tabval : (unsigned)idx;
+    e.xoff = IL ? tabval * c.four : 4u * (unsigned)idx;
+    return e;
 }
-__device__ __forceinline__ w32 &word_at(w32 *base, unsigned off4)
+template <bool IL>
+__device__ __forceinline__ Elem elem_at(const PassCfg &c, const Smem &sm, int idx)
 {
-    return *reinterpret_cast<w32 *>(reinterpret_cast<unsigned char *>(base) + off4);
+    return elem_of<IL>(c, IL ? (unsigned)sm.tab[idx] : 0u, idx);
 }
-__device__ __forceinline__ w32 &x_at(const Smem &sm, unsigned off4) { return word_at(sm.X, off4); }
-__device__ __forceinline__ unsigned sys_at(const Smem &sm, unsigned off4)
+__device__ __forceinline__ w32 &word_at(w32 *base, unsigned xoff)
 {
-    return *reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(sm.sys8) + (off4 >> 1));
+    return *reinterpret_cast<w32 *>(reinterpret_cast<unsigned char *>(base) + xoff);
+}
+__device__ __forceinline__ w32 &x_at(const Smem &sm, const Elem &e) { return word_at(sm.X, e.xoff); }
+// systematic values of the two codeblocks, each + 128, as an s16x2: one byte load per codeblock
+// (separate planes, so the compiler cannot merge them into a 16-bit load + two PRMTs) and one IMAD
+__device__ __forceinline__ w32 sys_biased(const PassCfg &c, const Smem &sm, const Elem &e)
+{
+    return (w32)sm.sysB[e.soff] * c.k64k + (w32)sm.sysA[e.soff];
 }
 
 // Backward sweep over one 8-step window whose first alpha vector is a0 (normalised): re-create
 // the window's alpha vectors in registers, then run beta, the extrinsic output and the in-place
-// update of X over it.  Returns the decision bits of the window (WANT only): sign of step k in
-// bit 15-k (codeblock A) / 31-k (codeblock B).
+// update of X over it.  tabin: the window's table entries (interleaved passes fetch them one window
+// ahead, so the look-up is off the critical path).  Returns the decision bits of the window (WANT
+// only): sign of step k in bit 15-k (codeblock A) / 31-k (codeblock B).
 template <bool IL, bool WANT>
 __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, const w32 *par, const int base, const int PP,
-                                          const w32 (&a0)[8], w32 (&b)[8], w32 *stage)
+                                          const unsigned (&tabin)[8], const w32 (&a0)[8], w32 (&b)[8], w32 *stage)
 {
     w32 aw[8][8], u[8], v[8];
-    unsigned off[8];
+    Elem el[8];
 #pragma unroll
     for (int s = 0; s < 8; s++) aw[0][s] = a0[s];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const int idx = base + k * PP;
-        off[k] = elem_off<IL>(sm, idx);
-        u[k] = x_at(sm, off[k]);
+        el[k] = elem_of<IL>(c, tabin[k], idx);
+        u[k] = x_at(sm, el[k]);
         v[k] = par[idx];
         if (k < 7) alpha_step_to(aw[k], u[k], v[k], aw[k + 1]);
     }
@@ -226,14 +290,13 @@ __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, cons
         // clamp to [-lim, lim-1], bias to [0, 2lim-1]
         const w32 y = __viaddmin_s16x2_relu(exm1, c.lim1, c.limmax);
         w32 es;
-        if (c.q2 == 3) es = ((y * 3u) >> 2) & 0x3fff3fffu;  // floor(3(ec+lim)/4), no cross-lane carry
+        if (c.q2 == 3) es = __umulhi(y, c.k3q) & 0x3fff3fffu;  // floor(3(ec+lim)/4) per lane
         else es = y;
-        const w32 ys = sext8x2(sys_at(sm, off[k]));
-        x_at(sm, off[k]) = vadd(vadd(ys, es), c.unbias);
+        x_at(sm, el[k]) = vadd(vadd(sys_biased(c, sm, el[k]), es), c.unbias);
         if (WANT) {
             const w32 lam = vadd(vadd(u[k], exm1), 0x00010001u);  // a-posteriori, :1038 (+ the dropped U)
             acc = (acc >> 1) | (lam & 0x80008000u);
-            if (stage) word_at(stage, off[k]) = lam;
+            if (stage) word_at(stage, el[k].xoff) = lam;
         }
         beta_step(b, u[k], v[k]);
     }
@@ -260,7 +323,10 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
     for (int s = 0; s < 8; s++) { a[s] = na[s]; b[s] = nb[s]; sa[s] = 0; sb[s] = 0; }
 
+    unsigned offn[8];  // interleaved passes: table entries of the window that is processed next
     if (active) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) offn[k] = IL ? (unsigned)sm.tab[k * PP + t] : 0u;
         // ---- warm-up: alpha over the last G steps of sub-block t-1 and beta over the first G steps
         //      of sub-block t+1, advanced together (two independent dependency chains).  The two
         //      edge threads run it on their own sub-block and throw the result away, which keeps the
@@ -275,8 +341,8 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int ia = base_a + k * PP, ib = base_b + (7 - k) * PP;
-                alpha_step(a, x_at(sm, elem_off<IL>(sm, ia)), par[ia]);
-                beta_step(b, x_at(sm, elem_off<IL>(sm, ib)), par[ib]);
+                alpha_step(a, x_at(sm, elem_at<IL>(c, sm, ia)), par[ia]);
+                beta_step(b, x_at(sm, elem_at<IL>(c, sm, ib)), par[ib]);
             }
         }
 #pragma unroll
@@ -295,6 +361,12 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
         //      windows 1..NW-2; the start of window NW-1 stays in registers
 #pragma unroll 1
         for (int w = 0; w < NW - 1; w++) {
+            Elem el[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                el[k] = elem_of<IL>(c, offn[k], (8 * w + k) * PP + t);
+                if (IL) offn[k] = sm.tab[(8 * (w + 1) + k) * PP + t];
+            }
             if (w > 0) {
                 norm8(a);
 #pragma unroll
@@ -302,10 +374,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
             }
             const int base = 8 * w * PP + t;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int idx = base + k * PP;
-                alpha_step(a, x_at(sm, elem_off<IL>(sm, idx)), par[idx]);
-            }
+            for (int k = 0; k < 8; k++) alpha_step(a, x_at(sm, el[k]), par[base + k * PP]);
         }
         if (NW > 1) norm8(a);
     }
@@ -329,7 +398,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int idx = base + k * PP;
-                alpha_step(tmp, x_at(sm, elem_off<IL>(sm, idx)), par[idx]);
+                alpha_step(tmp, x_at(sm, elem_at<IL>(c, sm, idx)), par[idx]);
             }
 #pragma unroll
             for (int s = 0; s < 8; s++) sa[s] = tmp[s];
@@ -352,7 +421,13 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
                 aw0[s] = spec[s];
                 if (mid) aw0[s] = sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t];
             }
-            const w32 acc = bwd_window<IL, WANT>(c, sm, par, 8 * w * PP + t, PP, aw0, b, stage);
+            unsigned off[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                off[k] = offn[k];
+                if (IL) offn[k] = sm.tab[(8 * max(w - 1, 0) + k) * PP + t];
+            }
+            const w32 acc = bwd_window<IL, WANT>(c, sm, par, 8 * w * PP + t, PP, off, aw0, b, stage);
             if (w == w_sb) {
 #pragma unroll
                 for (int s = 0; s < 8; s++) sb[s] = b[s];
@@ -409,18 +484,20 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
     return changed;
 }
 
-// ---- de-multiplex + quantise one group of four trellis steps of both codeblocks into shared memory
-__device__ __forceinline__ void put4(const Smem &sm, int q, int L, int PP, const int (&va)[12], const int (&vb)[12])
+// ---- de-multiplex one group of four trellis steps (12 packed words: sys,par1,par2 x 4) into shared memory
+__device__ __forceinline__ void put4(const Smem &sm, int q, int L, int PP, const w32 (&v)[12])
 {
+    const int n = 4 * q;  // L is a multiple of 8, so the four steps share their sub-block
+    const int tt = n / L, j = n - tt * L;
+    const int ad = j * PP + tt;
 #pragma unroll
     for (int m = 0; m < 4; m++) {
-        const int n = 4 * q + m;
-        const int tt = n / L, j = n - tt * L;
-        const int ad = j * PP + tt;
-        sm.X[ad] = pack2(va[3 * m], vb[3 * m]);
-        sm.sys8[ad] = (uint16_t)((va[3 * m] & 0xff) | ((vb[3 * m] & 0xff) << 8));
-        sm.par1[ad] = pack2(va[3 * m + 1], vb[3 * m + 1]);
-        sm.par2[ad] = pack2(va[3 * m + 2], vb[3 * m + 2]);
+        sm.X[ad + m * PP] = v[3 * m];
+        const w32 sb = vadd(v[3 * m], 0x00800080u);  // value + 128 in each lane
+        sm.sysA[ad + m * PP] = (uint8_t)sb;
+        sm.sysB[ad + m * PP] = (uint8_t)(sb >> 16);
+        sm.par1[ad + m * PP] = v[3 * m + 1];
+        sm.par2[ad + m * PP] = v[3 * m + 2];
     }
 }
 
@@ -433,12 +510,14 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     const int L = 8 * NW, K = P * L;
     const int W = L * PP;  // words per array
     Smem sm;
+    const int Wp = (W + 7) & ~7;  // every region starts 16-byte aligned
     sm.X = reinterpret_cast<w32 *>(smem_raw);
-    sm.par1 = sm.X + W;
-    sm.par2 = sm.par1 + W;
-    sm.sys8 = reinterpret_cast<uint16_t *>(sm.par2 + W);
-    sm.tab = sm.sys8 + W + (W & 1);
-    sm.ckpt = reinterpret_cast<w32 *>(sm.tab + W + (W & 1));
+    sm.par1 = sm.X + Wp;
+    sm.par2 = sm.par1 + Wp;
+    sm.sysA = reinterpret_cast<uint8_t *>(sm.par2 + Wp);
+    sm.sysB = sm.sysA + Wp;
+    sm.tab = reinterpret_cast<uint16_t *>(sm.sysB + Wp);
+    sm.ckpt = reinterpret_cast<w32 *>(sm.tab + Wp);
     sm.dec = sm.ckpt + (size_t)g.n_ckpt * 7 * P;
     sm.edge = sm.dec + (size_t)((NW + 1) / 2) * P;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -452,34 +531,50 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     // ---- load + quantise + de-multiplex (once per decode); element n = tt*L + j -> word j*PP + tt.
     //      Two groups of loads are in flight per thread before the first is consumed.
     {
+        const w32 clipv = dup2(clip), nclipv = dup2(-clip);
         const int nq = K / 4;
         int q = tid;
         for (; q + nthr < nq; q += 2 * nthr) {
-            int va0[12], vb0[12], va1[12], vb1[12];
-            load12<LLR_T>(A.llr, row, cbA, q, scale, clip, va0);
-            load12<LLR_T>(A.llr, row, cbB, q, scale, clip, vb0);
-            load12<LLR_T>(A.llr, row, cbA, q + nthr, scale, clip, va1);
-            load12<LLR_T>(A.llr, row, cbB, q + nthr, scale, clip, vb1);
-            put4(sm, q, L, PP, va0, vb0);
-            put4(sm, q + nthr, L, PP, va1, vb1);
+            Raw12<LLR_T> ra0, rb0, ra1, rb1;
+            load12<LLR_T>(A.llr, row, cbA, q, ra0);
+            load12<LLR_T>(A.llr, row, cbB, q, rb0);
+            load12<LLR_T>(A.llr, row, cbA, q + nthr, ra1);
+            load12<LLR_T>(A.llr, row, cbB, q + nthr, rb1);
+            w32 v[12];
+            pack12<LLR_T>(ra0, rb0, scale, clipv, nclipv, v);
+            put4(sm, q, L, PP, v);
+            pack12<LLR_T>(ra1, rb1, scale, clipv, nclipv, v);
+            put4(sm, q + nthr, L, PP, v);
         }
         if (q < nq) {
-            int va[12], vb[12];
-            load12<LLR_T>(A.llr, row, cbA, q, scale, clip, va);
-            load12<LLR_T>(A.llr, row, cbB, q, scale, clip, vb);
-            put4(sm, q, L, PP, va, vb);
+            Raw12<LLR_T> ra, rb;
+            load12<LLR_T>(A.llr, row, cbA, q, ra);
+            load12<LLR_T>(A.llr, row, cbB, q, rb);
+            w32 v[12];
+            pack12<LLR_T>(ra, rb, scale, clipv, nclipv, v);
+            put4(sm, q, L, PP, v);
         }
     }
-    for (int i = tid; i < W; i += nthr) sm.tab[i] = __ldg(A.tab2 + i);
-    // ---- pull the rows of the codeblock pair that will run on this SM slot next into L2
+    {   // QPP table: 128-bit loads (the table and the shared-memory array are 16-byte aligned)
+        const int n16 = (W * 2) / 16;
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.tab2);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.tab);
+        for (int i = tid; i < n16; i += nthr) dst[i] = __ldg(src + i);
+        for (int i = n16 * 8 + tid; i < W; i += nthr) sm.tab[i] = __ldg(A.tab2 + i);
+    }
+    // ---- pull the rows of the codeblock pair that will run on this SM slot next into L2 (bulk
+    //      prefetch, a few KB per instruction; rows are 16-byte multiples)
     if (A.prefetch_stride > 0) {
         const long long nxt = (long long)2 * (blockIdx.x + A.prefetch_stride);
         if (nxt < A.n_cb) {
             const size_t esz = LLR_T == TDB200_LLR_F64 ? 8 : (LLR_T == TDB200_LLR_F32 ? 4 : 1);
             const char *p = static_cast<const char *>(A.llr) + (size_t)nxt * row * esz;
-            const size_t nbytes = (nxt + 1 < A.n_cb ? 2 : 1) * row * esz;
-            for (size_t o = (size_t)tid * 128; o < nbytes; o += (size_t)nthr * 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+            const size_t nbytes = ((nxt + 1 < A.n_cb ? 2 : 1) * row * esz) & ~(size_t)15;
+            const size_t chunk = 4096;
+            for (size_t o = (size_t)tid * chunk; o < nbytes; o += (size_t)nthr * chunk) {
+                const unsigned sz = (unsigned)(nbytes - o < chunk ? nbytes - o : chunk);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + o), "r"(sz) : "memory");
+            }
         }
     }
 
@@ -487,8 +582,8 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     c.q2 = A.q2;
     c.lim1 = dup2(A.ext_lim + 1);
     c.limmax = dup2(2 * A.ext_lim - 1);
-    c.unbias = dup2(A.q2 == 3 ? -(3 * A.ext_lim / 4) : -A.ext_lim);
-    c.neg1 = A.neg1;
+    c.unbias = dup2((A.q2 == 3 ? -(3 * A.ext_lim / 4) : -A.ext_lim) - 128);
+    c.neg1 = A.opaque[0]; c.four = A.opaque[1]; c.k64k = A.opaque[2]; c.k3q = A.opaque[3];
     const bool first_fixed = (tid == 0), last_fixed = (tid == P - 1);
 
     // ---- boundary vectors.  [s][0..7]: s = SISO
@@ -557,7 +652,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
                 for (int kk = 0; kk < 16; kk++) {
                     const int j = 16 * w2 + (kk & 8) + 7 - (kk & 7);  // step k of a window sits in bit 7-k of its byte
                     if (j < L) {
-                        const int e = sm.tab[j * PP + tid] >> 2;
+                        const int e = sm.tab[j * PP + tid];
                         const int jj = e / PP, tt = e - jj * PP;
                         const int n = tt * L + jj;
                         byA[n] = (uint8_t)(((word >> kk) & 1u) ^ 1u);
@@ -585,9 +680,10 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
             float la = 0.f, lb = 0.f, ea = 0.f, eb = 0.f;
             if (i < K) {
                 const int tt = i / L, j = i - tt * L;
-                const int e = sm.tab[j * PP + tt] >> 2;
+                const int e = sm.tab[j * PP + tt];
                 const w32 lam = sm.par1[e];
-                const w32 ex = vadd(sm.X[e], vneg(sext8x2(sm.sys8[e])));
+                const w32 ysb = (w32)sm.sysA[e] | ((w32)sm.sysB[e] << 16);
+                const w32 ex = vadd(vadd(sm.X[e], vneg(ysb)), 0x00800080u);
                 la = (float)(int16_t)(lam & 0xffff) * inv; lb = (float)(int16_t)(lam >> 16) * inv;
                 ea = (float)(int16_t)(ex & 0xffff) * inv; eb = (float)(int16_t)(ex >> 16) * inv;
             }
@@ -599,14 +695,21 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
 
 typedef void (*kernel_fn)(FastArgs);
 
-// The specialised instance exists for the BASELINE geometry only (K=6144: P=128, NW=6, G=16).
+// Specialised instances exist for the BASELINE block size only: K=6144 as 128 sub-blocks of 48 steps
+// or 192 sub-blocks of 32 steps (guard 16 either way); everything else runs the generic kernel.
+template <int LLR_T>
+kernel_fn pick_kernel_t(const FastGeom &g)
+{
+    if (g.P == 128 && g.NW == 6 && g.G == 16 && g.PP == 129) return fast_s16_kernel<LLR_T, 128, 6, 16>;
+    if (g.P == 192 && g.NW == 4 && g.G == 16 && g.PP == 193) return fast_s16_kernel<LLR_T, 192, 4, 16>;
+    return fast_s16_kernel<LLR_T, 0, 0, 0>;
+}
 kernel_fn pick_kernel(const FastGeom &g, int llr_type)
 {
-    const bool spec = (g.P == 128 && g.NW == 6 && g.G == 16 && g.PP == 129);
     switch (llr_type) {
-        case TDB200_LLR_F32: return spec ? fast_s16_kernel<TDB200_LLR_F32, 128, 6, 16> : fast_s16_kernel<TDB200_LLR_F32, 0, 0, 0>;
-        case TDB200_LLR_F64: return spec ? fast_s16_kernel<TDB200_LLR_F64, 128, 6, 16> : fast_s16_kernel<TDB200_LLR_F64, 0, 0, 0>;
-        default: return spec ? fast_s16_kernel<TDB200_LLR_S8, 128, 6, 16> : fast_s16_kernel<TDB200_LLR_S8, 0, 0, 0>;
+        case TDB200_LLR_F32: return pick_kernel_t<TDB200_LLR_F32>(g);
+        case TDB200_LLR_F64: return pick_kernel_t<TDB200_LLR_F64>(g);
+        default: return pick_kernel_t<TDB200_LLR_S8>(g);
     }
 }
 
@@ -615,8 +718,8 @@ kernel_fn pick_kernel(const FastGeom &g, int llr_type)
 int fast_s16_smem_bytes(const FastGeom &g)
 {
     const int nwarps = g.threads / 32;
-    const int W = g.L * g.PP, W2 = W + (W & 1);
-    return 3 * 4 * W + 2 * 2 * W2 + 4 * g.n_ckpt * 7 * g.P + 4 * ((g.NW + 1) / 2) * g.P + 4 * 16 * nwarps;
+    const int W = g.L * g.PP, Wp = (W + 7) & ~7;
+    return 3 * 4 * Wp + 2 * 2 * Wp + 4 * g.n_ckpt * 7 * g.P + 4 * ((g.NW + 1) / 2) * g.P + 4 * 16 * nwarps;
 }
 
 cudaError_t fast_s16_configure(FastGeom &g, int sm_count)

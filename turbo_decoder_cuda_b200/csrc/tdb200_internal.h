@@ -97,8 +97,8 @@ struct FastArgs {
     int n_iter;
     int frac_bits, llr_clip, ext_lim /* Ce+1, multiple of 4 */, q2;
     int early_term;
-    uint32_t neg1;  // 0xffffffff (see vnot_fma)
-    const uint16_t *tab2;  // [L*PP] device: 4 * (smem word of element pi(tL+j)), stored at index j*PP+t
+    uint32_t opaque[4];  // {0xffffffff, 4, 65536, 0xC0000000}: see PassCfg in tdb200_fast.cu
+    const uint16_t *tab2;  // [L*PP] device: smem word of element pi(tL+j), stored at index j*PP+t
     int prefetch_stride;   // CTAs resident on the device at once (0 = no L2 prefetch of the next pair)
     // outputs (device, nullable)
     uint8_t *bits;
