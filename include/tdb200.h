@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TDB200_VERSION 2
+#define TDB200_VERSION 3
 
 typedef enum tdb200_status {
     TDB200_OK = 0,
@@ -77,7 +77,10 @@ typedef struct tdb200_config {
                        Ignored by TDB200_ALGO_LOGMAP_F64 (always unsegmented). */
     int warmup;     /* guard steps recomputed from the neighbouring sub-block before each
                        sub-block boundary; 0 = next-iteration initialisation only */
-    int early_term; /* 1 = stop a codeblock when its hard decisions repeat (min 2 iterations) */
+    int early_term; /* 1 = stop a codeblock when an iteration leaves every hard decision unchanged AND
+                       every a-posteriori magnitude is at least et_threshold (min 2 iterations) */
+    int et_threshold; /* magnitude test of the stopping rule, fixed-point units, a power of two
+                         (1 = decisions only).  0 = default: 2^(frac_bits+3), i.e. |LLR| >= 8 */
     int ext_scale_q2; /* extrinsic scaling in quarters for the max-log modes: 3 = 0.75, 4 = 1.0;
                          0 = default (3 for max-log, 4 for Log-MAP) */
     int frac_bits;  /* fixed-point fractional bits of TDB200_ALGO_MAXLOG_S16 and of

@@ -89,7 +89,8 @@ typedef struct tdo_fx_params {
     int llr_clip;     /* |q| clamp for channel values */
     int ext_clip;     /* |Le| clamp */
     int ext_scale_q2; /* extrinsic scale in quarters: 3 = 0.75, 4 = 1.0 */
-    int early_term;   /* 1: stop when hard decisions repeat between two iterations */
+    int early_term;   /* 1: stop when an iteration changes no hard decision and every |a-posteriori| >= et_threshold */
+    int et_threshold; /* fixed-point units; values < 1 are treated as 1 */
 } tdo_fx_params;
 
 /* Returns the number of iterations run.  bits_out[K] final decisions; le_out

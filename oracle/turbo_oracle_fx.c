@@ -143,8 +143,10 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
         memcpy(niiB[s * P + P - 1], b, sizeof(b));
     }
 
+    const int et_T = p->et_threshold < 1 ? 1 : p->et_threshold;
     int it;
     for (it = 0; it < p->n_iter; it++) {
+        int weak = 0;
         for (int s = 0; s < 2; s++) {
             const int *yp = s ? yp2 : yp1;
             /* warm-ups read the a-priori values as they were when the pass started (in the kernel
@@ -197,6 +199,7 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                     if (k == G) memcpy(newB[t], b, sizeof(b));
                     if (s == 1) {
                         cur_bits[n] = lam < 0 ? 0 : 1;
+                        if (lam < et_T && lam > -et_T) weak = 1;
                         if (le_out) le_out[n] = es;
                     }
                 }
@@ -213,7 +216,7 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
             if (cur_bits[i] != prev_bits[i]) same = 0;
             prev_bits[i] = cur_bits[i];
         }
-        if (p->early_term && same && it >= 1) {
+        if (p->early_term && same && !weak && it >= 1) {
             it++;
             break;
         }

@@ -139,6 +139,7 @@ def test_early_termination(oracle, K, ebn0):
     out = dec.decode(llr32, want=("bits", "iters_used"))
     prm = _fx_params(K, n_iter, plan["sub_block"], plan["warmup"])
     prm.early_term = 1
+    prm.et_threshold = 1 << (prm.frac_bits + 3)  # the library default: |LLR| >= 8
     its = [oracle.fx_decode(llr32[c], pi, prm)[2] for c in range(n_cb)]
     assert out["iters_used"].tolist() == its
     for c in range(n_cb):

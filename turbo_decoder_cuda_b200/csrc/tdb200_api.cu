@@ -263,6 +263,9 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         if (c.frac_bits < 1 || c.frac_bits > 4) return fail(TDB200_ERR_INVALID_ARG, "frac_bits=%d out of range [1,4]", c.frac_bits);
         if (c.ext_scale_q2 == 0) c.ext_scale_q2 = 3;
         if (c.ext_scale_q2 != 3 && c.ext_scale_q2 != 4) return fail(TDB200_ERR_INVALID_ARG, "ext_scale_q2=%d (3 or 4)", c.ext_scale_q2);
+        if (c.et_threshold == 0) c.et_threshold = 1 << (c.frac_bits + 3);
+        if (c.et_threshold < 1 || c.et_threshold > 4096 || (c.et_threshold & (c.et_threshold - 1)))
+            return fail(TDB200_ERR_INVALID_ARG, "et_threshold=%d must be a power of two in [1,4096]", c.et_threshold);
         if (c.ext_clip == 0) c.ext_clip = (1 << (c.frac_bits + 7)) - 1;
         if (c.ext_clip < 63 || c.ext_clip > 2047 || ((c.ext_clip + 1) & 3))
             return fail(TDB200_ERR_INVALID_ARG, "ext_clip=%d: need 63 <= ext_clip <= 2047 and ext_clip+1 a multiple of 4", c.ext_clip);
@@ -413,7 +416,7 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
             a.frac_bits = c.frac_bits;
             a.llr_clip = std::min((1 << (c.frac_bits + 4)) - 1, 127);  // systematic values are kept as int8 pairs in shared memory
             a.ext_lim = c.ext_clip + 1;
-            a.q2 = c.ext_scale_q2; a.early_term = c.early_term;
+            a.q2 = c.ext_scale_q2; a.early_term = c.early_term; a.et_threshold = c.et_threshold;
             a.tab2 = d->d_tab2;
             a.opaque[0] = 0xffffffffu; a.opaque[1] = 4u; a.opaque[2] = 65536u; a.opaque[3] = 0xC0000000u;
             a.prefetch_stride = d->geom.resident_ctas;

@@ -198,6 +198,7 @@ struct PassCfg {
     w32 four;    // 4
     w32 k64k;    // 65536
     w32 k3q;     // 0xC0000000: mulhi(y, k3q) = (3*y) >> 2
+    w32 etT, et2T, etmask;  // dup2(T), dup2(2T), dup2(2T-1): magnitude test of the stopping rule
 };
 
 __device__ __forceinline__ w32 vnot_fma(w32 x, w32 neg1) { return x * neg1 + neg1; }  // ~x
@@ -265,10 +266,11 @@ __device__ __forceinline__ w32 sys_biased(const PassCfg &c, const Smem &sm, cons
 // the window's alpha vectors in registers, then run beta, the extrinsic output and the in-place
 // update of X over it.  tabin: the window's table entries (interleaved passes fetch them one window
 // ahead, so the look-up is off the critical path).  Returns the decision bits of the window (WANT
-// only): sign of step k in bit 15-k (codeblock A) / 31-k (codeblock B).
+// only): sign of step k in bit 15-k (codeblock A) / 31-k (codeblock B); weak collects, per lane, a
+// non-zero value if some |a-posteriori| of the window is below the stopping threshold.
 template <bool IL, bool WANT>
 __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, const w32 *par, const int base, const int PP,
-                                          const unsigned (&tabin)[8], const w32 (&a0)[8], w32 (&b)[8], w32 *stage)
+                                          const unsigned (&tabin)[8], const w32 (&a0)[8], w32 (&b)[8], w32 *stage, w32 &weak)
 {
     w32 aw[8][8], u[8], v[8];
     Elem el[8];
@@ -296,6 +298,8 @@ __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, cons
         if (WANT) {
             const w32 lam = vadd(vadd(u[k], exm1), 0x00010001u);  // a-posteriori, :1038 (+ the dropped U)
             acc = (acc >> 1) | (lam & 0x80008000u);
+            // clamp(lam + T, 0, 2T) is 0 or 2T exactly when |lam| >= T (lam >= T or lam <= -T)
+            weak |= __viaddmin_s16x2_relu(lam, c.etT, c.et2T) & c.etmask;
             if (stage) word_at(stage, el[k].xoff) = lam;
         }
         beta_step(b, u[k], v[k]);
@@ -307,10 +311,11 @@ __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, cons
 // na/nb: boundary vectors (alpha G steps before the sub-block, beta G steps after it); on return
 // they hold the vectors for the next iteration of this SISO.  With WANT the hard decisions of this
 // pass go to sm.dec (one word per two windows) and the return value has bits 0-15 / 16-31 set
-// where a decision of codeblock A / B differs from what sm.dec held before.
+// where a decision of codeblock A / B differs from what sm.dec held before; weak gets a non-zero
+// low / high half if some a-posteriori magnitude of codeblock A / B is below the stopping threshold.
 template <bool IL, bool WANT, int KP, int KNW, int KG>
 __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, const Smem &sm, const w32 *par, w32 (&na)[8], w32 (&nb)[8],
-                                         const bool first_fixed, const bool last_fixed, w32 *stage)
+                                         const bool first_fixed, const bool last_fixed, w32 *stage, w32 &weak)
 {
     const int P = KP ? KP : g.P, PP = KP ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW, G = KP ? KG : g.G;
     const int L = 8 * NW;
@@ -427,7 +432,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
                 off[k] = offn[k];
                 if (IL) offn[k] = sm.tab[(8 * max(w - 1, 0) + k) * PP + t];
             }
-            const w32 acc = bwd_window<IL, WANT>(c, sm, par, 8 * w * PP + t, PP, off, aw0, b, stage);
+            const w32 acc = bwd_window<IL, WANT>(c, sm, par, 8 * w * PP + t, PP, off, aw0, b, stage, weak);
             if (w == w_sb) {
 #pragma unroll
                 for (int s = 0; s < 8; s++) sb[s] = b[s];
@@ -584,6 +589,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     c.limmax = dup2(2 * A.ext_lim - 1);
     c.unbias = dup2((A.q2 == 3 ? -(3 * A.ext_lim / 4) : -A.ext_lim) - 128);
     c.neg1 = A.opaque[0]; c.four = A.opaque[1]; c.k64k = A.opaque[2]; c.k3q = A.opaque[3];
+    c.etT = dup2(A.et_threshold); c.et2T = dup2(2 * A.et_threshold); c.etmask = dup2(2 * A.et_threshold - 1);
     const bool first_fixed = (tid == 0), last_fixed = (tid == P - 1);
 
     // ---- boundary vectors.  [s][0..7]: s = SISO
@@ -617,16 +623,18 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     int used = A.n_iter, usedA = 0, usedB = 0;
     for (int it = 0; it < A.n_iter; it++) {
         const bool last = (it == A.n_iter - 1);
-        siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], first_fixed, last_fixed, nullptr);
+        w32 weak = 0;
+        siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], first_fixed, last_fixed, nullptr, weak);
         if (A.early_term || last) {
             // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
             // (by then dead) parity-1 array
             const w32 chg = siso_pass<true, true, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed,
-                                                               (want_soft && last) ? sm.par1 : nullptr);
+                                                               (want_soft && last) ? sm.par1 : nullptr, weak);
             if (A.early_term) {
-                // hard-decision-aided stop: no decision of an iteration differs from the previous one
-                const int chA = __syncthreads_or((int)(chg & 0xffffu));
-                const int chB = __syncthreads_or((int)(chg >> 16));
+                // stop: no decision of this iteration differs from the previous one and no
+                // a-posteriori value is weaker than the threshold
+                const int chA = __syncthreads_or((int)((chg | weak) & 0xffffu));
+                const int chB = __syncthreads_or((int)((chg | weak) >> 16));
                 if (it >= 1) {
                     if (!chA && !usedA) usedA = it + 1;
                     if (!chB && !usedB) usedB = it + 1;
@@ -634,7 +642,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
                 }
             }
         } else {
-            siso_pass<true, false, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed, nullptr);
+            siso_pass<true, false, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed, nullptr, weak);
         }
     }
     if (!usedA) usedA = used;

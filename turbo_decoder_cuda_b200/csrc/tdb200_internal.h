@@ -96,7 +96,7 @@ struct FastArgs {
     FastGeom g;
     int n_iter;
     int frac_bits, llr_clip, ext_lim /* Ce+1, multiple of 4 */, q2;
-    int early_term;
+    int early_term, et_threshold;
     uint32_t opaque[4];  // {0xffffffff, 4, 65536, 0xC0000000}: see PassCfg in tdb200_fast.cu
     const uint16_t *tab2;  // [L*PP] device: smem word of element pi(tL+j), stored at index j*PP+t
     int prefetch_stride;   // CTAs resident on the device at once (0 = no L2 prefetch of the next pair)

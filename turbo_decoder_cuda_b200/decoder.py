@@ -35,7 +35,7 @@ class TdbError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
-        "K", "f1", "f2", "n_iter", "algo", "sub_block", "warmup", "early_term", "ext_scale_q2",
+        "K", "f1", "f2", "n_iter", "algo", "sub_block", "warmup", "early_term", "et_threshold", "ext_scale_q2",
         "frac_bits", "ext_clip", "device", "max_batch")]
 
 
@@ -113,7 +113,7 @@ class TurboDecoder:
     """Batched iterative PCCC decoder handle (tdb200_create / tdb200_destroy)."""
 
     def __init__(self, K, n_iter=8, algo="maxlog_s16", f1=0, f2=0, sub_block=0, warmup=0,
-                 early_term=False, ext_scale_q2=0, frac_bits=0, ext_clip=0, device=0, max_batch=0):
+                 early_term=False, ext_scale_q2=0, frac_bits=0, ext_clip=0, device=0, max_batch=0, et_threshold=0):
         L = load_library()
         cfg = Config()
         _check(L.tdb200_default_config(C.byref(cfg), K))
@@ -121,7 +121,7 @@ class TurboDecoder:
         cfg.algo = ALGO_NAMES[algo] if isinstance(algo, str) else int(algo)
         cfg.sub_block, cfg.warmup, cfg.early_term = sub_block, warmup, int(early_term)
         cfg.ext_scale_q2, cfg.frac_bits, cfg.device, cfg.max_batch = ext_scale_q2, frac_bits, device, max_batch
-        cfg.ext_clip = ext_clip
+        cfg.ext_clip, cfg.et_threshold = ext_clip, et_threshold
         h = C.c_void_p()
         _check(L.tdb200_create(C.byref(cfg), C.byref(h)))
         self._h = h
