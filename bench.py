@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.02)
+            self._halt.wait(0.002)
 
     def stop(self):
         self._halt.set()
@@ -115,7 +115,8 @@ def run_reference(args):
     from turbo_decoder_cuda_b200 import synth
     cores = host_cores()
     decode, kind = cpu_reference_decoder()
-    n_sample = args.ref_sample or max(4 * cores, 8)
+    # a bounded sample per step: ~5 s of CPU work at ~25 ms per codeword and core
+    n_sample = args.ref_sample or min(args.batch, 192 * cores)
     bits, llr = synth.make_batch(K, n_sample, args.ebn0, seed=1000, device="cpu", dtype=torch.float64)
     llr = llr.numpy()
     for _ in range(args.warmup):
@@ -272,7 +273,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()
             decode, kind = cpu_reference_decoder()
-            n_sample = args.ref_sample or max(4 * cores, 8)
+            n_sample = args.ref_sample or min(batch, 512 * cores)  # ~10-15 s of CPU work
             sample = llr[:n_sample].double().cpu().numpy()
             out, secs = decode(sample, cores)
             line["cpu_baseline"] = {
@@ -287,7 +288,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="codeblocks per GPU per step")

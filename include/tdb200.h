@@ -86,7 +86,8 @@ typedef struct tdb200_config {
     int frac_bits;  /* fixed-point fractional bits of TDB200_ALGO_MAXLOG_S16 and of
                        TDB200_LLR_S8 input; 0 = default (3) */
     int ext_clip;   /* TDB200_ALGO_MAXLOG_S16: extrinsic values are clamped to [-(ext_clip+1), ext_clip]
-                       (fixed-point units); ext_clip+1 must be a multiple of 4.  0 = default */
+                       (fixed-point units); ext_clip+1 must be a multiple of 4.
+                       0 = default: 2^(frac_bits+6) - 1, i.e. |Le| < 64 */
     int device;     /* CUDA device ordinal */
     int max_batch;  /* codeblocks the workspace is sized for per launch; larger batches are
                        processed in chunks.  0 = default for the algo */

@@ -21,9 +21,9 @@ def _torch_cuda():
     return torch
 
 
-def _fx_params(K, n_iter, L, G, F=3, q2=3):
+def _fx_params(K, n_iter, L, G, F=3, q2=3, ext_clip=0):
     return FxParams(K=K, n_iter=n_iter, sub_len=L, warmup=G, frac_bits=F,
-                    llr_clip=min((1 << (F + 4)) - 1, 127), ext_clip=(1 << (F + 7)) - 1,
+                    llr_clip=min((1 << (F + 4)) - 1, 127), ext_clip=ext_clip or (1 << (F + 6)) - 1,
                     ext_scale_q2=q2, early_term=0)
 
 
@@ -68,17 +68,17 @@ def test_bit_exact_vs_fixed_point_model(oracle, K, L, G, n_cb, n_iter, ebn0):
     _check(oracle, dec, llr32, llr32, pi, prm, n_cb, K)                             # host path
 
 
-@pytest.mark.parametrize("F,q2", [(4, 3), (3, 4), (2, 3)])
-def test_fixed_point_formats(oracle, F, q2):
+@pytest.mark.parametrize("F,q2,ec", [(4, 3, 0), (3, 4, 0), (2, 3, 0), (3, 3, 63), (3, 3, 1023), (3, 4, 255)])
+def test_fixed_point_formats(oracle, F, q2, ec):
     _torch_cuda()
     from turbo_decoder_cuda_b200 import TurboDecoder
     K, n_cb, n_iter = 1024, 4, 5
     pi = oracle.qpp(K)
     _, llr = oracle.make_batch(K, n_cb, 1.0, seed=31)
     llr32 = llr.astype(np.float32)
-    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16", frac_bits=F, ext_scale_q2=q2)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16", frac_bits=F, ext_scale_q2=q2, ext_clip=ec)
     plan = dec.plan()
-    _check(oracle, dec, llr32, llr32, pi, _fx_params(K, n_iter, plan["sub_block"], plan["warmup"], F, q2), n_cb, K)
+    _check(oracle, dec, llr32, llr32, pi, _fx_params(K, n_iter, plan["sub_block"], plan["warmup"], F, q2, ec), n_cb, K)
 
 
 def test_input_types(oracle):

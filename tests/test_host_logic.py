@@ -80,7 +80,7 @@ def test_synth_matches_oracle_encoder(oracle):
 
 def _fx(K, n_iter, L, G, q2=3, F=3):
     return FxParams(K=K, n_iter=n_iter, sub_len=L, warmup=G, frac_bits=F, llr_clip=127,
-                    ext_clip=(1 << (F + 7)) - 1, ext_scale_q2=q2, early_term=0)
+                    ext_clip=(1 << (F + 6)) - 1, ext_scale_q2=q2, early_term=0)
 
 
 def test_fixed_point_model_is_exact_maxlog_when_unsegmented(oracle):

@@ -266,7 +266,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         if (c.et_threshold == 0) c.et_threshold = 1 << (c.frac_bits + 3);
         if (c.et_threshold < 1 || c.et_threshold > 4096 || (c.et_threshold & (c.et_threshold - 1)))
             return fail(TDB200_ERR_INVALID_ARG, "et_threshold=%d must be a power of two in [1,4096]", c.et_threshold);
-        if (c.ext_clip == 0) c.ext_clip = (1 << (c.frac_bits + 7)) - 1;
+        if (c.ext_clip == 0) c.ext_clip = (1 << (c.frac_bits + 6)) - 1;  // |Le| < 64.0: keeps every metric sum inside int16
         if (c.ext_clip < 63 || c.ext_clip > 2047 || ((c.ext_clip + 1) & 3))
             return fail(TDB200_ERR_INVALID_ARG, "ext_clip=%d: need 63 <= ext_clip <= 2047 and ext_clip+1 a multiple of 4", c.ext_clip);
         // ---- sub-block geometry: K = P * L, L = 8 * NW, P <= 256 threads
