@@ -113,13 +113,23 @@ struct tdb200_decoder {
     void *ws64_block = nullptr;
     FastGeom geom{};
     uint16_t *d_tab2 = nullptr;
-    // staging for TDB200_MEM_HOST callers (one chunk)
-    void *d_in = nullptr;
-    size_t d_in_bytes = 0;
-    uint8_t *d_bits = nullptr;
-    int32_t *d_bits_iters = nullptr;
-    int32_t *d_iters_used = nullptr;
-    void *d_llr1 = nullptr, *d_llr2 = nullptr, *d_ext2 = nullptr;
+    // staging for TDB200_MEM_HOST callers: a ring of kSlots chunks, so that the H2D copy of chunk
+    // i+1, the kernel of chunk i and the D2H copy of chunk i-1 overlap (three internal streams)
+    static constexpr int kSlots = 3;
+    struct Slot {
+        void *d_in = nullptr;
+        size_t d_in_bytes = 0;
+        uint8_t *d_bits = nullptr;
+        int32_t *d_bits_iters = nullptr;
+        int32_t *d_iters_used = nullptr;
+        void *d_llr1 = nullptr, *d_llr2 = nullptr, *d_ext2 = nullptr;
+        cudaEvent_t in_ready = nullptr, k_done = nullptr, out_done = nullptr;
+    } slot[kSlots];
+    int slot_cap = 0;  // codeblocks one slot is sized for
+    cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_start = nullptr;
+    void *siso_in = nullptr, *siso_out = nullptr;  // staging of tdb200_siso_batch (host callers)
+    size_t siso_in_bytes = 0;
     int launches_last = 0;
 };
 
@@ -186,9 +196,19 @@ void tdb200_destroy(tdb200_decoder *d)
 {
     if (!d) return;
     cudaSetDevice(d->cfg.device);
-    cudaFree(d->d_pi); cudaFree(d->d_pi_inv); cudaFree(d->ws64_block); cudaFree(d->d_tab2); cudaFree(d->d_in);
-    cudaFree(d->d_bits); cudaFree(d->d_bits_iters); cudaFree(d->d_iters_used);
-    cudaFree(d->d_llr1); cudaFree(d->d_llr2); cudaFree(d->d_ext2);
+    cudaFree(d->d_pi); cudaFree(d->d_pi_inv); cudaFree(d->ws64_block); cudaFree(d->d_tab2);
+    cudaFree(d->siso_in); cudaFree(d->siso_out);
+    for (auto &sl : d->slot) {
+        cudaFree(sl.d_in); cudaFree(sl.d_bits); cudaFree(sl.d_bits_iters); cudaFree(sl.d_iters_used);
+        cudaFree(sl.d_llr1); cudaFree(sl.d_llr2); cudaFree(sl.d_ext2);
+        if (sl.in_ready) cudaEventDestroy(sl.in_ready);
+        if (sl.k_done) cudaEventDestroy(sl.k_done);
+        if (sl.out_done) cudaEventDestroy(sl.out_done);
+    }
+    if (d->ev_start) cudaEventDestroy(d->ev_start);
+    if (d->s_h2d) cudaStreamDestroy(d->s_h2d);
+    if (d->s_k) cudaStreamDestroy(d->s_k);
+    if (d->s_d2h) cudaStreamDestroy(d->s_d2h);
     delete d;
 }
 
@@ -341,6 +361,51 @@ int tdb200_get_plan(const tdb200_decoder *d, tdb200_plan_info *info)
     return TDB200_OK;
 }
 
+// Lazily create the pipeline objects of a handle (first host-memory call).
+static int ensure_pipeline(tdb200_decoder *d)
+{
+    if (d->s_h2d) return TDB200_OK;
+    TDB_CUDA(cudaStreamCreateWithFlags(&d->s_h2d, cudaStreamNonBlocking));
+    TDB_CUDA(cudaStreamCreateWithFlags(&d->s_k, cudaStreamNonBlocking));
+    TDB_CUDA(cudaStreamCreateWithFlags(&d->s_d2h, cudaStreamNonBlocking));
+    TDB_CUDA(cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming));
+    for (auto &sl : d->slot) {
+        TDB_CUDA(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
+        TDB_CUDA(cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
+        TDB_CUDA(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+    }
+    return TDB200_OK;
+}
+
+// One chunk of n codeblocks, all pointers device pointers, enqueued on st.
+static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int n, uint8_t *v_bits, int32_t *v_bits_iters,
+                        int32_t *v_iters, void *v_llr1, void *v_llr2, void *v_ext2, cudaStream_t st)
+{
+    const tdb200_config &c = d->cfg;
+    if (c.algo == TDB200_ALGO_LOGMAP_F64) {
+        Ref64Args a{};
+        a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.K = c.K; a.n_iter = c.n_iter;
+        a.pi = d->d_pi; a.pi_inv = d->d_pi_inv; a.ws = d->ws64;
+        a.bits = v_bits; a.bits_iters = v_bits_iters;
+        a.llr1 = static_cast<double *>(v_llr1); a.llr2 = static_cast<double *>(v_llr2); a.ext2 = static_cast<double *>(v_ext2);
+        TDB_CUDA(launch_ref64_decode(a, st, &d->launches_last));
+    } else {
+        FastArgs a{};
+        a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.g = d->geom; a.n_iter = c.n_iter;
+        a.frac_bits = c.frac_bits;
+        a.llr_clip = std::min((1 << (c.frac_bits + 4)) - 1, 127);  // systematic values are kept as bytes in shared memory
+        a.ext_lim = c.ext_clip + 1;
+        a.q2 = c.ext_scale_q2; a.early_term = c.early_term; a.et_threshold = c.et_threshold;
+        a.tab2 = d->d_tab2;
+        a.opaque[0] = 0xffffffffu; a.opaque[1] = 4u; a.opaque[2] = 65536u; a.opaque[3] = 0xC0000000u;
+        a.prefetch_stride = d->geom.resident_ctas;
+        a.bits = v_bits; a.iters_used = v_iters;
+        a.llr2 = static_cast<float *>(v_llr2); a.ext2 = static_cast<float *>(v_ext2);
+        TDB_CUDA(launch_fast_s16(a, st, &d->launches_last));
+    }
+    return TDB200_OK;
+}
+
 int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int mem, int n_cb,
                         const tdb200_outputs *out, void *stream)
 {
@@ -355,8 +420,6 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
     TDB_CUDA(cudaSetDevice(c.device));
     const int K = c.K, T = d->T, NL = d->NL;
     const size_t esz = llr_elem_size(llr_type);
-    const bool host = (mem == TDB200_MEM_HOST);
-    const int chunk = c.max_batch;
 
     const bool f64 = (c.algo == TDB200_ALGO_LOGMAP_F64);
     const size_t fsz = f64 ? sizeof(double) : sizeof(float);  // native float type of the LLR outputs
@@ -365,75 +428,84 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
     if (!f64 && c.early_term && out->llr_siso2)
         return fail(TDB200_ERR_UNSUPPORTED, "llr_siso2 is not available with early termination (the stopping iteration is not known in advance)");
 
-    if (host) {
-        int s = ensure(d->d_in, d->d_in_bytes, (size_t)chunk * NL * esz);
-        if (s) return s;
-        if (out->bits && (s = ensure_once(d->d_bits, (size_t)chunk * K))) return s;
-        if (out->bits_iters && (s = ensure_once(d->d_bits_iters, sizeof(int32_t) * (size_t)chunk * c.n_iter * K))) return s;
-        if (out->iters_used && (s = ensure_once(d->d_iters_used, sizeof(int32_t) * (size_t)chunk))) return s;
-        if (out->llr_siso1 && (s = ensure_once(d->d_llr1, 8 * (size_t)chunk * T))) return s;
-        if (out->llr_siso2 && (s = ensure_once(d->d_llr2, 8 * (size_t)chunk * T))) return s;
-        if (out->ext_siso2 && (s = ensure_once(d->d_ext2, 8 * (size_t)chunk * T))) return s;
+    if (mem == TDB200_MEM_DEVICE) {
+        // ---- device buffers: chunks of max_batch (the fp64 workspace is sized for that), all on `stream`
+        for (int c0 = 0; c0 < n_cb; c0 += c.max_batch) {
+            const int n = std::min(c.max_batch, n_cb - c0);
+            int s = launch_chunk(d, static_cast<const char *>(llr) + (size_t)c0 * NL * esz, llr_type, n,
+                                 out->bits ? out->bits + (size_t)c0 * K : nullptr,
+                                 out->bits_iters ? out->bits_iters + (size_t)c0 * c.n_iter * K : nullptr,
+                                 out->iters_used ? out->iters_used + c0 : nullptr,
+                                 out->llr_siso1 ? static_cast<char *>(out->llr_siso1) + fsz * (size_t)c0 * T : nullptr,
+                                 out->llr_siso2 ? static_cast<char *>(out->llr_siso2) + fsz * (size_t)c0 * T : nullptr,
+                                 out->ext_siso2 ? static_cast<char *>(out->ext_siso2) + fsz * (size_t)c0 * T : nullptr, st);
+            if (s) return s;
+        }
+        if (f64 && out->iters_used) {  // the fp64 mode always runs every iteration
+            std::vector<int32_t> v(n_cb, c.n_iter);
+            TDB_CUDA(cudaMemcpyAsync(out->iters_used, v.data(), sizeof(int32_t) * n_cb, cudaMemcpyHostToDevice, st));
+            TDB_CUDA(cudaStreamSynchronize(st));  // v goes out of scope
+        }
+        return TDB200_OK;
     }
 
-    for (int c0 = 0; c0 < n_cb; c0 += chunk) {
-        const int n = std::min(chunk, n_cb - c0);
-        const char *src = static_cast<const char *>(llr) + (size_t)c0 * NL * esz;
-        // device-side views of this chunk
-        const void *v_llr = src;
-        uint8_t *v_bits = out->bits ? out->bits + (size_t)c0 * K : nullptr;
-        int32_t *v_bits_iters = out->bits_iters ? out->bits_iters + (size_t)c0 * c.n_iter * K : nullptr;
-        int32_t *v_iters = out->iters_used ? out->iters_used + c0 : nullptr;
-        char *v_llr1 = out->llr_siso1 ? static_cast<char *>(out->llr_siso1) + fsz * (size_t)c0 * T : nullptr;
-        char *v_llr2 = out->llr_siso2 ? static_cast<char *>(out->llr_siso2) + fsz * (size_t)c0 * T : nullptr;
-        char *v_ext2 = out->ext_siso2 ? static_cast<char *>(out->ext_siso2) + fsz * (size_t)c0 * T : nullptr;
-        if (host) {
-            TDB_CUDA(cudaMemcpyAsync(d->d_in, src, (size_t)n * NL * esz, cudaMemcpyHostToDevice, st));
-            v_llr = d->d_in;
-            if (v_bits) v_bits = d->d_bits;
-            if (v_bits_iters) v_bits_iters = d->d_bits_iters;
-            if (v_iters) v_iters = d->d_iters_used;
-            if (v_llr1) v_llr1 = static_cast<char *>(d->d_llr1);
-            if (v_llr2) v_llr2 = static_cast<char *>(d->d_llr2);
-            if (v_ext2) v_ext2 = static_cast<char *>(d->d_ext2);
-        }
-        if (f64) {
-            Ref64Args a{};
-            a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.K = K; a.n_iter = c.n_iter;
-            a.pi = d->d_pi; a.pi_inv = d->d_pi_inv; a.ws = d->ws64;
-            a.bits = v_bits; a.bits_iters = v_bits_iters;
-            a.llr1 = reinterpret_cast<double *>(v_llr1); a.llr2 = reinterpret_cast<double *>(v_llr2);
-            a.ext2 = reinterpret_cast<double *>(v_ext2);
-            TDB_CUDA(launch_ref64_decode(a, st, &d->launches_last));
-            if (v_iters) {  // the fp64 mode always runs every iteration
-                std::vector<int32_t> v(n, c.n_iter);
-                TDB_CUDA(cudaMemcpyAsync(v_iters, v.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-                TDB_CUDA(cudaStreamSynchronize(st));  // v goes out of scope
-            }
-        } else {
-            FastArgs a{};
-            a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.g = d->geom; a.n_iter = c.n_iter;
-            a.frac_bits = c.frac_bits;
-            a.llr_clip = std::min((1 << (c.frac_bits + 4)) - 1, 127);  // systematic values are kept as int8 pairs in shared memory
-            a.ext_lim = c.ext_clip + 1;
-            a.q2 = c.ext_scale_q2; a.early_term = c.early_term; a.et_threshold = c.et_threshold;
-            a.tab2 = d->d_tab2;
-            a.opaque[0] = 0xffffffffu; a.opaque[1] = 4u; a.opaque[2] = 65536u; a.opaque[3] = 0xC0000000u;
-            a.prefetch_stride = d->geom.resident_ctas;
-            a.bits = v_bits; a.iters_used = v_iters;
-            a.llr2 = reinterpret_cast<float *>(v_llr2); a.ext2 = reinterpret_cast<float *>(v_ext2);
-            TDB_CUDA(launch_fast_s16(a, st, &d->launches_last));
-        }
-        if (host) {
-            if (out->bits) TDB_CUDA(cudaMemcpyAsync(out->bits + (size_t)c0 * K, d->d_bits, (size_t)n * K, cudaMemcpyDeviceToHost, st));
-            if (out->bits_iters) TDB_CUDA(cudaMemcpyAsync(out->bits_iters + (size_t)c0 * c.n_iter * K, d->d_bits_iters, sizeof(int32_t) * (size_t)n * c.n_iter * K, cudaMemcpyDeviceToHost, st));
-            if (out->iters_used) TDB_CUDA(cudaMemcpyAsync(out->iters_used + c0, d->d_iters_used, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-            if (out->llr_siso1) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->llr_siso1) + fsz * (size_t)c0 * T, d->d_llr1, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, st));
-            if (out->llr_siso2) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->llr_siso2) + fsz * (size_t)c0 * T, d->d_llr2, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, st));
-            if (out->ext_siso2) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->ext_siso2) + fsz * (size_t)c0 * T, d->d_ext2, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, st));
-            TDB_CUDA(cudaStreamSynchronize(st));  // staging buffers are reused by the next chunk
-        }
+    // ---- host buffers: a three-stage pipeline over chunks of `cap` codeblocks.  With pinned host
+    //      memory the H2D copy of chunk i+1, the kernel of chunk i and the D2H copy of chunk i-1
+    //      run concurrently; with pageable memory the copies serialise but the result is the same.
+    int s = ensure_pipeline(d);
+    if (s) return s;
+    if (d->slot_cap == 0) {
+        // about eight chunks per max_batch, at least one full wave of CTAs for the throughput kernel
+        int cap = std::max(64, c.max_batch / 8);
+        if (!f64) cap = std::max(cap, 2 * std::max(d->geom.resident_ctas, 1));
+        d->slot_cap = std::min(cap, c.max_batch);
     }
+    const int cap = d->slot_cap;
+    for (auto &sl : d->slot) {
+        if ((s = ensure(sl.d_in, sl.d_in_bytes, (size_t)cap * NL * esz))) return s;
+        if (out->bits && (s = ensure_once(sl.d_bits, (size_t)cap * K))) return s;
+        if (out->bits_iters && (s = ensure_once(sl.d_bits_iters, sizeof(int32_t) * (size_t)cap * c.n_iter * K))) return s;
+        if (out->iters_used && !f64 && (s = ensure_once(sl.d_iters_used, sizeof(int32_t) * (size_t)cap))) return s;
+        if (out->llr_siso1 && (s = ensure_once(sl.d_llr1, 8 * (size_t)cap * T))) return s;
+        if (out->llr_siso2 && (s = ensure_once(sl.d_llr2, 8 * (size_t)cap * T))) return s;
+        if (out->ext_siso2 && (s = ensure_once(sl.d_ext2, 8 * (size_t)cap * T))) return s;
+    }
+    // work already queued on the caller's stream comes first
+    TDB_CUDA(cudaEventRecord(d->ev_start, st));
+    TDB_CUDA(cudaStreamWaitEvent(d->s_h2d, d->ev_start, 0));
+    TDB_CUDA(cudaStreamWaitEvent(d->s_k, d->ev_start, 0));
+    TDB_CUDA(cudaStreamWaitEvent(d->s_d2h, d->ev_start, 0));
+    int i = 0;
+    for (int c0 = 0; c0 < n_cb; c0 += cap, i++) {
+        const int n = std::min(cap, n_cb - c0);
+        tdb200_decoder::Slot &sl = d->slot[i % tdb200_decoder::kSlots];
+        const bool reused = i >= tdb200_decoder::kSlots;
+        if (reused) TDB_CUDA(cudaStreamWaitEvent(d->s_h2d, sl.k_done, 0));  // the kernel that read this slot's input
+        TDB_CUDA(cudaMemcpyAsync(sl.d_in, static_cast<const char *>(llr) + (size_t)c0 * NL * esz, (size_t)n * NL * esz,
+                                 cudaMemcpyHostToDevice, d->s_h2d));
+        TDB_CUDA(cudaEventRecord(sl.in_ready, d->s_h2d));
+        TDB_CUDA(cudaStreamWaitEvent(d->s_k, sl.in_ready, 0));
+        if (reused) TDB_CUDA(cudaStreamWaitEvent(d->s_k, sl.out_done, 0));  // the copy-out of this slot's previous results
+        s = launch_chunk(d, sl.d_in, llr_type, n, out->bits ? sl.d_bits : nullptr, out->bits_iters ? sl.d_bits_iters : nullptr,
+                         (out->iters_used && !f64) ? sl.d_iters_used : nullptr, out->llr_siso1 ? sl.d_llr1 : nullptr,
+                         out->llr_siso2 ? sl.d_llr2 : nullptr, out->ext_siso2 ? sl.d_ext2 : nullptr, d->s_k);
+        if (s) return s;
+        TDB_CUDA(cudaEventRecord(sl.k_done, d->s_k));
+        TDB_CUDA(cudaStreamWaitEvent(d->s_d2h, sl.k_done, 0));
+        cudaStream_t so = d->s_d2h;
+        if (out->bits) TDB_CUDA(cudaMemcpyAsync(out->bits + (size_t)c0 * K, sl.d_bits, (size_t)n * K, cudaMemcpyDeviceToHost, so));
+        if (out->bits_iters) TDB_CUDA(cudaMemcpyAsync(out->bits_iters + (size_t)c0 * c.n_iter * K, sl.d_bits_iters, sizeof(int32_t) * (size_t)n * c.n_iter * K, cudaMemcpyDeviceToHost, so));
+        if (out->iters_used && !f64) TDB_CUDA(cudaMemcpyAsync(out->iters_used + c0, sl.d_iters_used, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, so));
+        if (out->llr_siso1) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->llr_siso1) + fsz * (size_t)c0 * T, sl.d_llr1, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, so));
+        if (out->llr_siso2) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->llr_siso2) + fsz * (size_t)c0 * T, sl.d_llr2, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, so));
+        if (out->ext_siso2) TDB_CUDA(cudaMemcpyAsync(static_cast<char *>(out->ext_siso2) + fsz * (size_t)c0 * T, sl.d_ext2, fsz * (size_t)n * T, cudaMemcpyDeviceToHost, so));
+        TDB_CUDA(cudaEventRecord(sl.out_done, so));
+    }
+    // results are in the caller's memory when this returns; the caller's stream is ordered after them
+    for (int k = 0; k < std::min(i, (int)tdb200_decoder::kSlots); k++) TDB_CUDA(cudaStreamWaitEvent(st, d->slot[k].out_done, 0));
+    TDB_CUDA(cudaStreamSynchronize(d->s_d2h));
+    if (f64 && out->iters_used)
+        for (int k = 0; k < n_cb; k++) out->iters_used[k] = c.n_iter;  // the fp64 mode always runs every iteration
     return TDB200_OK;
 }
 
@@ -450,25 +522,25 @@ int tdb200_siso_batch(tdb200_decoder *d, const double *recs, const double *La, i
     const int T = d->T, chunk = d->cfg.max_batch;
     const bool host = (mem == TDB200_MEM_HOST);
     if (host) {
-        int s = ensure(d->d_in, d->d_in_bytes, (size_t)chunk * d->NL * 8);  // >= 3T doubles per codeblock
+        int s = ensure(d->siso_in, d->siso_in_bytes, (size_t)chunk * 3 * T * 8);
         if (s) return s;
-        if ((s = ensure_once(d->d_llr1, 8 * (size_t)chunk * T))) return s;
+        if ((s = ensure_once(d->siso_out, 8 * (size_t)chunk * T))) return s;
     }
     for (int c0 = 0; c0 < n_cb; c0 += chunk) {
         const int n = std::min(chunk, n_cb - c0);
         Ref64SisoArgs a{};
         a.terminated = terminated; a.n_cb = n; a.T = T; a.ws = d->ws64;
         if (host) {
-            double *din = static_cast<double *>(d->d_in);
+            double *din = static_cast<double *>(d->siso_in);
             TDB_CUDA(cudaMemcpyAsync(din, recs + (size_t)c0 * 2 * T, 8 * (size_t)n * 2 * T, cudaMemcpyHostToDevice, st));
             TDB_CUDA(cudaMemcpyAsync(din + (size_t)chunk * 2 * T, La + (size_t)c0 * T, 8 * (size_t)n * T, cudaMemcpyHostToDevice, st));
-            a.recs = din; a.La = din + (size_t)chunk * 2 * T; a.LLR = static_cast<double *>(d->d_llr1);
+            a.recs = din; a.La = din + (size_t)chunk * 2 * T; a.LLR = static_cast<double *>(d->siso_out);
         } else {
             a.recs = recs + (size_t)c0 * 2 * T; a.La = La + (size_t)c0 * T; a.LLR = LLR + (size_t)c0 * T;
         }
         TDB_CUDA(launch_ref64_siso(a, st, &d->launches_last));
         if (host) {
-            TDB_CUDA(cudaMemcpyAsync(LLR + (size_t)c0 * T, d->d_llr1, 8 * (size_t)n * T, cudaMemcpyDeviceToHost, st));
+            TDB_CUDA(cudaMemcpyAsync(LLR + (size_t)c0 * T, d->siso_out, 8 * (size_t)n * T, cudaMemcpyDeviceToHost, st));
             TDB_CUDA(cudaStreamSynchronize(st));
         }
     }
