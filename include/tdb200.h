@@ -49,9 +49,11 @@ typedef enum tdb200_algo {
     /* max-log-MAP in packed 16-bit fixed point (two codeblocks per 32-bit lane), sub-block
      * parallel with boundary-state initialisation.  The throughput mode. */
     TDB200_ALGO_MAXLOG_S16 = 1,
-    /* fp32 Log-MAP (max* with the exact Jacobian correction), sub-block parallel. */
+    /* fp32 Log-MAP: max*(x,y) = max + ln(1+e^-|x-y|) evaluated exactly (the reference tabulates the
+     * same correction in 16 steps), sub-block parallel with boundary-state initialisation -- the
+     * windowed Log-MAP.  One codeblock per CTA; extrinsic scale 1.0 as in the reference. */
     TDB200_ALGO_LOGMAP_F32 = 2,
-    /* fp32 max-log-MAP, sub-block parallel. */
+    /* fp32 max-log-MAP on the same structure (extrinsic scale 0.75 by default). */
     TDB200_ALGO_MAXLOG_F32 = 3
 } tdb200_algo;
 

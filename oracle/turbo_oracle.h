@@ -99,6 +99,27 @@ typedef struct tdo_fx_params {
 int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                   int *bits_out, int *le_out, int *overflow);
 
+/* ------------------------------------------------------------------------
+ * fp32 specification of the sub-block-parallel Log-MAP / max-log kernels
+ * (TDB200_ALGO_LOGMAP_F32 / TDB200_ALGO_MAXLOG_F32), turbo_oracle_f32.c.
+ * ---------------------------------------------------------------------- */
+typedef struct tdo_f32_params {
+    int K;
+    int n_iter;
+    int sub_len;        /* L */
+    int warmup;         /* G */
+    int logmap;         /* 1: max* with the exact correction, 0: max */
+    int early_term;
+    float ext_scale;    /* 1.0 (Log-MAP) / 0.75 (max-log) */
+    float ext_clamp;    /* |Le| clamp */
+    float et_threshold; /* LLR units */
+} tdo_f32_params;
+
+/* Returns the iterations run.  bits_out[K]; llr_out / le_out (may be NULL): last SISO-2
+ * a-posteriori / scaled extrinsic, K values in SISO-2 (interleaved) order. */
+int tdo_f32_decode(const float *llr_in, const int *pi, const tdo_f32_params *p,
+                   int *bits_out, float *llr_out, float *le_out);
+
 #ifdef __cplusplus
 }
 #endif

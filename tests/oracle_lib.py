@@ -46,6 +46,11 @@ class FxParams(C.Structure):
         "ext_scale_q2", "early_term", "et_threshold")]
 
 
+class F32Params(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("K", "n_iter", "sub_len", "warmup", "logmap", "early_term")] + \
+               [(n, C.c_float) for n in ("ext_scale", "ext_clamp", "et_threshold")]
+
+
 def _opt(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -72,6 +77,8 @@ class Oracle:
         L.tdo_turbo_decode_batch.restype = C.c_double
         L.tdo_fx_decode.argtypes = [_fp, _ip, C.POINTER(FxParams), _ip, C.c_void_p, C.c_void_p]
         L.tdo_fx_decode.restype = C.c_int
+        L.tdo_f32_decode.argtypes = [_fp, _ip, C.POINTER(F32Params), _ip, C.c_void_p, C.c_void_p]
+        L.tdo_f32_decode.restype = C.c_int
 
     # ---- constants
     def trellis(self):
@@ -158,6 +165,16 @@ class Oracle:
         it = self.lib.tdo_fx_decode(np.ascontiguousarray(llr_f32, np.float32), pi, C.byref(params),
                                     bits, _opt(le), C.cast(C.byref(ovf), C.c_void_p))
         return bits, le, it, ovf.value
+
+
+    def f32_decode(self, llr_f32, pi, params, want_soft=False):
+        """fp32 windowed Log-MAP / max-log model: (bits, llr, le, iterations); soft values in SISO-2 order."""
+        K = len(pi)
+        bits = np.zeros(K, np.int32)
+        llr = np.zeros(K, np.float32) if want_soft else None
+        le = np.zeros(K, np.float32) if want_soft else None
+        it = self.lib.tdo_f32_decode(np.ascontiguousarray(llr_f32, np.float32), pi, C.byref(params), bits, _opt(llr), _opt(le))
+        return bits, llr, le, it
 
 
 class RefLib:

@@ -59,10 +59,11 @@ def main():
     decs = []
     for name, kw in cfgs:
         kw = dict(kw)
+        limit = kw.pop("frames", None)   # per-configuration cap on the frames per point (slow modes)
         kw.setdefault("n_iter", 8)
         kw.setdefault("algo", "maxlog_s16")
         kw.setdefault("max_batch", args.chunk)
-        decs.append((name, kw, TurboDecoder(args.K, **kw)))
+        decs.append((name, dict(kw, frames=limit), TurboDecoder(args.K, **kw)))
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "a") as f:
         for eb in args.ebn0:
@@ -73,11 +74,11 @@ def main():
                 n = min(args.chunk, args.n - done)
                 bits, llr = synth.make_batch(args.K, n, eb, seed=args.seed * 100003 + ci, device=dev)
                 for name, kw, dec in decs:
-                    slow = kw["algo"] == "logmap_f64"
-                    if slow and acc[name][2] >= args.n_slow:
+                    cap = kw.get("frames") or (args.n_slow if kw["algo"] == "logmap_f64" else args.n)
+                    if acc[name][2] >= cap:
                         continue
-                    m = min(n, args.n_slow - acc[name][2]) if slow else n
-                    x = llr[:m].double() if slow else llr[:m]
+                    m = min(n, cap - acc[name][2])
+                    x = llr[:m].double() if kw["algo"] == "logmap_f64" else llr[:m]
                     want = ("bits", "iters_used") if kw.get("early_term") else ("bits",)
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
@@ -97,7 +98,7 @@ def main():
                 be, fe, nf, its, secs = acc[name]
                 lo, hi = wilson(fe, nf)
                 plan = dec.plan()
-                line = {"K": args.K, "ebn0_db": eb, "cfg": name, "params": kw, "sub_block": plan["sub_block"],
+                line = {"K": args.K, "ebn0_db": eb, "cfg": name, "params": {k: v for k, v in kw.items() if v is not None}, "sub_block": plan["sub_block"],
                         "guard": plan["warmup"], "frames": nf, "bit_errors": be, "frame_errors": fe,
                         "ber": be / (nf * args.K), "fer": fe / nf, "fer_ci95": [lo, hi],
                         "mean_iters": its / nf, "gbit_s_incl_sync": nf * args.K / secs / 1e9}

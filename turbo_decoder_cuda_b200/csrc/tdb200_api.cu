@@ -277,11 +277,12 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         w.alpha = p; p += 8 * (T + 1) * nb;
         w.beta = p; p += 8 * (T + 1) * nb;
         w.max_batch = c.max_batch;
-    } else if (c.algo == TDB200_ALGO_MAXLOG_S16) {
+    } else if (c.algo == TDB200_ALGO_MAXLOG_S16 || c.algo == TDB200_ALGO_LOGMAP_F32 || c.algo == TDB200_ALGO_MAXLOG_F32) {
+        const bool s16 = (c.algo == TDB200_ALGO_MAXLOG_S16);
         if (c.max_batch <= 0) c.max_batch = 16384;
         if (c.frac_bits == 0) c.frac_bits = 3;
         if (c.frac_bits < 1 || c.frac_bits > 4) return fail(TDB200_ERR_INVALID_ARG, "frac_bits=%d out of range [1,4]", c.frac_bits);
-        if (c.ext_scale_q2 == 0) c.ext_scale_q2 = 3;
+        if (c.ext_scale_q2 == 0) c.ext_scale_q2 = (c.algo == TDB200_ALGO_LOGMAP_F32) ? 4 : 3;
         if (c.ext_scale_q2 != 3 && c.ext_scale_q2 != 4) return fail(TDB200_ERR_INVALID_ARG, "ext_scale_q2=%d (3 or 4)", c.ext_scale_q2);
         if (c.et_threshold == 0) c.et_threshold = 1 << (c.frac_bits + 3);
         if (c.et_threshold < 1 || c.et_threshold > 4096 || (c.et_threshold & (c.et_threshold - 1)))
@@ -310,11 +311,12 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         g.PP = g.P | 1;  // odd row pitch: de-multiplex stores spread over the banks, walks stay conflict-free
         g.threads = ((g.P + 31) / 32) * 32;
         g.n_ckpt = std::max(g.NW - 2, 0);
-        g.smem_bytes = fast_s16_smem_bytes(g);
+        g.smem_bytes = s16 ? fast_s16_smem_bytes(g) : f32_smem_bytes(g);
         if ((size_t)g.smem_bytes > prop.sharedMemPerBlockOptin)
             return fail(TDB200_ERR_UNSUPPORTED, "plan needs %d B of shared memory per CTA, device allows %zu", g.smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
         c.sub_block = L; c.warmup = g.G;
-        TDB_CUDA(fast_s16_configure(g, d->sm_count));
+        if (s16) TDB_CUDA(fast_s16_configure(g, d->sm_count));
+        else TDB_CUDA(f32_configure(g));
         // word address of element pi(tL+j), stored at j*PP+t
         std::vector<uint16_t> tab((size_t)L * g.PP, 0);
         for (int i = 0; i < K; i++) {
@@ -324,7 +326,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         TDB_CUDA(cudaMalloc(&d->d_tab2, sizeof(uint16_t) * tab.size()));
         TDB_CUDA(cudaMemcpy(d->d_tab2, tab.data(), sizeof(uint16_t) * tab.size(), cudaMemcpyHostToDevice));
     } else {
-        return fail(TDB200_ERR_UNSUPPORTED, "algo %d is not built into this library yet", c.algo);
+        return fail(TDB200_ERR_INVALID_ARG, "algo=%d", c.algo);
     }
     return TDB200_OK;
 }
@@ -356,7 +358,8 @@ int tdb200_get_plan(const tdb200_decoder *d, tdb200_plan_info *info)
         info->sub_block = d->cfg.K; info->n_sub_blocks = 1; info->cb_per_cta = 8; info->threads_per_cta = 64;
     } else {
         info->sub_block = d->geom.L; info->n_sub_blocks = d->geom.P; info->warmup = d->geom.G;
-        info->cb_per_cta = 2; info->threads_per_cta = d->geom.threads; info->smem_bytes = d->geom.smem_bytes;
+        info->cb_per_cta = (d->cfg.algo == TDB200_ALGO_MAXLOG_S16) ? 2 : 1;
+        info->threads_per_cta = d->geom.threads; info->smem_bytes = d->geom.smem_bytes;
     }
     return TDB200_OK;
 }
@@ -389,6 +392,18 @@ static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int 
         a.bits = v_bits; a.bits_iters = v_bits_iters;
         a.llr1 = static_cast<double *>(v_llr1); a.llr2 = static_cast<double *>(v_llr2); a.ext2 = static_cast<double *>(v_ext2);
         TDB_CUDA(launch_ref64_decode(a, st, &d->launches_last));
+    } else if (c.algo != TDB200_ALGO_MAXLOG_S16) {
+        F32Args a{};
+        a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.g = d->geom; a.n_iter = c.n_iter;
+        a.logmap = (c.algo == TDB200_ALGO_LOGMAP_F32);
+        a.ext_scale = 0.25f * (float)c.ext_scale_q2;
+        a.ext_clamp = 1.0e6f;  // the fp32 modes do not clamp the extrinsic (the reference does not either)
+        a.early_term = c.early_term;
+        a.et_threshold = (float)c.et_threshold / (float)(1 << c.frac_bits);
+        a.tab2 = d->d_tab2;
+        a.bits = v_bits; a.iters_used = v_iters;
+        a.llr2 = static_cast<float *>(v_llr2); a.ext2 = static_cast<float *>(v_ext2);
+        TDB_CUDA(launch_f32(a, st, &d->launches_last));
     } else {
         FastArgs a{};
         a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.g = d->geom; a.n_iter = c.n_iter;

@@ -105,6 +105,27 @@ struct FastArgs {
     int32_t *iters_used;
     float *llr2, *ext2;  // [n_cb][K+3]
 };
+// ------------------------------------------------------------------ fp32 sub-block-parallel path
+struct F32Args {
+    const void *llr;  // [n_cb][3K+12] device
+    int llr_type;
+    int n_cb;
+    FastGeom g;       // same geometry rules as the int16 kernel, one codeblock per CTA
+    int n_iter;
+    int logmap;       // 1: max* with the exact correction, 0: max
+    float ext_scale;  // 1.0 (Log-MAP) or 0.75 (max-log)
+    float ext_clamp;  // |Le| clamp (LLR units)
+    int early_term;
+    float et_threshold;    // LLR units
+    const uint16_t *tab2;  // [L*PP] device: smem word of element pi(tL+j), stored at index j*PP+t
+    uint8_t *bits;
+    int32_t *iters_used;
+    float *llr2, *ext2;  // [n_cb][K+3]
+};
+cudaError_t f32_configure(const FastGeom &g);
+cudaError_t launch_f32(const F32Args &a, cudaStream_t st, int *n_launches);
+int f32_smem_bytes(const FastGeom &g);
+
 cudaError_t fast_s16_configure(FastGeom &g, int sm_count);  // opt in to the dynamic shared memory size
 cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches);
 int fast_s16_smem_bytes(const FastGeom &g);
