@@ -1,0 +1,75 @@
+"""BER/FER parity against the reference's own published curve (BASELINE configs[2]).
+
+Golden data: ITTC/result.txt:102-116 of the reference -- block error rate of its CPU Log-MAP,
+K = 6144, per iteration (rows) and Eb/N0 = 0.0 ... 1.0 dB in 0.1 dB steps (columns).  Row 8 (8
+iterations) reads 0.9733 0.7746 0.3800 0.0875 0.00937 0.00052 0.00004 ...  The run stopped a point
+after 50 block errors at the LAST (15th) iteration or 100 000 frames (ITTC/main.cpp:239-243), which
+fixes the frame counts behind those numbers: 17 639 frames at 0.3 dB, 100 000 from 0.4 dB on.
+The decoders here see true Gaussian noise, the reference a 12-term CLT approximation
+(log_map.cpp:1359-1392); at these error rates the difference is inside the intervals used below.
+"""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REF_BLER_8IT = {0.3: (0.0874766143, 17639), 0.4: (0.00937, 100000), 0.5: (0.00052, 100000)}
+
+
+def _fer(algo, ebn0, n, **kw):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from turbo_decoder_cuda_b200 import TurboDecoder, synth
+    dev = torch.device("cuda", 0)
+    K = 6144
+    dec = TurboDecoder(K, n_iter=8, algo=algo, max_batch=4096, **kw)
+    fe = 0
+    for ci, c0 in enumerate(range(0, n, 4096)):
+        m = min(4096, n - c0)
+        bits, llr = synth.make_batch(K, m, ebn0, seed=1234 + 17 * ci + int(100 * ebn0), device=dev)
+        x = llr.double() if algo == "logmap_f64" else llr
+        out = dec.decode(x, want=("bits",))
+        fe += int(((out["bits"] != bits).sum(dim=1) > 0).sum().item())
+    return fe / n
+
+
+def _within(fer, n, ebn0, k=3.5):
+    """|ours - reference| within k standard deviations of the difference of two binomial estimates."""
+    p_ref, n_ref = REF_BLER_8IT[ebn0]
+    sd = math.sqrt(p_ref * (1 - p_ref) / n_ref + max(fer, p_ref) * (1 - max(fer, p_ref)) / n)
+    return abs(fer - p_ref) <= k * sd, sd
+
+
+@pytest.mark.parametrize("ebn0,n", [(0.3, 8192), (0.4, 32768)])
+def test_windowed_logmap_f32_on_reference_curve(ebn0, n):
+    """Sub-block-parallel Log-MAP (128 sub-blocks of 48 steps, guard 16) against the reference's
+    unsegmented CPU Log-MAP."""
+    fer = _fer("logmap_f32", ebn0, n)
+    ok, sd = _within(fer, n, ebn0)
+    assert ok, "FER %.4g vs reference %.4g (sd %.2g)" % (fer, REF_BLER_8IT[ebn0][0], sd)
+
+
+def test_long_windows_on_reference_curve():
+    """Windows of 128 steps with guard 32 are indistinguishable from the unsegmented recursion."""
+    fer = _fer("logmap_f32", 0.4, 32768, sub_block=128, warmup=32)
+    ok, sd = _within(fer, 32768, 0.4)
+    assert ok, "FER %.4g vs reference %.4g (sd %.2g)" % (fer, REF_BLER_8IT[0.4][0], sd)
+
+
+def test_reference_order_fp64_on_reference_curve():
+    fer = _fer("logmap_f64", 0.3, 2048)
+    ok, sd = _within(fer, 2048, 0.3)
+    assert ok, "FER %.4g vs reference %.4g (sd %.2g)" % (fer, REF_BLER_8IT[0.3][0], sd)
+
+
+def test_maxlog_s16_loss_is_bounded():
+    """Scaled max-log-MAP in 16-bit fixed point is NOT on the Log-MAP curve (the known max-log loss,
+    about 0.15 dB here); it must stay within 0.2 dB: its FER at 0.6 dB is below the reference's at 0.4 dB."""
+    fer = _fer("maxlog_s16", 0.6, 16384)
+    assert fer < REF_BLER_8IT[0.4][0], fer
+    # reference at 0.8 / 0.9 dB: 1e-5 / 2e-5 (result.txt:109); 0.15 dB to the right of that, 16384 frames
+    # hold 0.2 block errors on average -- more than two would be a different curve
+    assert _fer("maxlog_s16", 1.0, 16384) <= 2.0 / 16384

@@ -160,3 +160,26 @@ def test_decodes_clean_codewords(oracle):
     dec = TurboDecoder(K, n_iter=8, algo="maxlog_s16")
     out = dec.decode(torch.from_numpy(llr.astype(np.float32)).cuda(), want=("bits",))
     assert np.array_equal(out["bits"].cpu().numpy(), bits.astype(np.uint8))
+
+
+def test_every_lte_block_size(oracle):
+    """BASELINE configs[3], correctness side: all 188 LTE block sizes (K = 40 ... 6144) decode
+    bit-exactly against the integer model with the library's own plan for that K."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    sizes = oracle.lte_sizes()
+    assert len(sizes) == 188 and sizes[0] == 40 and sizes[-1] == 6144
+    n_iter = 3
+    for K in sizes:
+        pi = oracle.qpp(K)
+        bits, llr = oracle.make_batch(K, 3, 1.5, seed=K)       # odd batch: one CTA runs half empty
+        llr32 = llr.astype(np.float32)
+        dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16", max_batch=4)
+        plan = dec.plan()
+        assert plan["sub_block"] * plan["n_sub_blocks"] == K
+        out = dec.decode(llr32, want=("bits",))
+        prm = _fx_params(K, n_iter, plan["sub_block"], plan["warmup"])
+        for c in (0, 2):
+            b, _, _, ovf = oracle.fx_decode(llr32[c], pi, prm)
+            assert ovf == 0 and np.array_equal(out["bits"][c], b.astype(np.uint8)), "K=%d cb %d" % (K, c)
+        dec.close()
