@@ -534,30 +534,29 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     const int clip = A.llr_clip;
 
     // ---- load + quantise + de-multiplex (once per decode); element n = tt*L + j -> word j*PP + tt.
-    //      Two groups of loads are in flight per thread before the first is consumed.
+    //      NG groups of loads (NG x 2 codeblocks x 48 bytes) are in flight per thread before the
+    //      first is consumed: the phase is pure load latency, so depth is what shortens it.
     {
+        constexpr int NG = (LLR_T == TDB200_LLR_F64) ? 2 : 4;
         const w32 clipv = dup2(clip), nclipv = dup2(-clip);
         const int nq = K / 4;
-        int q = tid;
-        for (; q + nthr < nq; q += 2 * nthr) {
-            Raw12<LLR_T> ra0, rb0, ra1, rb1;
-            load12<LLR_T>(A.llr, row, cbA, q, ra0);
-            load12<LLR_T>(A.llr, row, cbB, q, rb0);
-            load12<LLR_T>(A.llr, row, cbA, q + nthr, ra1);
-            load12<LLR_T>(A.llr, row, cbB, q + nthr, rb1);
-            w32 v[12];
-            pack12<LLR_T>(ra0, rb0, scale, clipv, nclipv, v);
-            put4(sm, q, L, PP, v);
-            pack12<LLR_T>(ra1, rb1, scale, clipv, nclipv, v);
-            put4(sm, q + nthr, L, PP, v);
-        }
-        if (q < nq) {
-            Raw12<LLR_T> ra, rb;
-            load12<LLR_T>(A.llr, row, cbA, q, ra);
-            load12<LLR_T>(A.llr, row, cbB, q, rb);
-            w32 v[12];
-            pack12<LLR_T>(ra, rb, scale, clipv, nclipv, v);
-            put4(sm, q, L, PP, v);
+        for (int q0 = tid; q0 < nq; q0 += NG * nthr) {
+            Raw12<LLR_T> ra[NG], rb[NG];
+#pragma unroll
+            for (int j = 0; j < NG; j++) {
+                const int q = min(q0 + j * nthr, nq - 1);  // the clamp re-reads the last group instead of branching
+                load12<LLR_T>(A.llr, row, cbA, q, ra[j]);
+                load12<LLR_T>(A.llr, row, cbB, q, rb[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < NG; j++) {
+                const int q = q0 + j * nthr;
+                if (q < nq) {
+                    w32 v[12];
+                    pack12<LLR_T>(ra[j], rb[j], scale, clipv, nclipv, v);
+                    put4(sm, q, L, PP, v);
+                }
+            }
         }
     }
     {   // QPP table: 128-bit loads (the table and the shared-memory array are 16-byte aligned)
