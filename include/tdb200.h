@@ -139,6 +139,19 @@ int tdb200_decode_batch(tdb200_decoder *dec, const void *llr, int llr_type, int 
 int tdb200_siso_batch(tdb200_decoder *dec, const double *recs, const double *La, int terminated,
                       double *LLR, int mem, int n_cb, void *stream);
 
+/* ---- the caller side of the path, for harnesses that keep everything on the device -------------
+ * Replaces TurboEnCoding(int *source, int *coded_source, int source_length) (ITTC/main.h:14,
+ * log_map.cpp:700-730) for a batch: bits [n_cb][K] (one byte per bit) -> coded [n_cb][3K+12] in the
+ * reference's multiplex order, (13,15)_8 PCCC with trellis termination.  Bit-exact with the reference. */
+int tdb200_encode_batch(tdb200_decoder *dec, const uint8_t *bits, uint8_t *coded, int mem, int n_cb, void *stream);
+
+/* Replaces module() (BPSK) + AWGN() + demodule() (ITTC/main.cpp:197-202): coded [n_cb][3K+12] bits ->
+ * llr [n_cb][3K+12] = 2 r / sigma^2, r = (2c-1) + sigma * n.  n is standard normal from Philox4x32-10,
+ * a pure function of (seed, element index) -- the reference's 12-term CLT noise seeded from time() is
+ * not reproducible, so the agreement is statistical.  llr_type: TDB200_LLR_F32 or TDB200_LLR_F64. */
+int tdb200_channel_batch(tdb200_decoder *dec, const uint8_t *coded, void *llr, int llr_type, int mem, int n_cb,
+                         double sigma, uint64_t seed, void *stream);
+
 /* Introspection (what the plan resolved to). */
 typedef struct tdb200_plan_info {
     int K, f1, f2, n_iter, algo;

@@ -1,0 +1,82 @@
+"""GPU tests of the caller side of the path kept on the device: tdb200_encode_batch
+(TurboEnCoding, ITTC/log_map.cpp:700-730) bit-exact against the oracle's restatement and, where the
+reference build travelled (oracle/_ref), against the reference itself; tdb200_channel_batch
+(module + AWGN + demodule, ITTC/main.cpp:197-202) by its statistics."""
+import numpy as np
+import pytest
+
+from oracle_lib import RefLib
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch
+
+
+@pytest.mark.parametrize("K", [40, 48, 104, 512, 1008, 2048, 4160, 6144])
+def test_encoder_bit_exact(oracle, K):
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    rng = np.random.default_rng(K)
+    n_cb = 5
+    bits = rng.integers(0, 2, size=(n_cb, K), dtype=np.uint8)
+    bits[0] = 0
+    bits[0, 0] = 1          # impulse: the reference's known answer 111011011011... / tail 000111000111 for K = 6144
+    bits[1] = 1
+    pi = oracle.qpp(K)
+    dec = TurboDecoder(K, algo="maxlog_s16", max_batch=8)
+    dev_out = dec.encode(torch.from_numpy(bits).cuda()).cpu().numpy()
+    host_out = dec.encode(bits)
+    ref = RefLib(K, *oracle.lte_params(K)) if RefLib.available() else None
+    for c in range(n_cb):
+        want = oracle.encode(bits[c].astype(np.int32), pi).astype(np.uint8)
+        assert np.array_equal(dev_out[c], want), "device path, cb %d" % c
+        assert np.array_equal(host_out[c], want), "host path, cb %d" % c
+        if ref is not None:
+            assert np.array_equal(want, ref.encode(bits[c].astype(np.int32)).astype(np.uint8))
+    if K == 6144:
+        assert "".join(map(str, dev_out[0][:12])) == "111011011011"
+
+
+def test_channel_statistics_and_determinism(oracle):
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_cb = 6144, 64
+    dec = TurboDecoder(K, algo="maxlog_s16", max_batch=64)
+    sigma = oracle.sigma(1.0, K)
+    coded = torch.randint(0, 2, (n_cb, 3 * K + 12), dtype=torch.uint8, device="cuda")
+    a = dec.channel(coded, sigma, seed=11)
+    b = dec.channel(coded, sigma, seed=11)
+    c = dec.channel(coded, sigma, seed=12)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    # LLR = 2 (x + sigma n) / sigma^2  ->  n recovered from the known x is standard normal
+    x = coded.float() * 2 - 1
+    n = (a * (sigma * sigma / 2) - x) / sigma
+    N = n.numel()
+    assert abs(float(n.mean())) < 5 / N ** 0.5
+    assert abs(float(n.var()) - 1.0) < 5 * (2.0 / N) ** 0.5
+    assert abs(float((n ** 4).mean()) - 3.0) < 0.05          # kurtosis of a Gaussian (a 12-term CLT sum gives 2.9)
+    assert float(n.abs().max()) > 4.5                        # real tails: a CLT sum of 12 uniforms cannot exceed 6
+    # host path and float64 output agree with the device path
+    h = dec.channel(coded[:3].cpu().numpy(), sigma, seed=11)
+    assert np.array_equal(h, a[:3].cpu().numpy())
+    d64 = dec.channel(coded[:3], sigma, seed=11, dtype="float64")
+    assert np.allclose(d64.cpu().numpy(), a[:3].cpu().numpy(), rtol=1e-6)
+
+
+def test_encode_channel_decode_round_trip(oracle):
+    """Size-independent property at the BASELINE size: random bits -> device encoder -> device channel at
+    1.5 dB -> decoder returns the bits (every mode)."""
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_cb = 6144, 32
+    bits = torch.randint(0, 2, (n_cb, K), dtype=torch.uint8, device="cuda")
+    for algo in ("maxlog_s16", "maxlog_f32", "logmap_f32", "logmap_f64"):
+        dec = TurboDecoder(K, n_iter=8, algo=algo, max_batch=32)
+        llr = dec.channel(dec.encode(bits), oracle.sigma(1.5, K), seed=5, dtype="float64" if algo == "logmap_f64" else "float32")
+        out = dec.decode(llr, want=("bits",))
+        assert torch.equal(out["bits"], bits), algo

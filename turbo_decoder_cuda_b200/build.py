@@ -28,6 +28,7 @@ KERNEL_TUS = [
     ("tdb200_ref64.cu", ["-fmad=false"]),
     ("tdb200_fast.cu", ["-Xptxas", "-v"]),
     ("tdb200_f32.cu", ["-fmad=false", "-Xptxas", "-v"]),
+    ("tdb200_encode.cu", []),
 ]
 
 

@@ -524,6 +524,66 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
     return TDB200_OK;
 }
 
+int tdb200_encode_batch(tdb200_decoder *d, const uint8_t *bits, uint8_t *coded, int mem, int n_cb, void *stream)
+{
+    if (!d || !bits || !coded) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (n_cb < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d mem=%d", n_cb, mem);
+    if (n_cb == 0) return TDB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    const int K = d->cfg.K, NL = d->NL;
+    EncodeArgs a{};
+    a.pi = d->d_pi; a.K = K; a.n_cb = n_cb;
+    if (mem == TDB200_MEM_DEVICE) {
+        a.bits = bits; a.coded = coded;
+        TDB_CUDA(launch_encode(a, st));
+        return TDB200_OK;
+    }
+    uint8_t *db = nullptr, *dc = nullptr;
+    TDB_CUDA(cudaMalloc(&db, (size_t)n_cb * K));
+    if (cudaMalloc(&dc, (size_t)n_cb * NL) != cudaSuccess) { cudaFree(db); return fail(TDB200_ERR_ALLOC, "device allocation failed"); }
+    cudaError_t e = cudaMemcpyAsync(db, bits, (size_t)n_cb * K, cudaMemcpyHostToDevice, st);
+    a.bits = db; a.coded = dc;
+    if (e == cudaSuccess) e = launch_encode(a, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(coded, dc, (size_t)n_cb * NL, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(db); cudaFree(dc);
+    if (e != cudaSuccess) return fail(TDB200_ERR_CUDA, "tdb200_encode_batch: %s", cudaGetErrorString(e));
+    return TDB200_OK;
+}
+
+int tdb200_channel_batch(tdb200_decoder *d, const uint8_t *coded, void *llr, int llr_type, int mem, int n_cb,
+                         double sigma, uint64_t seed, void *stream)
+{
+    if (!d || !coded || !llr) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (n_cb < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d mem=%d", n_cb, mem);
+    if (llr_type != TDB200_LLR_F32 && llr_type != TDB200_LLR_F64) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d (F32 or F64)", llr_type);
+    if (!(sigma > 0.0)) return fail(TDB200_ERR_INVALID_ARG, "sigma must be positive");
+    if (n_cb == 0) return TDB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    const size_t n = (size_t)n_cb * d->NL, esz = llr_elem_size(llr_type);
+    ChannelArgs a{};
+    a.n = n; a.sigma = (float)sigma; a.seed = seed;
+    if (mem == TDB200_MEM_DEVICE) {
+        a.coded = coded;
+        TDB_CUDA(launch_channel(a, llr, llr_type, st));
+        return TDB200_OK;
+    }
+    uint8_t *dc = nullptr;
+    void *dl = nullptr;
+    TDB_CUDA(cudaMalloc(&dc, n));
+    if (cudaMalloc(&dl, n * esz) != cudaSuccess) { cudaFree(dc); return fail(TDB200_ERR_ALLOC, "device allocation failed"); }
+    cudaError_t e = cudaMemcpyAsync(dc, coded, n, cudaMemcpyHostToDevice, st);
+    a.coded = dc;
+    if (e == cudaSuccess) e = launch_channel(a, dl, llr_type, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(llr, dl, n * esz, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dc); cudaFree(dl);
+    if (e != cudaSuccess) return fail(TDB200_ERR_CUDA, "tdb200_channel_batch: %s", cudaGetErrorString(e));
+    return TDB200_OK;
+}
+
 int tdb200_siso_batch(tdb200_decoder *d, const double *recs, const double *La, int terminated,
                       double *LLR, int mem, int n_cb, void *stream)
 {

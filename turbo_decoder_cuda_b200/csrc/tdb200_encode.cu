@@ -1,0 +1,129 @@
+// tdb200_encode.cu -- the caller side of the decode path, on the device:
+//
+//   encode_kernel   TurboEnCoding() -> encoderm_turbo() -> rsc_encode()   ITTC/log_map.cpp:700-730, 530-583, 451-527
+//                   (13,15)_8 PCCC with trellis termination, the reference's multiplex order
+//                   [3i]=x_i, [3i+1]=z_i, [3i+2]=z'_i, then (x,z)x3 of RSC1 and (x',z')x3 of RSC2 (:566-578)
+//   channel_kernel  module() BPSK + AWGN() + demodule()                   ITTC/main.cpp:197-202, modanddem.cpp:175-224
+//                   LLR = 2 r / sigma^2 with r = (2c-1) + sigma*n.  The reference draws n from a 12-term
+//                   central-limit sum over rand() (mgrns, log_map.cpp:1359-1392, seeded from time());
+//                   here n is Philox4x32-10 + Box-Muller, a pure function of (seed, element index).
+//
+// The encoder is a linear recursion over GF(2), a_k = d_k ^ a_{k-2} ^ a_{k-3}; nothing like the
+// reference's bit-serial loop is needed to parallelise it.  One warp encodes one codeblock: lane l owns
+// a chunk of ceil(K/32) consecutive trellis steps.  Pass 1 runs the chunk from state 0 together
+// with the three unit states under zero input (four recursions packed in the bits of one word),
+// which yields the chunk's zero-state response z_l and its 3x3 state-transition matrix T_l.  The
+// true entry state of every chunk follows from the 32-step scan s_{l+1} = T_l s_l ^ z_l across the
+// lanes (shuffles); pass 2 re-runs the chunk from that state and emits the parity bits.  RSC2 reads
+// its input through the QPP table.
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+
+#include "tdb200_internal.h"
+
+namespace tdb200 {
+namespace {
+
+// One trellis step on four packed recursions (bit j of every word belongs to recursion j).
+// Registers s0 (newest), s1, s2; feedback 1011, forward 1101 (ITTC/log_map.h:34-36).
+__device__ __forceinline__ unsigned rsc_step4(unsigned d, unsigned &s0, unsigned &s1, unsigned &s2)
+{
+    const unsigned a = d ^ s1 ^ s2;
+    const unsigned p = a ^ s0 ^ s2;
+    s2 = s1; s1 = s0; s0 = a;
+    return p;
+}
+
+__global__ void __launch_bounds__(128) encode_kernel(EncodeArgs A)
+{
+    const int K = A.K;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= A.n_cb) return;
+    const uint8_t *src = A.bits + (size_t)warp * K;
+    uint8_t *out = A.coded + (size_t)warp * (3 * K + 12);
+    const int C = (K + 31) / 32;
+    const int lo = min(lane * C, K), hi = min(lo + C, K);
+
+    for (int enc = 0; enc < 2; enc++) {
+        // ---- pass 1: zero-state response of the chunk (bit 0) and images of the unit states (bits 1..3)
+        unsigned s0 = 2u, s1 = 4u, s2 = 8u;  // recursion j+1 starts in unit state e_j (s0, s1, s2)
+        for (int i = lo; i < hi; i++) {
+            const unsigned d = src[enc ? A.pi[i] : i] & 1u;
+            rsc_step4(d, s0, s1, s2);
+        }
+        // ---- scan over the lanes: entry state of lane l (3 bits: s0 | s1<<1 | s2<<2)
+        unsigned st = 0;  // lane 0 starts in the all-zero state
+        for (int l = 0; l < 31; l++) {
+            // state after lane l's chunk = T_l * st ^ z_l, evaluated by lane l, handed to lane l+1
+            unsigned nx0 = (s0 & 1u), nx1 = (s1 & 1u), nx2 = (s2 & 1u);
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                if ((st >> j) & 1u) { nx0 ^= (s0 >> (j + 1)) & 1u; nx1 ^= (s1 >> (j + 1)) & 1u; nx2 ^= (s2 >> (j + 1)) & 1u; }
+            const unsigned nxt = nx0 | (nx1 << 1) | (nx2 << 2);
+            const unsigned got = __shfl_sync(0xffffffffu, nxt, l);
+            if (lane == l + 1) st = got;
+        }
+        // ---- pass 2: the chunk from its true entry state, parity out
+        unsigned r0 = st & 1u, r1 = (st >> 1) & 1u, r2 = (st >> 2) & 1u;
+        for (int i = lo; i < hi; i++) {
+            const unsigned d = src[enc ? A.pi[i] : i] & 1u;
+            const unsigned p = rsc_step4(d, r0, r1, r2) & 1u;
+            if (enc == 0) { out[3 * i] = (uint8_t)d; out[3 * i + 1] = (uint8_t)p; }
+            else out[3 * i + 2] = (uint8_t)p;
+        }
+        // ---- termination (rsc_encode :483-491): the lane holding the end of the block runs three more steps
+        //      with d = s1 ^ s2, which drives the feedback sum to zero
+        const int last = (K - 1) / C;
+        if (lane == last) {
+            for (int m = 0; m < 3; m++) {
+                const unsigned d = (r1 ^ r2) & 1u;
+                const unsigned p = rsc_step4(d, r0, r1, r2) & 1u;
+                out[3 * K + 6 * enc + 2 * m] = (uint8_t)d;
+                out[3 * K + 6 * enc + 2 * m + 1] = (uint8_t)p;
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) channel_kernel(ChannelArgs A, T *llr)
+{
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // four elements per thread
+    const size_t i0 = 4 * q;
+    if (i0 >= A.n) return;
+    curandStatePhilox4_32_10_t st;
+    curand_init(A.seed, /*subsequence*/ q, /*offset*/ 0, &st);
+    const float4 g = curand_normal4(&st);
+    const float nz[4] = {g.x, g.y, g.z, g.w};
+    const float k = 2.0f / (A.sigma * A.sigma);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const size_t i = i0 + j;
+        if (i < A.n) {
+            const float x = A.coded[i] ? 1.0f : -1.0f;  // module(): bit 1 -> +1 (positive LLR = bit 1)
+            llr[i] = (T)((x + A.sigma * nz[j]) * k);
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_encode(const EncodeArgs &a, cudaStream_t st)
+{
+    if (a.n_cb == 0) return cudaSuccess;
+    const int warps_per_cta = 4;
+    encode_kernel<<<(a.n_cb + warps_per_cta - 1) / warps_per_cta, 32 * warps_per_cta, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_channel(const ChannelArgs &a, void *llr, int llr_type, cudaStream_t st)
+{
+    if (a.n == 0) return cudaSuccess;
+    const size_t threads = (a.n + 3) / 4;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    if (llr_type == TDB200_LLR_F64) channel_kernel<double><<<grid, 256, 0, st>>>(a, static_cast<double *>(llr));
+    else channel_kernel<float><<<grid, 256, 0, st>>>(a, static_cast<float *>(llr));
+    return cudaGetLastError();
+}
+
+}  // namespace tdb200

@@ -130,4 +130,20 @@ cudaError_t fast_s16_configure(FastGeom &g, int sm_count);  // opt in to the dyn
 cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches);
 int fast_s16_smem_bytes(const FastGeom &g);
 
+// ------------------------------------------------------------------ caller side: encoder + channel
+struct EncodeArgs {
+    const uint8_t *bits;  // [n_cb][K] device, one byte per bit
+    uint8_t *coded;       // [n_cb][3K+12] device
+    const int *pi;        // [K] device
+    int K, n_cb;
+};
+struct ChannelArgs {
+    const uint8_t *coded;  // [n] device
+    size_t n;
+    float sigma;
+    unsigned long long seed;
+};
+cudaError_t launch_encode(const EncodeArgs &a, cudaStream_t st);
+cudaError_t launch_channel(const ChannelArgs &a, void *llr, int llr_type, cudaStream_t st);
+
 }  // namespace tdb200

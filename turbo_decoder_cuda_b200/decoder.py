@@ -76,6 +76,9 @@ def load_library():
     L.tdb200_siso_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                     C.c_int, C.c_int, C.c_void_p]
     L.tdb200_get_plan.argtypes = [C.c_void_p, C.POINTER(PlanInfo)]
+    L.tdb200_encode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.tdb200_channel_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_double, C.c_uint64, C.c_void_p]
     _lib = L
     return L
 
@@ -183,6 +186,33 @@ class TurboDecoder:
         ptrs = {k: _ptr_of(v)[0] for k, v in outs.items()}
         self.decode_raw(ptr, _LLR_TYPES[tname], mem, n_cb, stream=stream, **ptrs)
         return outs
+
+    def encode(self, bits, stream=0):
+        """tdb200_encode_batch: bits [n_cb, K] uint8 -> coded [n_cb, 3K+12] uint8 (the TurboEnCoding replacement)."""
+        n_cb = int(bits.shape[0])
+        assert int(bits.shape[1]) == self.K and str(bits.dtype).endswith("uint8")
+        bp, mem = _ptr_of(bits)
+        if _is_torch(bits):
+            import torch
+            coded = torch.empty((n_cb, self.llr_len), dtype=torch.uint8, device=bits.device)
+        else:
+            coded = np.empty((n_cb, self.llr_len), dtype=np.uint8)
+        _check(self._L.tdb200_encode_batch(self._h, bp, _ptr_of(coded)[0], mem, n_cb, stream))
+        return coded
+
+    def channel(self, coded, sigma, seed, dtype="float32", stream=0):
+        """tdb200_channel_batch: BPSK + AWGN + LLR = 2r/sigma^2 on coded [n_cb, 3K+12] uint8."""
+        n_cb = int(coded.shape[0])
+        assert int(coded.shape[1]) == self.llr_len
+        cp, mem = _ptr_of(coded)
+        if _is_torch(coded):
+            import torch
+            llr = torch.empty((n_cb, self.llr_len), dtype=getattr(torch, dtype), device=coded.device)
+        else:
+            llr = np.empty((n_cb, self.llr_len), dtype=dtype)
+        _check(self._L.tdb200_channel_batch(self._h, cp, _ptr_of(llr)[0], _LLR_TYPES[dtype], mem, n_cb,
+                                            float(sigma), int(seed), stream))
+        return llr
 
     def siso(self, recs, La, terminated=1, stream=0):
         """One BCJR pass (tdb200_siso_batch), the Log_MAP_decoder replacement; doubles only."""

@@ -79,16 +79,38 @@ def channel_llr(coded, sigma, generator=None, dtype=torch.float32):
     return ((x + sigma * noise) * (2.0 / (sigma * sigma))).to(dtype)
 
 
-def make_batch(K, n_cb, ebn0_db, seed=0, device="cpu", dtype=torch.float32, chunk=4096):
-    """Seeded random codeblocks through the channel: (bits [n_cb,K] uint8, llr [n_cb,3K+12])."""
-    g = torch.Generator(device=device)
+_handles = {}
+
+
+def _handle(K, index):
+    """A decoder handle used only for its encoder / channel entry points (cached per block size and device)."""
+    from .decoder import TurboDecoder
+    key = (K, index)
+    if key not in _handles:
+        _handles[key] = TurboDecoder(K, n_iter=1, algo="maxlog_s16", device=index, max_batch=2)
+    return _handles[key]
+
+
+def make_batch(K, n_cb, ebn0_db, seed=0, device="cpu", dtype=torch.float32, chunk=4096, kernels=True):
+    """Seeded random codeblocks through the channel: (bits [n_cb,K] uint8, llr [n_cb,3K+12]).
+
+    On a CUDA device the encoder and the channel are the library's own kernels
+    (tdb200_encode_batch / tdb200_channel_batch, csrc/tdb200_encode.cu); on the CPU, or with
+    kernels=False, the batched torch restatement above.  The two paths draw different noise."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
     g.manual_seed(seed)
-    pi = qpp_permutation(K, device=device)
     sigma = sigma_from_ebn0(ebn0_db, K)
+    if dev.type == "cuda" and kernels and dtype in (torch.float32, torch.float64):
+        h = _handle(K, dev.index if dev.index is not None else torch.cuda.current_device())
+        bits = torch.randint(0, 2, (n_cb, K), generator=g, device=dev, dtype=torch.uint8)
+        llr = h.channel(h.encode(bits), sigma, seed=seed, dtype=str(dtype).replace("torch.", ""))
+        return bits, llr
+    pi = qpp_permutation(K, device=dev)
     bits_all, llr_all = [], []
     for c0 in range(0, n_cb, chunk):
         n = min(chunk, n_cb - c0)
-        bits = torch.randint(0, 2, (n, K), generator=g, device=device, dtype=torch.uint8)
+        bits = torch.randint(0, 2, (n, K), generator=g, device=dev, dtype=torch.uint8)
         llr_all.append(channel_llr(turbo_encode(bits, pi), sigma, g, dtype))
         bits_all.append(bits)
     return torch.cat(bits_all), torch.cat(llr_all)
