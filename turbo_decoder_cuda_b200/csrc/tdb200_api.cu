@@ -293,6 +293,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         // ---- sub-block geometry: K = P * L, L = 8 * NW, P <= 256 threads
         FastGeom &g = d->geom;
         int L = c.sub_block;
+        if (L == 0 && K <= 56) L = K;  // shortest blocks: one thread walks the whole trellis (shared memory admits >= 256 threads per SM only for L <= 56)
         if (L == 0) {
             static const int pref[] = {48, 40, 56, 32, 64, 24, 72, 80, 96, 16, 128, 8};
             for (int cand : pref)
@@ -311,6 +312,19 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         g.PP = g.P | 1;  // odd row pitch: de-multiplex stores spread over the banks, walks stay conflict-free
         g.threads = ((g.P + 31) / 32) * 32;
         g.n_ckpt = std::max(g.NW - 2, 0);
+        g.NP = 1; g.pair_bytes = 0;
+        if (s16) {
+            g.pair_bytes = fast_s16_pair_bytes(g);
+            // pairs per CTA: fill two warps when a codeblock needs less than one (measured: larger CTAs
+            // only add barrier coupling -- registers cap an SM at eight warps either way)
+            int np = (fast_s16_specialised(g) || g.P >= 32) ? 1 : std::max(1, std::min(64 / g.P, 64));
+            while (np > 1) {
+                g.NP = np; g.threads = ((np * g.P + 31) / 32) * 32;
+                if ((size_t)fast_s16_smem_bytes(g) <= prop.sharedMemPerBlockOptin) break;
+                np--;
+            }
+            g.NP = np; g.threads = ((np * g.P + 31) / 32) * 32;
+        }
         g.smem_bytes = s16 ? fast_s16_smem_bytes(g) : f32_smem_bytes(g);
         if ((size_t)g.smem_bytes > prop.sharedMemPerBlockOptin)
             return fail(TDB200_ERR_UNSUPPORTED, "plan needs %d B of shared memory per CTA, device allows %zu", g.smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
@@ -358,7 +372,7 @@ int tdb200_get_plan(const tdb200_decoder *d, tdb200_plan_info *info)
         info->sub_block = d->cfg.K; info->n_sub_blocks = 1; info->cb_per_cta = 8; info->threads_per_cta = 64;
     } else {
         info->sub_block = d->geom.L; info->n_sub_blocks = d->geom.P; info->warmup = d->geom.G;
-        info->cb_per_cta = (d->cfg.algo == TDB200_ALGO_MAXLOG_S16) ? 2 : 1;
+        info->cb_per_cta = (d->cfg.algo == TDB200_ALGO_MAXLOG_S16) ? 2 * d->geom.NP : 1;
         info->threads_per_cta = d->geom.threads; info->smem_bytes = d->geom.smem_bytes;
     }
     return TDB200_OK;
@@ -414,6 +428,7 @@ static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int 
         a.tab2 = d->d_tab2;
         a.opaque[0] = 0xffffffffu; a.opaque[1] = 4u; a.opaque[2] = 65536u; a.opaque[3] = 0xC0000000u;
         a.prefetch_stride = d->geom.resident_ctas;
+        a.sm_count = d->sm_count;
         a.bits = v_bits; a.iters_used = v_iters;
         a.llr2 = static_cast<float *>(v_llr2); a.ext2 = static_cast<float *>(v_ext2);
         TDB_CUDA(launch_fast_s16(a, st, &d->launches_last));

@@ -307,7 +307,8 @@ __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, cons
     return acc;
 }
 
-// One SISO pass of one sub-block.  IL = false: SISO-1 (natural order), true: SISO-2 (through tab).
+// One SISO pass of one sub-block (thread `t` of its codeblock pair; inactive threads only take part in
+// the barriers and the boundary exchange).  IL = false: SISO-1 (natural order), true: SISO-2 (through tab).
 // na/nb: boundary vectors (alpha G steps before the sub-block, beta G steps after it); on return
 // they hold the vectors for the next iteration of this SISO.  With WANT the hard decisions of this
 // pass go to sm.dec (one word per two windows) and the return value has bits 0-15 / 16-31 set
@@ -315,12 +316,11 @@ __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, cons
 // low / high half if some a-posteriori magnitude of codeblock A / B is below the stopping threshold.
 template <bool IL, bool WANT, int KP, int KNW, int KG>
 __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, const Smem &sm, const w32 *par, w32 (&na)[8], w32 (&nb)[8],
-                                         const bool first_fixed, const bool last_fixed, w32 *stage, w32 &weak)
+                                         const int t, const bool active, const bool first_fixed, const bool last_fixed, w32 *stage,
+                                         w32 &weak)
 {
     const int P = KP ? KP : g.P, PP = KP ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW, G = KP ? KG : g.G;
     const int L = 8 * NW;
-    const int t = threadIdx.x;
-    const bool active = KP ? true : (t < P);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int w_sa = (L - G) >> 3, w_sb = G >> 3;
     w32 a[8], b[8], a0[8], sa[8], sb[8];
@@ -506,6 +506,25 @@ __device__ __forceinline__ void put4(const Smem &sm, int q, int L, int PP, const
     }
 }
 
+// Shared memory of one CTA: NP codeblock-pair regions (X, par1, par2, sysA, sysB, ckpt, dec), then the
+// QPP table (one copy for all pairs), the warp-edge exchange words and the per-pair stop flags.
+__device__ __forceinline__ Smem pair_smem(unsigned char *raw, const FastGeom &g, int P, int NW, int Wp, int NP, int p)
+{
+    Smem sm;
+    unsigned char *r = raw + (size_t)p * g.pair_bytes;
+    sm.X = reinterpret_cast<w32 *>(r);
+    sm.par1 = sm.X + Wp;
+    sm.par2 = sm.par1 + Wp;
+    sm.sysA = reinterpret_cast<uint8_t *>(sm.par2 + Wp);
+    sm.sysB = sm.sysA + Wp;
+    sm.ckpt = reinterpret_cast<w32 *>(sm.sysB + Wp);
+    sm.dec = sm.ckpt + (size_t)g.n_ckpt * 7 * P;
+    unsigned char *sh = raw + (size_t)NP * g.pair_bytes;
+    sm.tab = reinterpret_cast<uint16_t *>(sh);
+    sm.edge = reinterpret_cast<w32 *>(sm.tab + Wp);
+    return sm;
+}
+
 template <int LLR_T, int KP, int KNW, int KG>
 __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) fast_s16_kernel(FastArgs A)
 {
@@ -513,20 +532,18 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     const FastGeom &g = A.g;
     const int P = KP ? KP : g.P, PP = KP ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW;
     const int L = 8 * NW, K = P * L;
-    const int W = L * PP;  // words per array
-    Smem sm;
-    const int Wp = (W + 7) & ~7;  // every region starts 16-byte aligned
-    sm.X = reinterpret_cast<w32 *>(smem_raw);
-    sm.par1 = sm.X + Wp;
-    sm.par2 = sm.par1 + Wp;
-    sm.sysA = reinterpret_cast<uint8_t *>(sm.par2 + Wp);
-    sm.sysB = sm.sysA + Wp;
-    sm.tab = reinterpret_cast<uint16_t *>(sm.sysB + Wp);
-    sm.ckpt = reinterpret_cast<w32 *>(sm.tab + Wp);
-    sm.dec = sm.ckpt + (size_t)g.n_ckpt * 7 * P;
-    sm.edge = sm.dec + (size_t)((NW + 1) / 2) * P;
+    const int W = L * PP;            // words per array
+    const int Wp = (W + 7) & ~7;     // every region starts 16-byte aligned
+    const int NP = KP ? 1 : A.pairs_per_cta;  // codeblock pairs this CTA decodes side by side (small K)
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int cbA = 2 * blockIdx.x;
+    const int n_pairs = (A.n_cb + 1) / 2;
+    // thread -> (pair slot q, sub-block t)
+    const int q = KP ? 0 : tid / P, t = KP ? tid : tid - q * P;
+    const int pair = blockIdx.x * NP + q;
+    const bool active = KP ? true : (q < NP && pair < n_pairs);
+    const Smem sm = pair_smem(smem_raw, g, P, NW, Wp, NP, active ? q : 0);
+    unsigned *flags = reinterpret_cast<unsigned *>(sm.edge + 16 * (nthr >> 5));
+    const int cbA = 2 * (active ? pair : 0);
     const bool hasB = cbA + 1 < A.n_cb;
     const int cbB = hasB ? cbA + 1 : cbA;
     const size_t row = (size_t)3 * K + 12;
@@ -536,7 +553,11 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     // ---- load + quantise + de-multiplex (once per decode); element n = tt*L + j -> word j*PP + tt.
     //      NG groups of loads (NG x 2 codeblocks x 48 bytes) are in flight per thread before the
     //      first is consumed: the phase is pure load latency, so depth is what shortens it.
-    {
+    for (int p = 0; p < NP; p++) {
+        const int pr = blockIdx.x * NP + p;
+        if (pr >= n_pairs) break;
+        const Smem smp = pair_smem(smem_raw, g, P, NW, Wp, NP, p);
+        const int a_cb = 2 * pr, b_cb = (a_cb + 1 < A.n_cb) ? a_cb + 1 : a_cb;
         constexpr int NG = (LLR_T == TDB200_LLR_F64) ? 2 : 4;
         const w32 clipv = dup2(clip), nclipv = dup2(-clip);
         const int nq = K / 4;
@@ -544,17 +565,17 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
             Raw12<LLR_T> ra[NG], rb[NG];
 #pragma unroll
             for (int j = 0; j < NG; j++) {
-                const int q = min(q0 + j * nthr, nq - 1);  // the clamp re-reads the last group instead of branching
-                load12<LLR_T>(A.llr, row, cbA, q, ra[j]);
-                load12<LLR_T>(A.llr, row, cbB, q, rb[j]);
+                const int qq = min(q0 + j * nthr, nq - 1);  // the clamp re-reads the last group instead of branching
+                load12<LLR_T>(A.llr, row, a_cb, qq, ra[j]);
+                load12<LLR_T>(A.llr, row, b_cb, qq, rb[j]);
             }
 #pragma unroll
             for (int j = 0; j < NG; j++) {
-                const int q = q0 + j * nthr;
-                if (q < nq) {
+                const int qq = q0 + j * nthr;
+                if (qq < nq) {
                     w32 v[12];
                     pack12<LLR_T>(ra[j], rb[j], scale, clipv, nclipv, v);
-                    put4(sm, q, L, PP, v);
+                    put4(smp, qq, L, PP, v);
                 }
             }
         }
@@ -568,7 +589,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     }
     // ---- pull the rows of the codeblock pair that will run on this SM slot next into L2 (bulk
     //      prefetch, a few KB per instruction; rows are 16-byte multiples)
-    if (A.prefetch_stride > 0) {
+    if (KP && A.prefetch_stride > 0) {
         const long long nxt = (long long)2 * (blockIdx.x + A.prefetch_stride);
         if (nxt < A.n_cb) {
             const size_t esz = LLR_T == TDB200_LLR_F64 ? 8 : (LLR_T == TDB200_LLR_F32 ? 4 : 1);
@@ -589,7 +610,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     c.unbias = dup2((A.q2 == 3 ? -(3 * A.ext_lim / 4) : -A.ext_lim) - 128);
     c.neg1 = A.opaque[0]; c.four = A.opaque[1]; c.k64k = A.opaque[2]; c.k3q = A.opaque[3];
     c.etT = dup2(A.et_threshold); c.et2T = dup2(2 * A.et_threshold); c.etmask = dup2(2 * A.et_threshold - 1);
-    const bool first_fixed = (tid == 0), last_fixed = (tid == P - 1);
+    const bool first_fixed = (t == 0), last_fixed = (t == P - 1);
 
     // ---- boundary vectors.  [s][0..7]: s = SISO
     w32 na[2][8], nb[2][8];
@@ -600,7 +621,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
             na[s][j] = (first_fixed && j) ? dup2(kFxNeg) : 0u;  // known start state, :943-948
             nb[s][j] = 0u;
         }
-        if (last_fixed) {
+        if (last_fixed && active) {
             // termination folded into beta(K): three tail steps back from state 0, :950-954
             w32 bt[8];
 #pragma unroll
@@ -623,25 +644,37 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     for (int it = 0; it < A.n_iter; it++) {
         const bool last = (it == A.n_iter - 1);
         w32 weak = 0;
-        siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], first_fixed, last_fixed, nullptr, weak);
+        siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
         if (A.early_term || last) {
             // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
             // (by then dead) parity-1 array
-            const w32 chg = siso_pass<true, true, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed,
+            const w32 chg = siso_pass<true, true, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed,
                                                                (want_soft && last) ? sm.par1 : nullptr, weak);
             if (A.early_term) {
                 // stop: no decision of this iteration differs from the previous one and no
-                // a-posteriori value is weaker than the threshold
-                const int chA = __syncthreads_or((int)((chg | weak) & 0xffffu));
-                const int chB = __syncthreads_or((int)((chg | weak) >> 16));
+                // a-posteriori value is weaker than the threshold -- per codeblock; a CTA leaves when
+                // all its codeblocks have stopped
+                int chA, chB;
+                if (KP) {
+                    chA = __syncthreads_or((int)((chg | weak) & 0xffffu));
+                    chB = __syncthreads_or((int)((chg | weak) >> 16));
+                } else {
+                    if (tid < NP) flags[tid] = 0u;
+                    __syncthreads();
+                    if (active && (chg | weak)) atomicOr(&flags[q], chg | weak);
+                    __syncthreads();
+                    const unsigned f = active ? flags[q] : 0u;
+                    chA = (int)(f & 0xffffu); chB = (int)(f >> 16);
+                }
                 if (it >= 1) {
                     if (!chA && !usedA) usedA = it + 1;
                     if (!chB && !usedB) usedB = it + 1;
-                    if (usedA && usedB) { used = it + 1; break; }
                 }
+                const bool done = (usedA && usedB) || !active;
+                if (KP ? done : (__syncthreads_and((int)done) != 0)) { used = it + 1; break; }
             }
         } else {
-            siso_pass<true, false, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], first_fixed, last_fixed, nullptr, weak);
+            siso_pass<true, false, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed, nullptr, weak);
         }
     }
     if (!usedA) usedA = used;
@@ -651,15 +684,15 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     //      random_deinterlvr_int :1264 is the scatter of those bits to byte n = pi(i) of a staging
     //      array (the dead parity-2 region), which then leaves with coalesced 32-bit stores
     if (A.bits) {
-        uint8_t *byA = reinterpret_cast<uint8_t *>(sm.par2), *byB = byA + K;
-        if (tid < P) {
+        if (active) {
+            uint8_t *byA = reinterpret_cast<uint8_t *>(sm.par2), *byB = byA + K;
             for (int w2 = 0; w2 < (NW + 1) / 2; w2++) {
-                const w32 word = sm.dec[w2 * P + tid];
+                const w32 word = sm.dec[w2 * P + t];
 #pragma unroll
                 for (int kk = 0; kk < 16; kk++) {
                     const int j = 16 * w2 + (kk & 8) + 7 - (kk & 7);  // step k of a window sits in bit 7-k of its byte
                     if (j < L) {
-                        const int e = sm.tab[j * PP + tid];
+                        const int e = sm.tab[j * PP + t];
                         const int jj = e / PP, tt = e - jj * PP;
                         const int n = tt * L + jj;
                         byA[n] = (uint8_t)(((word >> kk) & 1u) ^ 1u);
@@ -669,33 +702,47 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
             }
         }
         __syncthreads();
-        const uint32_t *wa = reinterpret_cast<const uint32_t *>(byA), *wb = reinterpret_cast<const uint32_t *>(byB);
-        uint32_t *oa = reinterpret_cast<uint32_t *>(A.bits + (size_t)cbA * K), *ob = reinterpret_cast<uint32_t *>(A.bits + (size_t)cbB * K);
-        for (int q = tid; q < K / 4; q += nthr) {
-            oa[q] = wa[q];
-            if (hasB) ob[q] = wb[q];
+        for (int p = 0; p < NP; p++) {
+            const int pr = blockIdx.x * NP + p;
+            if (pr >= n_pairs) break;
+            const Smem smp = pair_smem(smem_raw, g, P, NW, Wp, NP, p);
+            const uint32_t *wa = reinterpret_cast<const uint32_t *>(smp.par2), *wb = wa + K / 4;
+            const bool pB = 2 * pr + 1 < A.n_cb;
+            uint32_t *oa = reinterpret_cast<uint32_t *>(A.bits + (size_t)(2 * pr) * K), *ob = oa + K / 4;
+            for (int i = tid; i < K / 4; i += nthr) {
+                oa[i] = wa[i];
+                if (pB) ob[i] = wb[i];
+            }
         }
     }
-    if (A.iters_used && tid == 0) {
+    if (A.iters_used && active && t == 0) {
         A.iters_used[cbA] = usedA;
         if (hasB) A.iters_used[cbB] = usedB;
     }
     if (want_soft || A.ext2) {
         const float inv = 1.0f / scale;
         const int T = K + kTail;
-        for (int i = tid; i < T; i += nthr) {
-            float la = 0.f, lb = 0.f, ea = 0.f, eb = 0.f;
-            if (i < K) {
-                const int tt = i / L, j = i - tt * L;
-                const int e = sm.tab[j * PP + tt];
-                const w32 lam = sm.par1[e];
-                const w32 ysb = (w32)sm.sysA[e] | ((w32)sm.sysB[e] << 16);
-                const w32 ex = vadd(vadd(sm.X[e], vneg(ysb)), 0x00800080u);
-                la = (float)(int16_t)(lam & 0xffff) * inv; lb = (float)(int16_t)(lam >> 16) * inv;
-                ea = (float)(int16_t)(ex & 0xffff) * inv; eb = (float)(int16_t)(ex >> 16) * inv;
+        __syncthreads();
+        for (int p = 0; p < NP; p++) {
+            const int pr = blockIdx.x * NP + p;
+            if (pr >= n_pairs) break;
+            const Smem smp = pair_smem(smem_raw, g, P, NW, Wp, NP, p);
+            const int a_cb = 2 * pr;
+            const bool pB = a_cb + 1 < A.n_cb;
+            for (int i = tid; i < T; i += nthr) {
+                float la = 0.f, lb = 0.f, ea = 0.f, eb = 0.f;
+                if (i < K) {
+                    const int tt = i / L, j = i - tt * L;
+                    const int e = smp.tab[j * PP + tt];
+                    const w32 lam = smp.par1[e];
+                    const w32 ysb = (w32)smp.sysA[e] | ((w32)smp.sysB[e] << 16);
+                    const w32 ex = vadd(vadd(smp.X[e], vneg(ysb)), 0x00800080u);
+                    la = (float)(int16_t)(lam & 0xffff) * inv; lb = (float)(int16_t)(lam >> 16) * inv;
+                    ea = (float)(int16_t)(ex & 0xffff) * inv; eb = (float)(int16_t)(ex >> 16) * inv;
+                }
+                if (A.llr2) { A.llr2[(size_t)a_cb * T + i] = la; if (pB) A.llr2[(size_t)(a_cb + 1) * T + i] = lb; }
+                if (A.ext2) { A.ext2[(size_t)a_cb * T + i] = ea; if (pB) A.ext2[(size_t)(a_cb + 1) * T + i] = eb; }
             }
-            if (A.llr2) { A.llr2[(size_t)cbA * T + i] = la; if (hasB) A.llr2[(size_t)cbB * T + i] = lb; }
-            if (A.ext2) { A.ext2[(size_t)cbA * T + i] = ea; if (hasB) A.ext2[(size_t)cbB * T + i] = eb; }
         }
     }
 }
@@ -704,11 +751,14 @@ typedef void (*kernel_fn)(FastArgs);
 
 // Specialised instances exist for the BASELINE block size only: K=6144 as 128 sub-blocks of 48 steps
 // or 192 sub-blocks of 32 steps (guard 16 either way); everything else runs the generic kernel.
+bool spec128(const FastGeom &g) { return g.P == 128 && g.NW == 6 && g.G == 16 && g.PP == 129; }
+bool spec192(const FastGeom &g) { return g.P == 192 && g.NW == 4 && g.G == 16 && g.PP == 193; }
+
 template <int LLR_T>
 kernel_fn pick_kernel_t(const FastGeom &g)
 {
-    if (g.P == 128 && g.NW == 6 && g.G == 16 && g.PP == 129) return fast_s16_kernel<LLR_T, 128, 6, 16>;
-    if (g.P == 192 && g.NW == 4 && g.G == 16 && g.PP == 193) return fast_s16_kernel<LLR_T, 192, 4, 16>;
+    if (spec128(g)) return fast_s16_kernel<LLR_T, 128, 6, 16>;
+    if (spec192(g)) return fast_s16_kernel<LLR_T, 192, 4, 16>;
     return fast_s16_kernel<LLR_T, 0, 0, 0>;
 }
 kernel_fn pick_kernel(const FastGeom &g, int llr_type)
@@ -722,12 +772,21 @@ kernel_fn pick_kernel(const FastGeom &g, int llr_type)
 
 }  // namespace
 
-int fast_s16_smem_bytes(const FastGeom &g)
+bool fast_s16_specialised(const FastGeom &g) { return spec128(g) || spec192(g); }
+
+// bytes of one codeblock-pair region / of the part shared by the pairs of a CTA of `threads` threads
+int fast_s16_pair_bytes(const FastGeom &g)
 {
-    const int nwarps = g.threads / 32;
     const int W = g.L * g.PP, Wp = (W + 7) & ~7;
-    return 3 * 4 * Wp + 2 * 2 * Wp + 4 * g.n_ckpt * 7 * g.P + 4 * ((g.NW + 1) / 2) * g.P + 4 * 16 * nwarps;
+    const int b = 3 * 4 * Wp + 2 * Wp + 4 * g.n_ckpt * 7 * g.P + 4 * ((g.NW + 1) / 2) * g.P;
+    return (b + 15) & ~15;
 }
+static int shared_bytes(const FastGeom &g, int threads, int np)
+{
+    const int W = g.L * g.PP, Wp = (W + 7) & ~7;
+    return 2 * Wp + 4 * 16 * (threads / 32) + 4 * ((np + 3) & ~3);
+}
+int fast_s16_smem_bytes(const FastGeom &g) { return g.pair_bytes * g.NP + shared_bytes(g, g.threads, g.NP); }
 
 cudaError_t fast_s16_configure(FastGeom &g, int sm_count)
 {
@@ -748,10 +807,18 @@ cudaError_t fast_s16_configure(FastGeom &g, int sm_count)
     return cudaSuccess;
 }
 
-cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches)
+cudaError_t launch_fast_s16(const FastArgs &a0, cudaStream_t st, int *n_launches)
 {
+    FastArgs a = a0;
     const int pairs = (a.n_cb + 1) / 2;
-    pick_kernel(a.g, a.llr_type)<<<pairs, a.g.threads, a.g.smem_bytes, st>>>(a);
+    // several pairs per CTA when a codeblock needs few threads -- but not so many that a small batch
+    // leaves SMs without work
+    int np = a.g.NP;
+    while (np > 1 && (pairs + np - 1) / np < 2 * a.sm_count) np = (np + 1) / 2;
+    a.pairs_per_cta = np;
+    const int threads = ((np * a.g.P + 31) / 32) * 32;
+    const int smem = a.g.pair_bytes * np + shared_bytes(a.g, threads, np);
+    pick_kernel(a.g, a.llr_type)<<<(pairs + np - 1) / np, threads, smem, st>>>(a);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

@@ -87,6 +87,8 @@ struct FastGeom {
     int n_ckpt;      // alpha checkpoints kept in shared memory per thread: max(NW-2, 0)
     int smem_bytes;
     int resident_ctas;  // CTAs of this geometry the whole device holds at once
+    int NP;             // codeblock pairs one CTA can decode side by side (1 for K >= 4096)
+    int pair_bytes;     // shared memory of one pair's region
 };
 
 struct FastArgs {
@@ -100,6 +102,8 @@ struct FastArgs {
     uint32_t opaque[4];  // {0xffffffff, 4, 65536, 0xC0000000}: see PassCfg in tdb200_fast.cu
     const uint16_t *tab2;  // [L*PP] device: smem word of element pi(tL+j), stored at index j*PP+t
     int prefetch_stride;   // CTAs resident on the device at once (0 = no L2 prefetch of the next pair)
+    int pairs_per_cta;     // filled in by launch_fast_s16
+    int sm_count;
     // outputs (device, nullable)
     uint8_t *bits;
     int32_t *iters_used;
@@ -129,6 +133,8 @@ int f32_smem_bytes(const FastGeom &g);
 cudaError_t fast_s16_configure(FastGeom &g, int sm_count);  // opt in to the dynamic shared memory size
 cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches);
 int fast_s16_smem_bytes(const FastGeom &g);
+int fast_s16_pair_bytes(const FastGeom &g);
+bool fast_s16_specialised(const FastGeom &g);  // compile-time geometry: one pair per CTA
 
 // ------------------------------------------------------------------ caller side: encoder + channel
 struct EncodeArgs {
