@@ -207,6 +207,32 @@ def run_ours(args):
     clocks = sampler.stop()
     ber = float((out_bits != bits).sum().item()) / (batch * K)
 
+    # ---- the same batch with early termination (informational; the headline is 8 fixed iterations)
+    et_info = None
+    if args.algo == "maxlog_s16" and not args.no_early_term:
+        dec_et = TurboDecoder(K, n_iter=N_ITER, algo=args.algo, device=local, max_batch=batch, sub_block=args.sub_block,
+                              warmup=args.guard, early_term=True)
+        et_iters = torch.empty((batch,), dtype=torch.int32, device=dev)
+        et_bits = torch.empty((batch, K), dtype=torch.uint8, device=dev)
+
+        def step_et():
+            dec_et.decode_raw(llr.data_ptr(), tdb.LLR_F32, tdb.MEM_DEVICE, batch, bits=et_bits.data_ptr(),
+                              iters_used=et_iters.data_ptr(), stream=sp)
+        for _ in range(3):
+            step_et()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(args.steps):
+            step_et()
+        g1.record(stream)
+        torch.cuda.synchronize()
+        et_info = {"gbit_s_this_rank": batch * K * args.steps / (g0.elapsed_time(g1) * 1e-3) / 1e9,
+                   "mean_iterations": float(et_iters.float().mean().item()),
+                   "ber": float((et_bits != bits).sum().item()) / (batch * K),
+                   "rule": "no hard decision changes and every |a-posteriori| >= 8.0, at most 8 iterations"}
+        dec_et.close()
+
     # ---- end to end through host buffers (pinned): H2D + decode + D2H inside the timed region
     h_llr = torch.empty(llr.shape, dtype=llr.dtype, pin_memory=True)
     h_llr.copy_(llr)
@@ -270,6 +296,8 @@ def run_ours(args):
                                  "frac": alu_ach / alu_peak, "ops_per_info_bit": OPS_PER_INFO_BIT}},
             "ber": ber,
         }
+        if et_info:
+            line["early_termination"] = et_info
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()
             decode, kind = cpu_reference_decoder()
@@ -296,6 +324,7 @@ def main():
     ap.add_argument("--algo", default="maxlog_s16")
     ap.add_argument("--ref-sample", type=int, default=0, help="codeblocks per CPU-baseline step (0 = 4 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-early-term", action="store_true", help="skip the informational early-termination leg")
     ap.add_argument("--sub-block", type=int, default=0, help="trellis steps per sub-block (0 = the library's plan)")
     ap.add_argument("--guard", type=int, default=0, help="warm-up steps across sub-block boundaries (with --sub-block)")
     args = ap.parse_args()

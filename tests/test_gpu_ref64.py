@@ -97,3 +97,44 @@ def test_empty_batch_and_bad_args():
         TurboDecoder(40, f1=4, f2=10, algo="logmap_f64")  # not a permutation
     with pytest.raises(TdbError):
         TurboDecoder(40, n_iter=0, algo="logmap_f64")
+
+
+def test_compat_layer_is_the_reference_call(oracle):
+    """The reference's own entry points, called the way ITTC/main.cpp:221 calls them (through the mangled
+    symbols of libtdb200_compat.so): TurboDecoding(double*, int*, int) fills flow_decoded for every
+    iteration and halves the caller's buffer; Log_MAP_decoder(...) is one BCJR pass."""
+    _torch_cuda()
+    import ctypes as C
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "turbo_decoder_cuda_b200", "lib", "libtdb200_compat.so")
+    if not os.path.exists(so):
+        pytest.skip("compat library not built")
+    os.environ["TDB200_COMPAT_ITERS"] = "6"
+    lib = C.CDLL(so)
+    K, n_iter = 512, 6
+    pi = oracle.qpp(K)
+    bits, llr = oracle.make_batch(K, 1, 1.5, seed=3)
+    buf = np.array(llr[0], np.float64, copy=True)
+    out = np.zeros(n_iter * K, np.int32)
+    dp, ip = np.ctypeslib.ndpointer(np.float64), np.ctypeslib.ndpointer(np.int32)
+    f = getattr(lib, "_Z13TurboDecodingPdPii")
+    f.argtypes = [dp, ip, C.c_int]
+    f.restype = None
+    f(buf, out, 3 * K + 12)
+    ob, o1, o2, le = oracle.decode(llr[0], pi, n_iter, want_llr=True)
+    assert np.array_equal(out.reshape(n_iter, K), ob)
+    assert np.array_equal(buf, llr[0] * 0.5), "the reference halves flow_for_decode in place (log_map.cpp:1202-1205)"
+    # one SISO pass on the demultiplexed half-LLRs
+    T = K + 3
+    recs = np.zeros(2 * T)
+    recs[0:2 * K:2] = 0.5 * llr[0][0:3 * K:3]
+    recs[1:2 * K:2] = 0.5 * llr[0][1:3 * K:3]
+    recs[2 * K:] = 0.5 * llr[0][3 * K:3 * K + 6]
+    La = np.zeros(T)
+    got = np.zeros(T)
+    g = getattr(lib, "_Z15Log_MAP_decoderPdS_iS_i")
+    g.argtypes = [dp, dp, C.c_int, dp, C.c_int]
+    g.restype = None
+    g(recs, La, 1, got, T)
+    want = oracle.siso(recs, La, terminated=1)
+    assert np.abs(got - want).max() < LLR_TOL

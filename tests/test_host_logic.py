@@ -169,3 +169,26 @@ def test_shard_range_properties():
             assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_reference_main_links_against_compat(lib, tmp_path):
+    """Link-level drop-in: the reference's own main.cpp + modanddem.cpp + the
+    encoder half of log_map.cpp link against libtdb200_compat with the two decode symbols taken from
+    us.  Needs the reference tree, so it runs in the dev container only (no GPU needed to LINK)."""
+    ref = "/root/reference/ITTC"
+    if not os.path.exists(os.path.join(ref, "main.cpp")):
+        pytest.skip("reference tree not present")
+    import subprocess
+    libdir = os.path.join(ROOT, "turbo_decoder_cuda_b200", "lib")
+    if not os.path.exists(os.path.join(libdir, "libtdb200_compat.so")):
+        pytest.skip("compat library not built")
+    exe = str(tmp_path / "turbo_sim")
+    objs = []
+    for src, extra in (("main.cpp", []), ("modanddem.cpp", []),
+                       ("log_map.cpp", ["-DTurboDecoding=ittc_cpu_TurboDecoding", "-DLog_MAP_decoder=ittc_cpu_Log_MAP_decoder"])):
+        o = str(tmp_path / (src + ".o"))
+        subprocess.check_call(["g++", "-O1", "-w", "-c", os.path.join(ref, src), "-o", o] + extra)
+        objs.append(o)
+    subprocess.check_call(["g++", "-o", exe] + objs + ["-L", libdir, "-ltdb200_compat", "-ltdb200", "-Wl,-rpath," + libdir])
+    syms = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
+    assert "_Z13TurboDecodingPdPii" in syms, "main.cpp's TurboDecoding call must resolve to the compat library"

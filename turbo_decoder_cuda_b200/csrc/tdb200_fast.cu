@@ -749,15 +749,20 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
 
 typedef void (*kernel_fn)(FastArgs);
 
-// Specialised instances exist for the BASELINE block size only: K=6144 as 128 sub-blocks of 48 steps
-// or 192 sub-blocks of 32 steps (guard 16 either way); everything else runs the generic kernel.
-bool spec128(const FastGeom &g) { return g.P == 128 && g.NW == 6 && g.G == 16 && g.PP == 129; }
+// Specialised (compile-time geometry) instances: 128 sub-blocks of 48 / 40 / 32 steps (K = 6144, the
+// BASELINE size, 5120, 4096) and K=6144 as 192 sub-blocks of 32 steps, guard 16; everything else runs
+// the generic kernel.
+bool spec128(const FastGeom &g) { return g.P == 128 && g.NW >= 4 && g.NW <= 6 && g.G == 16 && g.PP == 129; }
 bool spec192(const FastGeom &g) { return g.P == 192 && g.NW == 4 && g.G == 16 && g.PP == 193; }
 
 template <int LLR_T>
 kernel_fn pick_kernel_t(const FastGeom &g)
 {
-    if (spec128(g)) return fast_s16_kernel<LLR_T, 128, 6, 16>;
+    if (spec128(g)) {  // K = 1024 * NW: 6144, 5120, 4096
+        if (g.NW == 6) return fast_s16_kernel<LLR_T, 128, 6, 16>;
+        if (g.NW == 5) return fast_s16_kernel<LLR_T, 128, 5, 16>;
+        return fast_s16_kernel<LLR_T, 128, 4, 16>;
+    }
     if (spec192(g)) return fast_s16_kernel<LLR_T, 192, 4, 16>;
     return fast_s16_kernel<LLR_T, 0, 0, 0>;
 }
