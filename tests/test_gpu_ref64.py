@@ -138,3 +138,33 @@ def test_compat_layer_is_the_reference_call(oracle):
     g(recs, La, 1, got, T)
     want = oracle.siso(recs, La, terminated=1)
     assert np.abs(got - want).max() < LLR_TOL
+
+
+def test_error_paths_and_concurrent_handles(oracle):
+    """Argument checking returns status codes with a message (never a crash), and two handles with
+    different plans can live and run side by side (one stream each)."""
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TdbError, TurboDecoder
+    for kw in (dict(K=6145), dict(K=6144, n_iter=0), dict(K=6144, sub_block=50), dict(K=6144, sub_block=48, warmup=12),
+               dict(K=6144, frac_bits=9), dict(K=6144, ext_clip=62), dict(K=6144, et_threshold=48), dict(K=6144, algo=7),
+               dict(K=6144, f1=2, f2=2), dict(K=6144, device=99)):
+        with pytest.raises(TdbError) as e:
+            TurboDecoder(**kw)
+        assert e.value.status in (1, 2) and str(e.value)
+    d1 = TurboDecoder(6144, n_iter=4, algo="maxlog_s16")
+    d2 = TurboDecoder(512, n_iter=4, algo="maxlog_s16", sub_block=16, warmup=8)
+    with pytest.raises(TdbError):
+        d1.decode(torch.zeros((2, 3 * 6144 + 12), device="cuda"), want=("bits_iters",))   # fp64-mode output
+    b1, l1 = oracle.make_batch(6144, 4, 1.5, seed=1)
+    b2, l2 = oracle.make_batch(512, 6, 2.0, seed=2)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    x1, x2 = torch.from_numpy(l1.astype(np.float32)).cuda(), torch.from_numpy(l2.astype(np.float32)).cuda()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        o1 = d1.decode(x1, want=("bits",), stream=s1.cuda_stream)
+        o2 = d2.decode(x2, want=("bits",), stream=s2.cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(o1["bits"].cpu().numpy(), b1.astype(np.uint8))
+    assert np.array_equal(o2["bits"].cpu().numpy(), b2.astype(np.uint8))
+    d1.close(); d2.close()
+    d1.close()  # idempotent

@@ -31,11 +31,17 @@
 //    folded into a constant start vector once per decode.
 //  * EARLY TERMINATION (new functionality; the reference only has a placeholder,
 //    previous/Decoder.cc:1098-1099): every thread keeps the hard decisions of its own steps as a
-//    bit mask; when a whole iteration changes none of them for either codeblock the CTA stops.
+//    bit mask; a codeblock stops after the first iteration (>= 2) that changes none of them and
+//    leaves every |a-posteriori| at or above a threshold.  A CTA leaves when all its codeblocks did.
+//  * THE ALU PIPE IS THE BOUND (VIADDMNMX issues there and nowhere else), so address arithmetic,
+//    bit-wise NOT, byte packing and the 3/4 extrinsic scale are written as IMADs with opaque
+//    constants (PassCfg) to keep them on the fma-heavy pipe; the backward sweep is ONE rolled
+//    window body per pass (instruction-cache footprint).
 //
-// The kernel is a template over the geometry: the BASELINE block size K=6144 (P=128 sub-blocks of
-// L=48 steps, guard 16) gets compile-time constants -- every shared-memory address becomes
-// base+immediate -- and every other LTE size runs the same code with run-time geometry.
+// The kernel is a template over the geometry: K = 6144 / 5120 / 4096 (128 sub-blocks of 48 / 40 / 32
+// steps, guard 16) get compile-time constants -- every shared-memory address becomes
+// base+immediate -- and every other LTE size runs the same code with run-time geometry, several
+// codeblock pairs side by side in one CTA when a codeblock needs fewer than 32 threads.
 #include <cuda_runtime.h>
 
 #include "tdb200_internal.h"
