@@ -108,7 +108,7 @@ typedef struct tdo_f32_params {
     int n_iter;
     int sub_len;        /* L */
     int warmup;         /* G */
-    int logmap;         /* 1: max* with the exact correction, 0: max */
+    int logmap;         /* 0: max, 1: max* with the exact correction, 2: max* with the linear correction */
     int early_term;
     float ext_scale;    /* 1.0 (Log-MAP) / 0.75 (max-log) */
     float ext_clamp;    /* |Le| clamp */

@@ -30,6 +30,7 @@ static inline float mx(float x, float y)
 {
     float m = x > y ? x : y;
     if (!g_logmap) return m;
+    if (g_logmap == 2) return m + fmaxf(fmaf(-0.24904f, fabsf(x - y), 0.62429345f), 0.0f); /* linear correction, fused like the kernel's FFMA */
     float d = fabsf(x - y) * -1.4426950408889634f;
     float e = exp2f(d);
     float l = log2f(1.0f + e);

@@ -34,20 +34,23 @@ def _params(K, n_iter, L, G, logmap, et=0):
     (1008, 0, 0, 3, 4, 1.0),     # P = 21: not a warp multiple
     (40, 40, 0, 5, 6, 2.0),      # single sub-block: the unsegmented recursion
 ])
-def test_maxlog_f32_bit_exact(oracle, K, L, G, n_cb, n_iter, ebn0):
+@pytest.mark.parametrize("algo,lm", [("maxlog_f32", 0), ("linlogmap_f32", 2)])
+def test_maxlog_and_linear_logmap_f32_bit_exact(oracle, K, L, G, n_cb, n_iter, ebn0, algo, lm):
+    """Neither variant touches a special-function unit, so every float operation is IEEE and the
+    plain-C model reproduces the kernel bit for bit."""
     torch = _torch_cuda()
     from turbo_decoder_cuda_b200 import TurboDecoder
     pi = oracle.qpp(K)
     _, llr = oracle.make_batch(K, n_cb, ebn0, seed=5 + K + L)
     llr32 = llr.astype(np.float32)
-    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_f32", sub_block=L, warmup=G)
+    dec = TurboDecoder(K, n_iter=n_iter, algo=algo, sub_block=L, warmup=G)
     plan = dec.plan()
     assert plan["cb_per_cta"] == 1
     for x in (torch.from_numpy(llr32).cuda(), llr32):   # device path, host path
         out = dec.decode(x, want=("bits", "llr_siso2", "ext_siso2", "iters_used"))
         out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
         for c in range(n_cb):
-            b, l, le, it = oracle.f32_decode(llr32[c], pi, _params(K, n_iter, plan["sub_block"], plan["warmup"], 0), want_soft=True)
+            b, l, le, it = oracle.f32_decode(llr32[c], pi, _params(K, n_iter, plan["sub_block"], plan["warmup"], lm), want_soft=True)
             assert np.array_equal(out["bits"][c], b.astype(np.uint8))
             assert np.array_equal(out["llr_siso2"][c][:K], l), "a-posteriori values must be bit-identical"
             assert np.array_equal(out["ext_siso2"][c][:K], le)

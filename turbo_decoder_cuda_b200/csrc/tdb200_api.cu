@@ -277,12 +277,13 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         w.alpha = p; p += 8 * (T + 1) * nb;
         w.beta = p; p += 8 * (T + 1) * nb;
         w.max_batch = c.max_batch;
-    } else if (c.algo == TDB200_ALGO_MAXLOG_S16 || c.algo == TDB200_ALGO_LOGMAP_F32 || c.algo == TDB200_ALGO_MAXLOG_F32) {
+    } else if (c.algo == TDB200_ALGO_MAXLOG_S16 || c.algo == TDB200_ALGO_LOGMAP_F32 || c.algo == TDB200_ALGO_MAXLOG_F32 ||
+               c.algo == TDB200_ALGO_LINLOGMAP_F32) {
         const bool s16 = (c.algo == TDB200_ALGO_MAXLOG_S16);
         if (c.max_batch <= 0) c.max_batch = 16384;
         if (c.frac_bits == 0) c.frac_bits = 3;
         if (c.frac_bits < 1 || c.frac_bits > 4) return fail(TDB200_ERR_INVALID_ARG, "frac_bits=%d out of range [1,4]", c.frac_bits);
-        if (c.ext_scale_q2 == 0) c.ext_scale_q2 = (c.algo == TDB200_ALGO_LOGMAP_F32) ? 4 : 3;
+        if (c.ext_scale_q2 == 0) c.ext_scale_q2 = (c.algo == TDB200_ALGO_LOGMAP_F32 || c.algo == TDB200_ALGO_LINLOGMAP_F32) ? 4 : 3;
         if (c.ext_scale_q2 != 3 && c.ext_scale_q2 != 4) return fail(TDB200_ERR_INVALID_ARG, "ext_scale_q2=%d (3 or 4)", c.ext_scale_q2);
         if (c.et_threshold == 0) c.et_threshold = 1 << (c.frac_bits + 3);
         if (c.et_threshold < 1 || c.et_threshold > 4096 || (c.et_threshold & (c.et_threshold - 1)))
@@ -409,7 +410,7 @@ static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int 
     } else if (c.algo != TDB200_ALGO_MAXLOG_S16) {
         F32Args a{};
         a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.g = d->geom; a.n_iter = c.n_iter;
-        a.logmap = (c.algo == TDB200_ALGO_LOGMAP_F32);
+        a.logmap = (c.algo == TDB200_ALGO_LOGMAP_F32) ? 1 : (c.algo == TDB200_ALGO_LINLOGMAP_F32 ? 2 : 0);
         a.ext_scale = 0.25f * (float)c.ext_scale_q2;
         a.ext_clamp = 1.0e6f;  // the fp32 modes do not clamp the extrinsic (the reference does not either)
         a.early_term = c.early_term;

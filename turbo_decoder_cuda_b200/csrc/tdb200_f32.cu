@@ -1,6 +1,6 @@
-// tdb200_f32.cu -- TDB200_ALGO_LOGMAP_F32 / TDB200_ALGO_MAXLOG_F32: the sub-block-parallel decoder
-// in fp32, with the exact Jacobian correction  max*(x,y) = max(x,y) + ln(1 + e^-|x-y|)  (Log-MAP) or
-// without it (max-log-MAP).
+// tdb200_f32.cu -- TDB200_ALGO_LOGMAP_F32 / LINLOGMAP_F32 / MAXLOG_F32: the sub-block-parallel decoder
+// in fp32, with the exact Jacobian correction  max*(x,y) = max(x,y) + ln(1 + e^-|x-y|)  (Log-MAP), its
+// linear approximation, or without it (max-log-MAP).
 //
 // What it computes: the iterative PCCC decode of TurboDecoding() (ITTC/log_map.cpp:1146-1280) with
 // the component decoder Log_MAP_decoder() (:898-1047), where the reference's max* (E_algorithm,
@@ -32,11 +32,14 @@ namespace {
 
 constexpr float kNegF = -1.0e9f;  // metric of an impossible state
 
-template <bool LOGMAP>
+// LM: 0 = max, 1 = max* with the exact correction, 2 = max* with the linear correction
+//     max(0, 0.24904 * (2.5068 - d))  (least-squares fit of ln(1+e^-d); no special-function unit needed)
+template <int LOGMAP>
 __device__ __forceinline__ float mx(float x, float y)
 {
     const float m = fmaxf(x, y);
-    if (!LOGMAP) return m;
+    if (LOGMAP == 0) return m;
+    if (LOGMAP == 2) return m + fmaxf(__fmaf_rn(-0.24904f, fabsf(x - y), 0.62429345f), 0.f);  // one FFMA, as in the model
     // ln(1 + e^-d) = ln2 * lg2(1 + ex2(-d * log2 e)),  d = |x - y|
     float e, l;
     const float d = fabsf(x - y) * -1.4426950408889634f;
@@ -54,7 +57,7 @@ __device__ __forceinline__ void norm8(float (&m)[8])
 }
 
 // alpha(i+1) from alpha(i)   (:975-1001)
-template <bool LM>
+template <int LM>
 __device__ __forceinline__ void alpha_step_to(const float (&a)[8], float u, float v, float (&o)[8])
 {
     const float w = u + v;
@@ -64,11 +67,11 @@ __device__ __forceinline__ void alpha_step_to(const float (&a)[8], float u, floa
     const float o7 = mx<LM>(a[6], a[7] + w), o3 = mx<LM>(a[7], a[6] + w);
     o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3; o[4] = o4; o[5] = o5; o[6] = o6; o[7] = o7;
 }
-template <bool LM>
+template <int LM>
 __device__ __forceinline__ void alpha_step(float (&a)[8], float u, float v) { alpha_step_to<LM>(a, u, v, a); }
 
 // beta(i) from beta(i+1)   (:1004-1021)
-template <bool LM>
+template <int LM>
 __device__ __forceinline__ void beta_step(float (&b)[8], float u, float v)
 {
     const float w = u + v;
@@ -81,7 +84,7 @@ __device__ __forceinline__ void beta_step(float (&b)[8], float u, float v)
 
 // extrinsic = max*_{input 1}(alpha + c*V + beta') - max*_{input 0}(alpha + c*V + beta')   (:1024-1039
 // without the +U common to the input-1 branches, so this IS Le of :1234-1238)
-template <bool LM>
+template <int LM>
 __device__ __forceinline__ float extrinsic(const float (&a)[8], const float (&b)[8], float v)
 {
     const float m0a = mx<LM>(mx<LM>(a[0] + b[0], a[1] + b[4]), mx<LM>(a[6] + b[7], a[7] + b[3]));
@@ -116,7 +119,7 @@ __device__ __forceinline__ float load_llr(const void *base, size_t idx)
 }
 
 // One SISO pass of one sub-block; see siso_pass in tdb200_fast.cu for the schedule.
-template <bool LM, bool IL>
+template <int LM, bool IL>
 __device__ __forceinline__ unsigned siso_pass(const Pass &c, const Smem &sm, const __half *par, float (&na)[8], float (&nb)[8],
                                               const bool first_fixed, const bool last_fixed, const bool want, float *g_llr, float *g_ext,
                                               bool &weak)
@@ -284,7 +287,7 @@ __device__ __forceinline__ unsigned siso_pass(const Pass &c, const Smem &sm, con
     return changed;
 }
 
-template <int LLR_T, bool LM>
+template <int LLR_T, int LM>
 __global__ void __launch_bounds__(256, 1) f32_kernel(F32Args A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -384,12 +387,17 @@ __global__ void __launch_bounds__(256, 1) f32_kernel(F32Args A)
 }
 
 typedef void (*kernel_fn)(F32Args);
-kernel_fn pick(int llr_type, bool lm)
+template <int LLR_T>
+kernel_fn pick_t(int lm)
+{
+    return lm == 1 ? f32_kernel<LLR_T, 1> : (lm == 2 ? f32_kernel<LLR_T, 2> : f32_kernel<LLR_T, 0>);
+}
+kernel_fn pick(int llr_type, int lm)
 {
     switch (llr_type) {
-        case TDB200_LLR_F32: return lm ? f32_kernel<TDB200_LLR_F32, true> : f32_kernel<TDB200_LLR_F32, false>;
-        case TDB200_LLR_F64: return lm ? f32_kernel<TDB200_LLR_F64, true> : f32_kernel<TDB200_LLR_F64, false>;
-        default: return lm ? f32_kernel<TDB200_LLR_S8, true> : f32_kernel<TDB200_LLR_S8, false>;
+        case TDB200_LLR_F32: return pick_t<TDB200_LLR_F32>(lm);
+        case TDB200_LLR_F64: return pick_t<TDB200_LLR_F64>(lm);
+        default: return pick_t<TDB200_LLR_S8>(lm);
     }
 }
 
@@ -409,8 +417,8 @@ cudaError_t f32_configure(const FastGeom &)
     if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e0 != cudaSuccess) return e0;
     for (int t = TDB200_LLR_F64; t <= TDB200_LLR_S8; t++)
-        for (int lm = 0; lm < 2; lm++) {
-            cudaError_t e = cudaFuncSetAttribute(pick(t, lm != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        for (int lm = 0; lm < 3; lm++) {
+            cudaError_t e = cudaFuncSetAttribute(pick(t, lm), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             if (e != cudaSuccess) return e;
         }
     return cudaSuccess;
@@ -418,7 +426,7 @@ cudaError_t f32_configure(const FastGeom &)
 
 cudaError_t launch_f32(const F32Args &a, cudaStream_t st, int *n_launches)
 {
-    pick(a.llr_type, a.logmap != 0)<<<a.n_cb, a.g.threads, a.g.smem_bytes, st>>>(a);
+    pick(a.llr_type, a.logmap)<<<a.n_cb, a.g.threads, a.g.smem_bytes, st>>>(a);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

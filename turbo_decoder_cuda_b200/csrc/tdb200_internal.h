@@ -116,7 +116,7 @@ struct F32Args {
     int n_cb;
     FastGeom g;       // same geometry rules as the int16 kernel, one codeblock per CTA
     int n_iter;
-    int logmap;       // 1: max* with the exact correction, 0: max
+    int logmap;       // 0: max, 1: max* with the exact correction, 2: max* with the linear correction
     float ext_scale;  // 1.0 (Log-MAP) or 0.75 (max-log)
     float ext_clamp;  // |Le| clamp (LLR units)
     int early_term;
