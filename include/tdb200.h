@@ -65,7 +65,8 @@ typedef enum tdb200_algo {
 typedef enum tdb200_llr_type {
     TDB200_LLR_F64 = 0, /* the reference's type (double *flow_for_decode) */
     TDB200_LLR_F32 = 1,
-    TDB200_LLR_S8 = 2   /* already quantised: q = LLR * 2^frac_bits, saturated to int8 */
+    TDB200_LLR_S8 = 2,  /* already quantised: q = LLR * 2^frac_bits, saturated to int8 */
+    TDB200_LLR_F16 = 3  /* IEEE binary16: half the PCIe / HBM bytes of float32 */
 } tdb200_llr_type;
 
 /* Where caller buffers live. */

@@ -66,6 +66,8 @@ def test_channel_statistics_and_determinism(oracle):
     assert np.array_equal(h, a[:3].cpu().numpy())
     d64 = dec.channel(coded[:3], sigma, seed=11, dtype="float64")
     assert np.allclose(d64.cpu().numpy(), a[:3].cpu().numpy(), rtol=1e-6)
+    d16 = dec.channel(coded[:3], sigma, seed=11, dtype="float16")
+    assert torch.equal(d16, a[:3].half())
 
 
 def test_encode_channel_decode_round_trip(oracle):
@@ -75,8 +77,9 @@ def test_encode_channel_decode_round_trip(oracle):
     from turbo_decoder_cuda_b200 import TurboDecoder
     K, n_cb = 6144, 32
     bits = torch.randint(0, 2, (n_cb, K), dtype=torch.uint8, device="cuda")
-    for algo in ("maxlog_s16", "maxlog_f32", "logmap_f32", "logmap_f64"):
+    for algo, dt in (("maxlog_s16", "float32"), ("maxlog_s16", "float16"), ("maxlog_f32", "float32"), ("linlogmap_f32", "float16"),
+                     ("logmap_f32", "float32"), ("logmap_f64", "float64"), ("logmap_f64", "float16")):
         dec = TurboDecoder(K, n_iter=8, algo=algo, max_batch=32)
-        llr = dec.channel(dec.encode(bits), oracle.sigma(1.5, K), seed=5, dtype="float64" if algo == "logmap_f64" else "float32")
+        llr = dec.channel(dec.encode(bits), oracle.sigma(1.5, K), seed=5, dtype=dt)
         out = dec.decode(llr, want=("bits",))
         assert torch.equal(out["bits"], bits), algo

@@ -82,7 +82,7 @@ def test_fixed_point_formats(oracle, F, q2, ec):
 
 
 def test_input_types(oracle):
-    """float64 input is rounded to float32 first; int8 input is taken as already quantised."""
+    """float64 input is rounded to float32 first; int8 input is taken as already quantised; float16 is exact in float32."""
     _torch_cuda()
     from turbo_decoder_cuda_b200 import TurboDecoder
     K, n_cb, n_iter = 768, 3, 4
@@ -95,6 +95,10 @@ def test_input_types(oracle):
     _check(oracle, dec, llr, llr32, pi, prm, n_cb, K)
     q = np.clip(np.rint(llr32 * 8.0), -127, 127).astype(np.int8)
     _check(oracle, dec, q, (q.astype(np.float32) / 8.0), pi, prm, n_cb, K)
+    h = llr32.astype(np.float16)                       # binary16 transport: the model sees the rounded values
+    _check(oracle, dec, h, h.astype(np.float32), pi, prm, n_cb, K)
+    import torch
+    _check(oracle, dec, torch.from_numpy(h).cuda(), h.astype(np.float32), pi, prm, n_cb, K)
 
 
 def test_extreme_llrs_do_not_overflow(oracle):

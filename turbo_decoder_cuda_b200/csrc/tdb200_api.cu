@@ -152,7 +152,7 @@ static int ensure_once(P *&p, size_t bytes)
     return TDB200_OK;
 }
 
-static size_t llr_elem_size(int t) { return t == TDB200_LLR_F64 ? 8 : (t == TDB200_LLR_F32 ? 4 : 1); }
+static size_t llr_elem_size(int t) { return t == TDB200_LLR_F64 ? 8 : (t == TDB200_LLR_F32 ? 4 : (t == TDB200_LLR_F16 ? 2 : 1)); }
 
 extern "C" {
 
@@ -442,7 +442,7 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
 {
     if (!d || !llr || !out) return fail(TDB200_ERR_INVALID_ARG, "dec/llr/out is NULL");
     if (n_cb < 0) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d", n_cb);
-    if (llr_type < TDB200_LLR_F64 || llr_type > TDB200_LLR_S8) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d", llr_type);
+    if (llr_type < TDB200_LLR_F64 || llr_type > TDB200_LLR_F16) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d", llr_type);
     if (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE) return fail(TDB200_ERR_INVALID_ARG, "mem=%d", mem);
     d->launches_last = 0;
     if (n_cb == 0) return TDB200_OK;
@@ -573,7 +573,8 @@ int tdb200_channel_batch(tdb200_decoder *d, const uint8_t *coded, void *llr, int
 {
     if (!d || !coded || !llr) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
     if (n_cb < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d mem=%d", n_cb, mem);
-    if (llr_type != TDB200_LLR_F32 && llr_type != TDB200_LLR_F64) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d (F32 or F64)", llr_type);
+    if (llr_type != TDB200_LLR_F32 && llr_type != TDB200_LLR_F64 && llr_type != TDB200_LLR_F16)
+        return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d (F32, F64 or F16)", llr_type);
     if (!(sigma > 0.0)) return fail(TDB200_ERR_INVALID_ARG, "sigma must be positive");
     if (n_cb == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

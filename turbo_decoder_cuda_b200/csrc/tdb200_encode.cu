@@ -16,6 +16,7 @@
 // true entry state of every chunk follows from the 32-step scan s_{l+1} = T_l s_l ^ z_l across the
 // lanes (shuffles); pass 2 re-runs the chunk from that state and emits the parity bits.  RSC2 reads
 // its input through the QPP table.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <curand_kernel.h>
 
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256) channel_kernel(ChannelArgs A, T *llr)
         const size_t i = i0 + j;
         if (i < A.n) {
             const float x = A.coded[i] ? 1.0f : -1.0f;  // module(): bit 1 -> +1 (positive LLR = bit 1)
-            llr[i] = (T)((x + A.sigma * nz[j]) * k);
+            llr[i] = static_cast<T>((x + A.sigma * nz[j]) * k);
         }
     }
 }
@@ -122,6 +123,7 @@ cudaError_t launch_channel(const ChannelArgs &a, void *llr, int llr_type, cudaSt
     const size_t threads = (a.n + 3) / 4;
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (llr_type == TDB200_LLR_F64) channel_kernel<double><<<grid, 256, 0, st>>>(a, static_cast<double *>(llr));
+    else if (llr_type == TDB200_LLR_F16) channel_kernel<__half><<<grid, 256, 0, st>>>(a, static_cast<__half *>(llr));
     else channel_kernel<float><<<grid, 256, 0, st>>>(a, static_cast<float *>(llr));
     return cudaGetLastError();
 }

@@ -114,6 +114,7 @@ __device__ __forceinline__ float load_llr(const void *base, size_t idx)
     float x;
     if (LLR_T == TDB200_LLR_F32) x = __ldg(static_cast<const float *>(base) + idx);
     else if (LLR_T == TDB200_LLR_F64) x = (float)__ldg(static_cast<const double *>(base) + idx);
+    else if (LLR_T == TDB200_LLR_F16) x = __half2float(__ldg(static_cast<const __half *>(base) + idx));
     else x = (float)__ldg(static_cast<const int8_t *>(base) + idx) * 0.125f;  // S8: 3 fractional bits
     return (x == x) ? x : 0.f;  // NaN -> erasure
 }
@@ -397,6 +398,7 @@ kernel_fn pick(int llr_type, int lm)
     switch (llr_type) {
         case TDB200_LLR_F32: return pick_t<TDB200_LLR_F32>(lm);
         case TDB200_LLR_F64: return pick_t<TDB200_LLR_F64>(lm);
+        case TDB200_LLR_F16: return pick_t<TDB200_LLR_F16>(lm);
         default: return pick_t<TDB200_LLR_S8>(lm);
     }
 }
@@ -416,7 +418,7 @@ cudaError_t f32_configure(const FastGeom &)
     cudaError_t e0 = cudaGetDevice(&dev);
     if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e0 != cudaSuccess) return e0;
-    for (int t = TDB200_LLR_F64; t <= TDB200_LLR_S8; t++)
+    for (int t = TDB200_LLR_F64; t <= TDB200_LLR_F16; t++)
         for (int lm = 0; lm < 3; lm++) {
             cudaError_t e = cudaFuncSetAttribute(pick(t, lm), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             if (e != cudaSuccess) return e;

@@ -42,6 +42,7 @@
 // steps, guard 16) get compile-time constants -- every shared-memory address becomes
 // base+immediate -- and every other LTE size runs the same code with run-time geometry, several
 // codeblock pairs side by side in one CTA when a codeblock needs fewer than 32 threads.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "tdb200_internal.h"
@@ -119,6 +120,7 @@ struct Raw12 {
     float4 f[LLR_T == TDB200_LLR_F32 ? 3 : 1];
     double2 d[LLR_T == TDB200_LLR_F64 ? 6 : 1];
     int w[LLR_T == TDB200_LLR_S8 ? 3 : 1];
+    uint2 h[LLR_T == TDB200_LLR_F16 ? 3 : 1];  // 4 halves each
 };
 
 template <int LLR_T>
@@ -132,12 +134,18 @@ __device__ __forceinline__ void load12(const void *base, size_t row_elems, int c
         const double2 *p = reinterpret_cast<const double2 *>(static_cast<const double *>(base) + (size_t)cb * row_elems) + 6 * q;
 #pragma unroll
         for (int k = 0; k < 6; k++) r.d[k] = __ldg(p + k);
+    } else if (LLR_T == TDB200_LLR_F16) {
+        const uint2 *p = reinterpret_cast<const uint2 *>(static_cast<const __half *>(base) + (size_t)cb * row_elems) + 3 * q;
+#pragma unroll
+        for (int k = 0; k < 3; k++) r.h[k] = __ldg(p + k);
     } else {
         const int *p = reinterpret_cast<const int *>(static_cast<const int8_t *>(base) + (size_t)cb * row_elems) + 3 * q;
 #pragma unroll
         for (int k = 0; k < 3; k++) r.w[k] = __ldg(p + k);
     }
 }
+__device__ __forceinline__ float h_lo(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+__device__ __forceinline__ float h_hi(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
 // quantise + pack the 12 values of codeblocks A and B into 12 s16x2 words
 template <int LLR_T>
@@ -156,6 +164,14 @@ __device__ __forceinline__ void pack12(const Raw12<LLR_T> &a, const Raw12<LLR_T>
         for (int k = 0; k < 6; k++) {
             out[2 * k] = quant2((float)a.d[k].x, (float)b.d[k].x, scale, clipv, nclipv);
             out[2 * k + 1] = quant2((float)a.d[k].y, (float)b.d[k].y, scale, clipv, nclipv);
+        }
+    } else if (LLR_T == TDB200_LLR_F16) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            out[4 * k] = quant2(h_lo(a.h[k].x), h_lo(b.h[k].x), scale, clipv, nclipv);
+            out[4 * k + 1] = quant2(h_hi(a.h[k].x), h_hi(b.h[k].x), scale, clipv, nclipv);
+            out[4 * k + 2] = quant2(h_lo(a.h[k].y), h_lo(b.h[k].y), scale, clipv, nclipv);
+            out[4 * k + 3] = quant2(h_hi(a.h[k].y), h_hi(b.h[k].y), scale, clipv, nclipv);
         }
     } else {
 #pragma unroll
@@ -180,6 +196,7 @@ __device__ __forceinline__ int load1(const void *base, size_t idx, float scale, 
 {
     if (LLR_T == TDB200_LLR_F32) return quant(__ldg(static_cast<const float *>(base) + idx), scale, clip);
     if (LLR_T == TDB200_LLR_F64) return quant((float)__ldg(static_cast<const double *>(base) + idx), scale, clip);
+    if (LLR_T == TDB200_LLR_F16) return quant(__half2float(__ldg(static_cast<const __half *>(base) + idx)), scale, clip);
     const int v = (int)__ldg(static_cast<const int8_t *>(base) + idx);
     return max(min(v, clip), -clip);
 }
@@ -598,7 +615,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     if (KP && A.prefetch_stride > 0) {
         const long long nxt = (long long)2 * (blockIdx.x + A.prefetch_stride);
         if (nxt < A.n_cb) {
-            const size_t esz = LLR_T == TDB200_LLR_F64 ? 8 : (LLR_T == TDB200_LLR_F32 ? 4 : 1);
+            const size_t esz = LLR_T == TDB200_LLR_F64 ? 8 : (LLR_T == TDB200_LLR_F32 ? 4 : (LLR_T == TDB200_LLR_F16 ? 2 : 1));
             const char *p = static_cast<const char *>(A.llr) + (size_t)nxt * row * esz;
             const size_t nbytes = ((nxt + 1 < A.n_cb ? 2 : 1) * row * esz) & ~(size_t)15;
             const size_t chunk = 4096;
@@ -779,6 +796,7 @@ kernel_fn pick_kernel(const FastGeom &g, int llr_type)
     switch (llr_type) {
         case TDB200_LLR_F32: return pick_kernel_t<TDB200_LLR_F32>(g);
         case TDB200_LLR_F64: return pick_kernel_t<TDB200_LLR_F64>(g);
+        case TDB200_LLR_F16: return pick_kernel_t<TDB200_LLR_F16>(g);
         default: return pick_kernel_t<TDB200_LLR_S8>(g);
     }
 }
@@ -809,7 +827,7 @@ cudaError_t fast_s16_configure(FastGeom &g, int sm_count)
     cudaError_t e0 = cudaGetDevice(&dev);
     if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e0 != cudaSuccess) return e0;
-    for (int t = TDB200_LLR_F64; t <= TDB200_LLR_S8; t++) {
+    for (int t = TDB200_LLR_F64; t <= TDB200_LLR_F16; t++) {
         cudaError_t e = cudaFuncSetAttribute(pick_kernel(g, t), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
         if (e != cudaSuccess) return e;
     }

@@ -20,6 +20,7 @@
 // 32 lanes.  Warps never talk to each other, so the only synchronisation is __syncwarp().
 // Compile with -fmad=false: products here are exact (x * +-1, x * 0.5) so contraction would not
 // change results, but the flag keeps that a non-question.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "tdb200_internal.h"
@@ -52,6 +53,7 @@ __device__ __forceinline__ double load_llr_half(const void *p, int type, size_t 
     // flow_for_decode[i] *= 0.5, ITTC/log_map.cpp:1202-1205 (done on a copy)
     if (type == TDB200_LLR_F64) return static_cast<const double *>(p)[idx] * 0.5;
     if (type == TDB200_LLR_F32) return static_cast<double>(static_cast<const float *>(p)[idx]) * 0.5;
+    if (type == TDB200_LLR_F16) return static_cast<double>(__half2float(static_cast<const __half *>(p)[idx])) * 0.5;
     return static_cast<double>(static_cast<const int8_t *>(p)[idx]) * 0.0625;  // S8, 3 fractional bits
 }
 

@@ -24,7 +24,7 @@ ALGO_MAXLOG_F32 = 3
 ALGO_LINLOGMAP_F32 = 4
 ALGO_NAMES = {"logmap_f64": 0, "maxlog_s16": 1, "logmap_f32": 2, "maxlog_f32": 3, "linlogmap_f32": 4}
 
-LLR_F64, LLR_F32, LLR_S8 = 0, 1, 2
+LLR_F64, LLR_F32, LLR_S8, LLR_F16 = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 
 
@@ -110,7 +110,7 @@ def _ptr_of(x):
     return x.ctypes.data, MEM_HOST
 
 
-_LLR_TYPES = {"float64": LLR_F64, "float32": LLR_F32, "int8": LLR_S8}
+_LLR_TYPES = {"float64": LLR_F64, "float32": LLR_F32, "int8": LLR_S8, "float16": LLR_F16}
 
 
 class TurboDecoder:
