@@ -149,7 +149,7 @@ void tdo_turbo_encode(const int *bits, int K, const int *pi, int *coded)
     int T = K + MREG;
     int *rsc1 = (int *)malloc(sizeof(int) * 2 * T);
     int *rsc2 = (int *)malloc(sizeof(int) * 2 * T);
-    int *in2 = (int *)malloc(sizeof(int) * K);
+    int *in2 = (int *)calloc((size_t)K, sizeof(int));
     rsc_encode(bits, K, rsc1);
     for (int i = 0; i < K; i++) in2[i] = bits[pi[i]]; /* randominterleaver_int, :54-63 */
     rsc_encode(in2, K, rsc2);
