@@ -115,8 +115,12 @@ def run_reference(args):
     from turbo_decoder_cuda_b200 import synth
     cores = host_cores()
     decode, kind = cpu_reference_decoder()
-    # a bounded sample per step: ~5 s of CPU work at ~25 ms per codeword and core
-    n_sample = args.ref_sample or min(args.batch, 192 * cores)
+    # a bounded sample per step, sized from a calibration decode so that the whole run (all steps) stays
+    # near two minutes of wall time whatever --steps is
+    _, cal = synth.make_batch(K, max(cores, 1), args.ebn0, seed=999, device="cpu", dtype=torch.float64)
+    _, t_cal = decode(cal.numpy(), cores)           # seconds for one codeword per core
+    budget_s = 120.0
+    n_sample = args.ref_sample or int(max(cores, min(args.batch, cores * budget_s / (max(args.steps, 1) * max(t_cal, 1e-3)))))
     bits, llr = synth.make_batch(K, n_sample, args.ebn0, seed=1000, device="cpu", dtype=torch.float64)
     llr = llr.numpy()
     for _ in range(args.warmup):
