@@ -83,3 +83,21 @@ def test_encode_channel_decode_round_trip(oracle):
         llr = dec.channel(dec.encode(bits), oracle.sigma(1.5, K), seed=5, dtype=dt)
         out = dec.decode(llr, want=("bits",))
         assert torch.equal(out["bits"], bits), algo
+
+
+def test_cpp_multi_gpu_caller():
+    """compat/tdb200_burst.cpp: a C++ program over the C ABI (no Python, no torch in that process), one host
+    thread per visible GPU, codeblock-sharded.  At 2 dB nothing may be in error."""
+    _torch_cuda()
+    import json
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "turbo_decoder_cuda_b200", "lib", "tdb200_burst")
+    if not os.path.exists(exe):
+        pytest.skip("tdb200_burst not built")
+    out = subprocess.run([exe, "--total", "3001", "--chunk", "1024", "--ebn0", "2.0", "--early-term", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["codeblocks"] == 3001 and r["bit_errors"] == 0 and r["frame_errors"] == 0
+    assert 2.0 <= r["mean_iters"] < 8.0 and r["gbit_s"] > 1.0

@@ -5,6 +5,7 @@
 Outputs (git-ignored, shipped to the GPU box by gpurun):
     turbo_decoder_cuda_b200/lib/libtdb200.so         C ABI (include/tdb200.h) + kernels
     turbo_decoder_cuda_b200/lib/libtdb200_compat.so  reference-signature C++ wrappers (compat/)
+    turbo_decoder_cuda_b200/lib/tdb200_burst         C++ multi-GPU caller of the C ABI (compat/tdb200_burst.cpp)
 """
 import os
 import shutil
@@ -84,6 +85,15 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("compat build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    burst_src = os.path.join(COMPAT, "tdb200_burst.cpp")
+    burst_exe = os.path.join(LIB, "tdb200_burst")
+    if os.path.exists(burst_src) and (force or _stale(burst_exe, [burst_src, so] + hdrs)):
+        # a plain C++ caller of the C ABI (one host thread per GPU); nvcc only to find the CUDA runtime
+        cmd = [nvcc, "-O2", "-std=c++17", "-I", INCLUDE, burst_src, "-o", burst_exe, "-L", LIB, "-ltdb200",
+               "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-Xcompiler", "-pthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("tdb200_burst build failed:\n%s\n%s" % (r.stdout, r.stderr))
     if verbose:
         sys.stderr.write("".join(log))
     if any(log):
