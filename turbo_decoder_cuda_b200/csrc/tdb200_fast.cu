@@ -772,21 +772,25 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
 
 typedef void (*kernel_fn)(FastArgs);
 
-// Specialised (compile-time geometry) instances: 128 sub-blocks of 48 / 40 / 32 steps (K = 6144, the
-// BASELINE size, 5120, 4096) and K=6144 as 192 sub-blocks of 32 steps, guard 16; everything else runs
-// the generic kernel.
-bool spec128(const FastGeom &g) { return g.P == 128 && g.NW >= 4 && g.NW <= 6 && g.G == 16 && g.PP == 129; }
-bool spec128g8(const FastGeom &g) { return g.P == 128 && g.NW == 6 && g.G == 8 && g.PP == 129; }  // K=6144, guard 8: -0.04 dB, +6 %
+// Compile-time geometry exists for P sub-blocks of 8*NW steps with guard 16, P in {32, 64, 128}, NW in {4, 5, 6}
+// (K = 1024 ... 6144 in nine sizes -- the BASELINE size is P=128, NW=6), plus two alternative
+// plans for K = 6144: guard 8, and 192 sub-blocks of 32 steps.  Everything else runs the generic kernel.
+bool spec_pn(const FastGeom &g) { return (g.P == 32 || g.P == 64 || g.P == 128) && g.NW >= 4 && g.NW <= 6 && g.G == 16 && g.PP == (g.P | 1); }
+bool spec128g8(const FastGeom &g) { return g.P == 128 && g.NW == 6 && g.G == 8 && g.PP == 129; }  // -0.04 dB, +4 %
 bool spec192(const FastGeom &g) { return g.P == 192 && g.NW == 4 && g.G == 16 && g.PP == 193; }
+
+template <int LLR_T, int KP>
+kernel_fn pick_nw(int NW)
+{
+    if (NW == 6) return fast_s16_kernel<LLR_T, KP, 6, 16>;
+    if (NW == 5) return fast_s16_kernel<LLR_T, KP, 5, 16>;
+    return fast_s16_kernel<LLR_T, KP, 4, 16>;
+}
 
 template <int LLR_T>
 kernel_fn pick_kernel_t(const FastGeom &g)
 {
-    if (spec128(g)) {  // K = 1024 * NW: 6144, 5120, 4096
-        if (g.NW == 6) return fast_s16_kernel<LLR_T, 128, 6, 16>;
-        if (g.NW == 5) return fast_s16_kernel<LLR_T, 128, 5, 16>;
-        return fast_s16_kernel<LLR_T, 128, 4, 16>;
-    }
+    if (spec_pn(g)) return g.P == 128 ? pick_nw<LLR_T, 128>(g.NW) : (g.P == 64 ? pick_nw<LLR_T, 64>(g.NW) : pick_nw<LLR_T, 32>(g.NW));
     if (spec128g8(g)) return fast_s16_kernel<LLR_T, 128, 6, 8>;
     if (spec192(g)) return fast_s16_kernel<LLR_T, 192, 4, 16>;
     return fast_s16_kernel<LLR_T, 0, 0, 0>;
@@ -803,7 +807,7 @@ kernel_fn pick_kernel(const FastGeom &g, int llr_type)
 
 }  // namespace
 
-bool fast_s16_specialised(const FastGeom &g) { return spec128(g) || spec128g8(g) || spec192(g); }
+bool fast_s16_specialised(const FastGeom &g) { return spec_pn(g) || spec128g8(g) || spec192(g); }
 
 // bytes of one codeblock-pair region / of the part shared by the pairs of a CTA of `threads` threads
 int fast_s16_pair_bytes(const FastGeom &g)
