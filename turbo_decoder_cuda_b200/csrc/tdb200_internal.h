@@ -142,6 +142,8 @@ struct EncodeArgs {
     uint8_t *coded;       // [n_cb][3K+12] device
     const int *pi;        // [K] device
     int K, n_cb;
+    int stride_bits, stride_out, stride_pi;  // shared-memory chunk strides, filled in by launch_encode
+    unsigned magic_c, magic_3c;              // ceil(2^32 / C), ceil(2^32 / 3C), C = ceil(K/32)
 };
 struct ChannelArgs {
     const uint8_t *coded;  // [n] device
