@@ -101,3 +101,38 @@ def test_cpp_multi_gpu_caller():
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["codeblocks"] == 3001 and r["bit_errors"] == 0 and r["frame_errors"] == 0
     assert 2.0 <= r["mean_iters"] < 8.0 and r["gbit_s"] > 1.0
+
+
+def test_device_path_is_cuda_graph_capturable():
+    """With device buffers the three entry points only enqueue kernels on the caller's stream, so a whole
+    encode -> channel -> decode step can be captured once and replayed as a CUDA graph."""
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder, decoder as tdb
+    from turbo_decoder_cuda_b200.synth import sigma_from_ebn0
+    K, n = 6144, 64
+    dec = TurboDecoder(K, n_iter=8, algo="maxlog_s16", max_batch=n)
+    bits = torch.randint(0, 2, (n, K), dtype=torch.uint8, device="cuda")
+    coded = torch.empty((n, 3 * K + 12), dtype=torch.uint8, device="cuda")
+    llr = torch.empty((n, 3 * K + 12), dtype=torch.float32, device="cuda")
+    out = torch.zeros((n, K), dtype=torch.uint8, device="cuda")
+    L = dec._L
+    sigma = sigma_from_ebn0(1.5, K)
+
+    def step(stream):
+        assert L.tdb200_encode_batch(dec._h, bits.data_ptr(), coded.data_ptr(), tdb.MEM_DEVICE, n, stream) == 0
+        assert L.tdb200_channel_batch(dec._h, coded.data_ptr(), llr.data_ptr(), tdb.LLR_F32, tdb.MEM_DEVICE, n, sigma, 3, stream) == 0
+        dec.decode_raw(llr.data_ptr(), tdb.LLR_F32, tdb.MEM_DEVICE, n, bits=out.data_ptr(), stream=stream)
+
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        step(s.cuda_stream)          # warm-up outside the capture (lazy module loading)
+    s.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        step(torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        bits.copy_(torch.randint(0, 2, (n, K), dtype=torch.uint8, device="cuda"))
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, bits)
