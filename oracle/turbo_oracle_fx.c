@@ -4,7 +4,7 @@
  * TEST INFRASTRUCTURE ONLY (see turbo_oracle.h).  This is NOT a restatement of reference
  * code: the reference's CPU path is the fp64 Log-MAP in turbo_oracle.c.  It is the bit-exact
  * integer specification of the throughput kernel TDB200_ALGO_MAXLOG_S16
- * (turbo_decoder_cuda_b200/csrc/tdb200_fast.cu), written with plain int32 scalars and range
+ * (turbo_decoder_cuda_b200/csrc/tdb200_fast_kernel.cuh), written with plain int32 scalars and range
  * checks, so that the packed-s16x2 CUDA arithmetic can be verified bit for bit (hard
  * decisions AND extrinsics).  Its relation to the reference is algorithmic: it is
  * Log_MAP_decoder() (ITTC/log_map.cpp:898-1047) with

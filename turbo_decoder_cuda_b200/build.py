@@ -27,7 +27,12 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE
 KERNEL_TUS = [
     ("tdb200_api.cu", []),
     ("tdb200_ref64.cu", ["-fmad=false"]),
-    ("tdb200_fast.cu", ["-Xptxas", "-v"]),
+    ("tdb200_fast.cu", []),
+    # the throughput kernel: one translation unit per channel-LLR type, compiled in parallel
+    ("tdb200_fast_inst_f32.cu", ["-Xptxas", "-v"]),
+    ("tdb200_fast_inst_f64.cu", ["-Xptxas", "-v"]),
+    ("tdb200_fast_inst_s8.cu", ["-Xptxas", "-v"]),
+    ("tdb200_fast_inst_f16.cu", ["-Xptxas", "-v"]),
     ("tdb200_f32.cu", ["-fmad=false", "-Xptxas", "-v"]),
     ("tdb200_encode.cu", []),
 ]
@@ -59,6 +64,7 @@ def build(force=False, verbose=False):
     hdrs = _headers()
     objs = []
     log = []
+    jobs = []
     for src, extra in KERNEL_TUS:
         s = os.path.join(CSRC, src)
         if not os.path.exists(s):
@@ -66,11 +72,20 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + ARCH + COMMON + extra + ["-c", s, "-o", o]
-            r = subprocess.run(cmd, capture_output=True, text=True)
-            log.append(r.stderr)
-            if r.returncode != 0:
-                raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+            jobs.append((src, [nvcc] + ARCH + COMMON + extra + ["-c", s, "-o", o]))
+
+    def _compile(job):
+        src, cmd = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, r
+
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+            for src, r in pool.map(_compile, jobs):
+                log.append(r.stderr)
+                if r.returncode != 0:
+                    raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
     so = os.path.join(LIB, "libtdb200.so")
     if force or _stale(so, objs):
         cmd = [nvcc] + ARCH + ["-shared", "-o", so] + objs + ["-cudart", "static"]

@@ -10,7 +10,7 @@
 // oracle/turbo_oracle_f32.c; the max-log variant is bit-exact against it, the Log-MAP variant agrees
 // to the accuracy of the hardware ex2/lg2 approximations.
 //
-// Layout and schedule are those of the packed-int16 kernel (tdb200_fast.cu), one codeblock per CTA:
+// Layout and schedule are those of the packed-int16 kernel (tdb200_fast_kernel.cuh), one codeblock per CTA:
 //   * thread t owns trellis steps [tL,(t+1)L), 8 state metrics in registers;
 //   * boundary vectors = the neighbour's vector G steps before/after the boundary from the previous
 //     iteration, re-run over the G guard steps (warm-up);
@@ -119,7 +119,7 @@ __device__ __forceinline__ float load_llr(const void *base, size_t idx)
     return (x == x) ? x : 0.f;  // NaN -> erasure
 }
 
-// One SISO pass of one sub-block; see siso_pass in tdb200_fast.cu for the schedule.
+// One SISO pass of one sub-block; see siso_pass in tdb200_fast_kernel.cuh for the schedule.
 template <int LM, bool IL>
 __device__ __forceinline__ unsigned siso_pass(const Pass &c, const Smem &sm, const __half *par, float (&na)[8], float (&nb)[8],
                                               const bool first_fixed, const bool last_fixed, const bool want, float *g_llr, float *g_ext,

@@ -1,0 +1,798 @@
+// tdb200_fast_kernel.cuh -- TDB200_ALGO_MAXLOG_S16: the throughput decoder.
+//
+// What it computes (bit-exact integer specification: oracle/turbo_oracle_fx.c):
+// the iterative PCCC decode of TurboDecoding() (ITTC/log_map.cpp:1146-1280) with the
+// component decoder Log_MAP_decoder() (:898-1047) evaluated as max-log-MAP in 16-bit fixed
+// point.  How it is laid out has nothing in common with the reference's loops:
+//
+//  * ONE CTA DECODES TWO CODEBLOCKS, ALL ITERATIONS, ON CHIP.  The two codeblocks ride in the
+//    low/high halves of every 32-bit register (s16x2), so each VIADD.16x2 / VIADDMNMX.S16x2
+//    advances both.  Channel LLRs are read from HBM exactly once (128-bit loads, fused with
+//    quantisation and de-multiplexing into shared memory, cf. demultiplex() :1083-1127) and only
+//    hard decisions go back.
+//  * SUB-BLOCK PARALLEL BCJR.  The K-step trellis is cut into P = K/L sub-blocks; thread t
+//    owns steps [tL,(t+1)L) and keeps all 8 state metrics in registers (no shuffles, no
+//    barriers inside the recursions).  Boundary metrics come from the neighbouring sub-block:
+//    the vector it saved G steps before the boundary in the PREVIOUS iteration (next-iteration
+//    initialisation) is re-run over those G guard steps (warm-up) before each pass.
+//  * ALPHA IS RECOMPUTED, NOT STORED.  A forward sweep leaves one alpha checkpoint per 8-step
+//    window (7 words, in shared memory); the backward sweep re-creates the 8 alpha vectors of a
+//    window in registers, then runs beta and the extrinsic output over it.  Shared memory
+//    therefore holds only the a-priori/parity values, never the 8 x K metric array.
+//  * BRANCH METRICS ARE FREE.  With gamma(b,c) = b*U + c*V (U = Ls + La, V = Lp; the per-step
+//    constant the reference adds to every branch is dropped) a trellis step is 5 adds + 8 fused
+//    add-max; the reference's gamma table (:962-972) never exists.
+//  * U IS STORED, NOT La.  X[n] = Ls[n] + La[n] is kept per information bit; each SISO reads it
+//    (SISO-2 through the QPP permutation), and overwrites it in place with Ls + its own scaled
+//    extrinsic, which is exactly the other SISO's U.  Interleave/de-interleave (:54-96,
+//    :1221,:1242) are thus the addressing of one read and one write, conflict-free in the
+//    step-major layout (tdb200_internal.h).
+//  * Tail bits only shape the beta vector at step K (La is zero there, :1224-1227), so they are
+//    folded into a constant start vector once per decode.
+//  * EARLY TERMINATION (new functionality; the reference only has a placeholder,
+//    previous/Decoder.cc:1098-1099): every thread keeps the hard decisions of its own steps as a
+//    bit mask; a codeblock stops after the first iteration (>= 2) that changes none of them and
+//    leaves every |a-posteriori| at or above a threshold.  A CTA leaves when all its codeblocks did.
+//  * THE ALU PIPE IS THE BOUND (VIADDMNMX issues there and nowhere else), so address arithmetic,
+//    bit-wise NOT, byte packing and the 3/4 extrinsic scale are written as IMADs with opaque
+//    constants (PassCfg) to keep them on the fma-heavy pipe; the backward sweep is ONE rolled
+//    window body per pass (instruction-cache footprint).
+//
+// The kernel is a template over the geometry: K = 6144 / 5120 / 4096 (128 sub-blocks of 48 / 40 / 32
+// steps, guard 16) get compile-time constants -- every shared-memory address becomes
+// base+immediate -- and every other LTE size runs the same code with run-time geometry, several
+// codeblock pairs side by side in one CTA when a codeblock needs fewer than 32 threads.
+//
+// This header holds the device code and the per-input-type kernel table; it is instantiated once
+// per channel-LLR type in its own translation unit (tdb200_fast_inst_*.cu) so that the ~12 kernel
+// variants of each type compile in parallel.  The host side is tdb200_fast.cu.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "tdb200_internal.h"
+
+namespace tdb200 {
+namespace {
+
+typedef uint32_t w32;  // two int16 lanes: codeblock A in bits 0-15, codeblock B in bits 16-31
+
+__device__ __forceinline__ w32 vadd(w32 a, w32 b) { return __vadd2(a, b); }                        // VIADD.16x2      (fma-heavy pipe)
+__device__ __forceinline__ w32 vaddmax(w32 a, w32 b, w32 c) { return __viaddmax_s16x2(a, b, c); }  // VIADDMNMX.S16x2 (alu pipe): max(a+b,c)
+__device__ __forceinline__ w32 vneg(w32 a) { return __vadd2(~a, 0x00010001u); }
+__device__ __forceinline__ w32 pack2(int lo, int hi) { return (w32)(lo & 0xffff) | ((w32)hi << 16); }
+__device__ __forceinline__ w32 dup2(int v) { return pack2(v, v); }
+
+__device__ __forceinline__ void norm8(w32 (&m)[8])
+{
+    const w32 nz = vneg(m[0]);
+    m[0] = 0;
+#pragma unroll
+    for (int s = 1; s < 8; s++) m[s] = vadd(m[s], nz);
+}
+
+// alpha(i+1) from alpha(i); u = U_i, v = V_i   (the max-log form of :975-1001)
+__device__ __forceinline__ void alpha_step_to(const w32 (&a)[8], w32 u, w32 v, w32 (&o)[8])
+{
+    const w32 w = vadd(u, v);
+    const w32 t5 = vadd(a[2], v), t1 = vadd(a[3], v), t2 = vadd(a[4], v), t6 = vadd(a[5], v);
+    const w32 o0 = vaddmax(a[1], w, a[0]), o4 = vaddmax(a[0], w, a[1]);
+    const w32 o5 = vaddmax(a[3], u, t5), o1 = vaddmax(a[2], u, t1);
+    const w32 o2 = vaddmax(a[5], u, t2), o6 = vaddmax(a[4], u, t6);
+    const w32 o7 = vaddmax(a[7], w, a[6]), o3 = vaddmax(a[6], w, a[7]);
+    o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3; o[4] = o4; o[5] = o5; o[6] = o6; o[7] = o7;
+}
+__device__ __forceinline__ void alpha_step(w32 (&a)[8], w32 u, w32 v) { alpha_step_to(a, u, v, a); }
+
+// beta(i) from beta(i+1)   (:1004-1021)
+__device__ __forceinline__ void beta_step(w32 (&b)[8], w32 u, w32 v)
+{
+    const w32 w = vadd(u, v);
+    const w32 t2 = vadd(b[5], v), t3 = vadd(b[1], v), t4 = vadd(b[2], v), t5 = vadd(b[6], v);
+    const w32 o0 = vaddmax(b[4], w, b[0]), o1 = vaddmax(b[0], w, b[4]);
+    const w32 o2 = vaddmax(b[1], u, t2), o3 = vaddmax(b[5], u, t3);
+    const w32 o4 = vaddmax(b[6], u, t4), o5 = vaddmax(b[2], u, t5);
+    const w32 o6 = vaddmax(b[3], w, b[7]), o7 = vaddmax(b[7], w, b[3]);
+    b[0] = o0; b[1] = o1; b[2] = o2; b[3] = o3; b[4] = o4; b[5] = o5; b[6] = o6; b[7] = o7;
+}
+
+// ---- channel-LLR load + quantisation (q = clamp(rint(x * 2^F), +-clip), oracle: quant())
+__device__ __forceinline__ int quant(float x, float scale, int clip)
+{
+    float s = x * scale;
+    if (!(s == s)) return 0;
+    s = fminf(fmaxf(s, -32767.0f), 32767.0f);
+    const int q = __float2int_rn(s);
+    return max(min(q, clip), -clip);
+}
+
+// Two channel values (codeblock A, codeblock B) -> one clipped s16x2.  cvt.rni.sat.s16.f32 rounds
+// to nearest even, saturates and maps NaN to 0, exactly like quant() above for |clip| <= 32767.
+__device__ __forceinline__ w32 quant2(float a, float b, float scale, w32 clipv, w32 nclipv)
+{
+    short qa, qb;
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(qa) : "f"(a * scale));
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(qb) : "f"(b * scale));
+    w32 p;
+    asm("mov.b32 %0, {%1, %2};" : "=r"(p) : "h"(qa), "h"(qb));
+    return __vmins2(__vmaxs2(p, nclipv), clipv);
+}
+
+// 12 consecutive input values (4 systematic/parity1/parity2 triplets) of one codeblock, starting at
+// element 12*q, as loaded (128-bit loads for the float types)
+template <int LLR_T>
+struct Raw12 {
+    float4 f[LLR_T == TDB200_LLR_F32 ? 3 : 1];
+    double2 d[LLR_T == TDB200_LLR_F64 ? 6 : 1];
+    int w[LLR_T == TDB200_LLR_S8 ? 3 : 1];
+    uint2 h[LLR_T == TDB200_LLR_F16 ? 3 : 1];  // 4 halves each
+};
+
+template <int LLR_T>
+__device__ __forceinline__ void load12(const void *base, size_t row_elems, int cb, int q, Raw12<LLR_T> &r)
+{
+    if (LLR_T == TDB200_LLR_F32) {
+        const float4 *p = reinterpret_cast<const float4 *>(static_cast<const float *>(base) + (size_t)cb * row_elems) + 3 * q;
+#pragma unroll
+        for (int k = 0; k < 3; k++) r.f[k] = __ldg(p + k);
+    } else if (LLR_T == TDB200_LLR_F64) {
+        const double2 *p = reinterpret_cast<const double2 *>(static_cast<const double *>(base) + (size_t)cb * row_elems) + 6 * q;
+#pragma unroll
+        for (int k = 0; k < 6; k++) r.d[k] = __ldg(p + k);
+    } else if (LLR_T == TDB200_LLR_F16) {
+        const uint2 *p = reinterpret_cast<const uint2 *>(static_cast<const __half *>(base) + (size_t)cb * row_elems) + 3 * q;
+#pragma unroll
+        for (int k = 0; k < 3; k++) r.h[k] = __ldg(p + k);
+    } else {
+        const int *p = reinterpret_cast<const int *>(static_cast<const int8_t *>(base) + (size_t)cb * row_elems) + 3 * q;
+#pragma unroll
+        for (int k = 0; k < 3; k++) r.w[k] = __ldg(p + k);
+    }
+}
+__device__ __forceinline__ float h_lo(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+__device__ __forceinline__ float h_hi(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
+// quantise + pack the 12 values of codeblocks A and B into 12 s16x2 words
+template <int LLR_T>
+__device__ __forceinline__ void pack12(const Raw12<LLR_T> &a, const Raw12<LLR_T> &b, float scale, w32 clipv, w32 nclipv, w32 (&out)[12])
+{
+    if (LLR_T == TDB200_LLR_F32) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            out[4 * k] = quant2(a.f[k].x, b.f[k].x, scale, clipv, nclipv);
+            out[4 * k + 1] = quant2(a.f[k].y, b.f[k].y, scale, clipv, nclipv);
+            out[4 * k + 2] = quant2(a.f[k].z, b.f[k].z, scale, clipv, nclipv);
+            out[4 * k + 3] = quant2(a.f[k].w, b.f[k].w, scale, clipv, nclipv);
+        }
+    } else if (LLR_T == TDB200_LLR_F64) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            out[2 * k] = quant2((float)a.d[k].x, (float)b.d[k].x, scale, clipv, nclipv);
+            out[2 * k + 1] = quant2((float)a.d[k].y, (float)b.d[k].y, scale, clipv, nclipv);
+        }
+    } else if (LLR_T == TDB200_LLR_F16) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            out[4 * k] = quant2(h_lo(a.h[k].x), h_lo(b.h[k].x), scale, clipv, nclipv);
+            out[4 * k + 1] = quant2(h_hi(a.h[k].x), h_hi(b.h[k].x), scale, clipv, nclipv);
+            out[4 * k + 2] = quant2(h_lo(a.h[k].y), h_lo(b.h[k].y), scale, clipv, nclipv);
+            out[4 * k + 3] = quant2(h_hi(a.h[k].y), h_hi(b.h[k].y), scale, clipv, nclipv);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            // bytes {a_m, sign(a_m), b_m, sign(b_m)}; prmt, not __byte_perm: the intrinsic drops the
+            // sign-replication bit of the selector
+            w32 p0, p1, p2, p3;
+            asm("prmt.b32 %0, %1, %2, 0xc480;" : "=r"(p0) : "r"(a.w[k]), "r"(b.w[k]));
+            asm("prmt.b32 %0, %1, %2, 0xd591;" : "=r"(p1) : "r"(a.w[k]), "r"(b.w[k]));
+            asm("prmt.b32 %0, %1, %2, 0xe6a2;" : "=r"(p2) : "r"(a.w[k]), "r"(b.w[k]));
+            asm("prmt.b32 %0, %1, %2, 0xf7b3;" : "=r"(p3) : "r"(a.w[k]), "r"(b.w[k]));
+            out[4 * k] = __vmins2(__vmaxs2(p0, nclipv), clipv);
+            out[4 * k + 1] = __vmins2(__vmaxs2(p1, nclipv), clipv);
+            out[4 * k + 2] = __vmins2(__vmaxs2(p2, nclipv), clipv);
+            out[4 * k + 3] = __vmins2(__vmaxs2(p3, nclipv), clipv);
+        }
+    }
+}
+
+template <int LLR_T>
+__device__ __forceinline__ int load1(const void *base, size_t idx, float scale, int clip)
+{
+    if (LLR_T == TDB200_LLR_F32) return quant(__ldg(static_cast<const float *>(base) + idx), scale, clip);
+    if (LLR_T == TDB200_LLR_F64) return quant((float)__ldg(static_cast<const double *>(base) + idx), scale, clip);
+    if (LLR_T == TDB200_LLR_F16) return quant(__half2float(__ldg(static_cast<const __half *>(base) + idx)), scale, clip);
+    const int v = (int)__ldg(static_cast<const int8_t *>(base) + idx);
+    return max(min(v, clip), -clip);
+}
+
+struct Smem {
+    w32 *X, *par1, *par2;
+    uint8_t *sysA, *sysB;  // systematic value + 128 of codeblock A / B, one byte per trellis step
+    uint16_t *tab;
+    w32 *ckpt, *dec, *edge;
+};
+
+// Constants the compiler must not see through: ptxas strength-reduces x*-1-1, x*2, x*65536 and
+// mulhi(x, 3<<30) into ALU-pipe instructions (IADD3 / LEA / PRMT / SHF), and the ALU pipe is the one
+// the add-compare-select instructions saturate.  Passed as kernel arguments they stay IMADs on the
+// fma-heavy pipe, which has slack.
+struct PassCfg {
+    int q2;
+    w32 lim1;    // dup2(ext_lim + 1): the +1 completes m1 + ~m0 = m1 - m0 - 1
+    w32 limmax;  // dup2(2*ext_lim - 1)
+    w32 unbias;  // dup2(-(3*ext_lim/4) - 128) or dup2(-ext_lim - 128): extrinsic bias and systematic-byte bias
+    w32 neg1;    // 0xffffffff
+    w32 four;    // 4
+    w32 k64k;    // 65536
+    w32 k3q;     // 0xC0000000: mulhi(y, k3q) = (3*y) >> 2
+    w32 etT, et2T, etmask;  // dup2(T), dup2(2T), dup2(2T-1): magnitude test of the stopping rule
+};
+
+__device__ __forceinline__ w32 vnot_fma(w32 x, w32 neg1) { return x * neg1 + neg1; }  // ~x
+
+#ifndef TDB_LAMBDA_V3
+#define TDB_LAMBDA_V3 2
+#endif
+
+// max of four (alpha + beta') sums.  Form A: 1 fma-pipe + 3 ALU-pipe instructions; form B (three-input
+// maximum): 3 fma-pipe + 2 ALU-pipe.  TDB_LAMBDA_V3 of the four groups per step use form B, which is
+// what balances the two pipes in the backward window.
+template <bool V3>
+__device__ __forceinline__ w32 max4sum(w32 a0, w32 b0, w32 a1, w32 b1, w32 a2, w32 b2, w32 a3, w32 b3)
+{
+    if (V3) return vaddmax(a3, b3, __vimax3_s16x2(vadd(a0, b0), vadd(a1, b1), vadd(a2, b2)));
+    return vaddmax(a3, b3, vaddmax(a2, b2, vaddmax(a1, b1, vadd(a0, b0))));
+}
+
+// e - 1, where e = max_{input 1}(alpha + c*V + beta') - max_{input 0}(alpha + c*V + beta')
+// (:1024-1039 as max-log; the +U common to all input-1 branches is left out, so e IS the extrinsic
+// of :1234-1238).  The -1 is absorbed by the clamp constant.
+__device__ __forceinline__ w32 extrinsic_m1(const w32 (&a)[8], const w32 (&b)[8], w32 v, w32 neg1)
+{
+    const w32 m0a = max4sum<(TDB_LAMBDA_V3 > 0)>(a[0], b[0], a[1], b[4], a[6], b[7], a[7], b[3]);
+    const w32 m0b = max4sum<(TDB_LAMBDA_V3 > 2)>(a[2], b[5], a[3], b[1], a[4], b[2], a[5], b[6]);
+    const w32 m1a = max4sum<(TDB_LAMBDA_V3 > 3)>(a[0], b[4], a[1], b[0], a[6], b[3], a[7], b[7]);
+    const w32 m1b = max4sum<(TDB_LAMBDA_V3 > 1)>(a[2], b[1], a[3], b[5], a[4], b[6], a[5], b[2]);
+    const w32 m0 = vaddmax(m0b, v, m0a);
+    const w32 m1 = vaddmax(m1a, v, m1b);
+    return vadd(m1, vnot_fma(m0, neg1));
+}
+
+// Where a trellis step's a-priori word X and systematic byte pair live.  Natural-order passes
+// address them by step index (base + immediate); interleaved passes go through tab, which holds the
+// word index e of the element: its byte offset in the systematic planes, a quarter of the one in X.
+struct Elem {
+    unsigned xoff, soff;  // byte offsets into X / the systematic byte planes
+};
+template <bool IL>
+__device__ __forceinline__ Elem elem_of(const PassCfg &c, unsigned tabval, int idx)
+{
+    Elem e;
+    e.soff = IL ? tabval : (unsigned)idx;
+    e.xoff = IL ? tabval * c.four : 4u * (unsigned)idx;
+    return e;
+}
+template <bool IL>
+__device__ __forceinline__ Elem elem_at(const PassCfg &c, const Smem &sm, int idx)
+{
+    return elem_of<IL>(c, IL ? (unsigned)sm.tab[idx] : 0u, idx);
+}
+__device__ __forceinline__ w32 &word_at(w32 *base, unsigned xoff)
+{
+    return *reinterpret_cast<w32 *>(reinterpret_cast<unsigned char *>(base) + xoff);
+}
+__device__ __forceinline__ w32 &x_at(const Smem &sm, const Elem &e) { return word_at(sm.X, e.xoff); }
+// systematic values of the two codeblocks, each + 128, as an s16x2: one byte load per codeblock
+// (separate planes, so the compiler cannot merge them into a 16-bit load + two PRMTs) and one IMAD
+__device__ __forceinline__ w32 sys_biased(const PassCfg &c, const Smem &sm, const Elem &e)
+{
+    return (w32)sm.sysB[e.soff] * c.k64k + (w32)sm.sysA[e.soff];
+}
+
+// Backward sweep over one 8-step window whose first alpha vector is a0 (normalised): re-create
+// the window's alpha vectors in registers, then run beta, the extrinsic output and the in-place
+// update of X over it.  tabin: the window's table entries (interleaved passes fetch them one window
+// ahead, so the look-up is off the critical path).  Returns the decision bits of the window (WANT
+// only): sign of step k in bit 15-k (codeblock A) / 31-k (codeblock B); weak collects, per lane, a
+// non-zero value if some |a-posteriori| of the window is below the stopping threshold.
+template <bool IL, bool WANT>
+__device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, const w32 *par, const int base, const int PP,
+                                          const unsigned (&tabin)[8], const w32 (&a0)[8], w32 (&b)[8], w32 *stage, w32 &weak)
+{
+    w32 aw[8][8], u[8], v[8];
+    Elem el[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) aw[0][s] = a0[s];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int idx = base + k * PP;
+        el[k] = elem_of<IL>(c, tabin[k], idx);
+        u[k] = x_at(sm, el[k]);
+        v[k] = par[idx];
+        if (k < 7) alpha_step_to(aw[k], u[k], v[k], aw[k + 1]);
+    }
+    norm8(b);
+    w32 acc = 0;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+        const w32 exm1 = extrinsic_m1(aw[k], b, v[k], c.neg1);
+        // clamp to [-lim, lim-1], bias to [0, 2lim-1]
+        const w32 y = __viaddmin_s16x2_relu(exm1, c.lim1, c.limmax);
+        w32 es;
+        if (c.q2 == 3) es = __umulhi(y, c.k3q) & 0x3fff3fffu;  // floor(3(ec+lim)/4) per lane
+        else es = y;
+        x_at(sm, el[k]) = vadd(vadd(sys_biased(c, sm, el[k]), es), c.unbias);
+        if (WANT) {
+            const w32 lam = vadd(vadd(u[k], exm1), 0x00010001u);  // a-posteriori, :1038 (+ the dropped U)
+            acc = (acc >> 1) | (lam & 0x80008000u);
+            // clamp(lam + T, 0, 2T) is 0 or 2T exactly when |lam| >= T (lam >= T or lam <= -T)
+            weak |= __viaddmin_s16x2_relu(lam, c.etT, c.et2T) & c.etmask;
+            if (stage) word_at(stage, el[k].xoff) = lam;
+        }
+        beta_step(b, u[k], v[k]);
+    }
+    return acc;
+}
+
+// One SISO pass of one sub-block (thread `t` of its codeblock pair; inactive threads only take part in
+// the barriers and the boundary exchange).  IL = false: SISO-1 (natural order), true: SISO-2 (through tab).
+// na/nb: boundary vectors (alpha G steps before the sub-block, beta G steps after it); on return
+// they hold the vectors for the next iteration of this SISO.  With WANT the hard decisions of this
+// pass go to sm.dec (one word per two windows) and the return value has bits 0-15 / 16-31 set
+// where a decision of codeblock A / B differs from what sm.dec held before; weak gets a non-zero
+// low / high half if some a-posteriori magnitude of codeblock A / B is below the stopping threshold.
+template <bool IL, bool WANT, int KP, int KNW, int KG>
+__device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, const Smem &sm, const w32 *par, w32 (&na)[8], w32 (&nb)[8],
+                                         const int t, const bool active, const bool first_fixed, const bool last_fixed, w32 *stage,
+                                         w32 &weak)
+{
+    const int P = KP ? KP : g.P, PP = KP ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW, G = KP ? KG : g.G;
+    const int L = 8 * NW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int w_sa = (L - G) >> 3, w_sb = G >> 3;
+    w32 a[8], b[8], a0[8], sa[8], sb[8];
+    w32 changed = 0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) { a[s] = na[s]; b[s] = nb[s]; sa[s] = 0; sb[s] = 0; }
+
+    unsigned offn[8];  // interleaved passes: table entries of the window that is processed next
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) offn[k] = IL ? (unsigned)sm.tab[k * PP + t] : 0u;
+        // ---- warm-up: alpha over the last G steps of sub-block t-1 and beta over the first G steps
+        //      of sub-block t+1, advanced together (two independent dependency chains).  The two
+        //      edge threads run it on their own sub-block and throw the result away, which keeps the
+        //      loop free of divergence.
+        const int ta = first_fixed ? t : t - 1, tb = last_fixed ? t : t + 1;
+#pragma unroll 1
+        for (int g0 = 0; g0 < G; g0 += 8) {
+            const int base_a = (L - G + g0) * PP + ta;
+            const int base_b = (G - 8 - g0) * PP + tb;
+            norm8(a);
+            norm8(b);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int ia = base_a + k * PP, ib = base_b + (7 - k) * PP;
+                alpha_step(a, x_at(sm, elem_at<IL>(c, sm, ia)), par[ia]);
+                beta_step(b, x_at(sm, elem_at<IL>(c, sm, ib)), par[ib]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            if (first_fixed) a[s] = na[s];
+            if (last_fixed) b[s] = nb[s];
+        }
+        if (G == L) {
+#pragma unroll
+            for (int s = 0; s < 8; s++) sb[s] = b[s];
+        }
+        norm8(a);
+#pragma unroll
+        for (int s = 0; s < 8; s++) a0[s] = a[s];
+        // ---- forward sweep over windows 0..NW-2, leaving a (normalised) checkpoint at the start of
+        //      windows 1..NW-2; the start of window NW-1 stays in registers
+#pragma unroll 1
+        for (int w = 0; w < NW - 1; w++) {
+            Elem el[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                el[k] = elem_of<IL>(c, offn[k], (8 * w + k) * PP + t);
+                if (IL) offn[k] = sm.tab[(8 * (w + 1) + k) * PP + t];
+            }
+            if (w > 0) {
+                norm8(a);
+#pragma unroll
+                for (int s = 1; s < 8; s++) sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t] = a[s];
+            }
+            const int base = 8 * w * PP + t;
+#pragma unroll
+            for (int k = 0; k < 8; k++) alpha_step(a, x_at(sm, el[k]), par[base + k * PP]);
+        }
+        if (NW > 1) norm8(a);
+    }
+    __syncthreads();  // every warm-up read of X precedes every in-place update below
+    if (active) {
+        // alpha at local step L-G, for the right-hand neighbour's next iteration: the start vector
+        // of window w_sa -- live in registers for the first and last window, a checkpoint otherwise
+        if (G > 0) {
+            if (w_sa == NW - 1) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) sa[s] = a[s];
+            } else if (w_sa == 0) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) sa[s] = a0[s];
+            }
+        } else {  // alpha at the sub-block end
+            w32 tmp[8];
+#pragma unroll
+            for (int s = 0; s < 8; s++) tmp[s] = a[s];
+            const int base = 8 * (NW - 1) * PP + t;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int idx = base + k * PP;
+                alpha_step(tmp, x_at(sm, elem_at<IL>(c, sm, idx)), par[idx]);
+            }
+#pragma unroll
+            for (int s = 0; s < 8; s++) sa[s] = tmp[s];
+        }
+        // ---- backward sweep, ONE window body for all windows (instruction-cache footprint): the
+        //      start vector of a window comes from `spec` for the last and the first window (the
+        //      forward sweep's registers, then the saved a0) and from the checkpoints otherwise.
+        //      Every start vector is normalised, so component 0 is always 0.
+        w32 spec[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) spec[s] = a[s];
+        w32 hold = 0;  // decision bits of an odd window waiting for its even partner
+#pragma unroll 1
+        for (int w = NW - 1; w >= 0; w--) {
+            const bool mid = (w > 0) && (w < NW - 1);
+            w32 aw0[8];
+            aw0[0] = 0;
+#pragma unroll
+            for (int s = 1; s < 8; s++) {
+                aw0[s] = spec[s];
+                if (mid) aw0[s] = sm.ckpt[((w - 1) * 7 + (s - 1)) * P + t];
+            }
+            unsigned off[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                off[k] = offn[k];
+                if (IL) offn[k] = sm.tab[(8 * max(w - 1, 0) + k) * PP + t];
+            }
+            const w32 acc = bwd_window<IL, WANT>(c, sm, par, 8 * w * PP + t, PP, off, aw0, b, stage, weak);
+            if (w == w_sb) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) sb[s] = b[s];
+            }
+            if (WANT) {
+                if (w & 1) hold = acc;
+                else {
+                    const w32 word = (acc >> 8) | hold;
+                    changed |= word ^ sm.dec[(w >> 1) * P + t];
+                    sm.dec[(w >> 1) * P + t] = word;
+                    hold = 0;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 8; s++) spec[s] = a0[s];
+        }
+        if (G > 0 && w_sa > 0 && w_sa < NW - 1) {
+#pragma unroll
+            for (int s = 1; s < 8; s++) sa[s] = sm.ckpt[((w_sa - 1) * 7 + (s - 1)) * P + t];
+        }
+        norm8(sa);
+        norm8(sb);
+    }
+    // ---- hand the boundary vectors to the neighbours (they use them in the next iteration):
+    //      warp shuffles inside a warp, one shared-memory word per state across warp edges
+    w32 up[8], dn[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        up[s] = __shfl_up_sync(0xffffffffu, sa[s], 1);
+        dn[s] = __shfl_down_sync(0xffffffffu, sb[s], 1);
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) sm.edge[s * nwarps + warp] = sa[s];
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) sm.edge[(8 + s) * nwarps + warp] = sb[s];
+    }
+    __syncthreads();  // also orders this pass's X updates before the next pass's reads
+    if (lane == 0 && warp > 0) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) up[s] = sm.edge[s * nwarps + warp - 1];
+    }
+    if (lane == 31 && warp + 1 < nwarps) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) dn[s] = sm.edge[(8 + s) * nwarps + warp + 1];
+    }
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        if (!first_fixed) na[s] = up[s];
+        if (!last_fixed) nb[s] = dn[s];
+    }
+    return changed;
+}
+
+// ---- de-multiplex one group of four trellis steps (12 packed words: sys,par1,par2 x 4) into shared memory
+__device__ __forceinline__ void put4(const Smem &sm, int q, int L, int PP, const w32 (&v)[12])
+{
+    const int n = 4 * q;  // L is a multiple of 8, so the four steps share their sub-block
+    const int tt = n / L, j = n - tt * L;
+    const int ad = j * PP + tt;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        sm.X[ad + m * PP] = v[3 * m];
+        const w32 sb = vadd(v[3 * m], 0x00800080u);  // value + 128 in each lane
+        sm.sysA[ad + m * PP] = (uint8_t)sb;
+        sm.sysB[ad + m * PP] = (uint8_t)(sb >> 16);
+        sm.par1[ad + m * PP] = v[3 * m + 1];
+        sm.par2[ad + m * PP] = v[3 * m + 2];
+    }
+}
+
+// Shared memory of one CTA: NP codeblock-pair regions (X, par1, par2, sysA, sysB, ckpt, dec), then the
+// QPP table (one copy for all pairs), the warp-edge exchange words and the per-pair stop flags.
+__device__ __forceinline__ Smem pair_smem(unsigned char *raw, const FastGeom &g, int P, int NW, int Wp, int NP, int p)
+{
+    Smem sm;
+    unsigned char *r = raw + (size_t)p * g.pair_bytes;
+    sm.X = reinterpret_cast<w32 *>(r);
+    sm.par1 = sm.X + Wp;
+    sm.par2 = sm.par1 + Wp;
+    sm.sysA = reinterpret_cast<uint8_t *>(sm.par2 + Wp);
+    sm.sysB = sm.sysA + Wp;
+    sm.ckpt = reinterpret_cast<w32 *>(sm.sysB + Wp);
+    sm.dec = sm.ckpt + (size_t)g.n_ckpt * 7 * P;
+    unsigned char *sh = raw + (size_t)NP * g.pair_bytes;
+    sm.tab = reinterpret_cast<uint16_t *>(sh);
+    sm.edge = reinterpret_cast<w32 *>(sm.tab + Wp);
+    return sm;
+}
+
+template <int LLR_T, int KP, int KNW, int KG>
+__global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) fast_s16_kernel(FastArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FastGeom &g = A.g;
+    const int P = KP ? KP : g.P, PP = KP ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW;
+    const int L = 8 * NW, K = P * L;
+    const int W = L * PP;            // words per array
+    const int Wp = (W + 7) & ~7;     // every region starts 16-byte aligned
+    const int NP = KP ? 1 : A.pairs_per_cta;  // codeblock pairs this CTA decodes side by side (small K)
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int n_pairs = (A.n_cb + 1) / 2;
+    // thread -> (pair slot q, sub-block t)
+    const int q = KP ? 0 : tid / P, t = KP ? tid : tid - q * P;
+    const int pair = blockIdx.x * NP + q;
+    const bool active = KP ? true : (q < NP && pair < n_pairs);
+    const Smem sm = pair_smem(smem_raw, g, P, NW, Wp, NP, active ? q : 0);
+    unsigned *flags = reinterpret_cast<unsigned *>(sm.edge + 16 * (nthr >> 5));
+    const int cbA = 2 * (active ? pair : 0);
+    const bool hasB = cbA + 1 < A.n_cb;
+    const int cbB = hasB ? cbA + 1 : cbA;
+    const size_t row = (size_t)3 * K + 12;
+    const float scale = (float)(1 << A.frac_bits);
+    const int clip = A.llr_clip;
+
+    // ---- load + quantise + de-multiplex (once per decode); element n = tt*L + j -> word j*PP + tt.
+    //      NG groups of loads (NG x 2 codeblocks x 48 bytes) are in flight per thread before the
+    //      first is consumed: the phase is pure load latency, so depth is what shortens it.
+    for (int p = 0; p < NP; p++) {
+        const int pr = blockIdx.x * NP + p;
+        if (pr >= n_pairs) break;
+        const Smem smp = pair_smem(smem_raw, g, P, NW, Wp, NP, p);
+        const int a_cb = 2 * pr, b_cb = (a_cb + 1 < A.n_cb) ? a_cb + 1 : a_cb;
+        constexpr int NG = (LLR_T == TDB200_LLR_F64) ? 2 : 4;
+        const w32 clipv = dup2(clip), nclipv = dup2(-clip);
+        const int nq = K / 4;
+        for (int q0 = tid; q0 < nq; q0 += NG * nthr) {
+            Raw12<LLR_T> ra[NG], rb[NG];
+#pragma unroll
+            for (int j = 0; j < NG; j++) {
+                const int qq = min(q0 + j * nthr, nq - 1);  // the clamp re-reads the last group instead of branching
+                load12<LLR_T>(A.llr, row, a_cb, qq, ra[j]);
+                load12<LLR_T>(A.llr, row, b_cb, qq, rb[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < NG; j++) {
+                const int qq = q0 + j * nthr;
+                if (qq < nq) {
+                    w32 v[12];
+                    pack12<LLR_T>(ra[j], rb[j], scale, clipv, nclipv, v);
+                    put4(smp, qq, L, PP, v);
+                }
+            }
+        }
+    }
+    {   // QPP table: 128-bit loads (the table and the shared-memory array are 16-byte aligned)
+        const int n16 = (W * 2) / 16;
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.tab2);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.tab);
+        for (int i = tid; i < n16; i += nthr) dst[i] = __ldg(src + i);
+        for (int i = n16 * 8 + tid; i < W; i += nthr) sm.tab[i] = __ldg(A.tab2 + i);
+    }
+    // ---- pull the rows of the codeblock pair that will run on this SM slot next into L2 (bulk
+    //      prefetch, a few KB per instruction; rows are 16-byte multiples)
+    if (KP && A.prefetch_stride > 0) {
+        const long long nxt = (long long)2 * (blockIdx.x + A.prefetch_stride);
+        if (nxt < A.n_cb) {
+            const size_t esz = LLR_T == TDB200_LLR_F64 ? 8 : (LLR_T == TDB200_LLR_F32 ? 4 : (LLR_T == TDB200_LLR_F16 ? 2 : 1));
+            const char *p = static_cast<const char *>(A.llr) + (size_t)nxt * row * esz;
+            const size_t nbytes = ((nxt + 1 < A.n_cb ? 2 : 1) * row * esz) & ~(size_t)15;
+            const size_t chunk = 4096;
+            for (size_t o = (size_t)tid * chunk; o < nbytes; o += (size_t)nthr * chunk) {
+                const unsigned sz = (unsigned)(nbytes - o < chunk ? nbytes - o : chunk);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + o), "r"(sz) : "memory");
+            }
+        }
+    }
+
+    PassCfg c;
+    c.q2 = A.q2;
+    c.lim1 = dup2(A.ext_lim + 1);
+    c.limmax = dup2(2 * A.ext_lim - 1);
+    c.unbias = dup2((A.q2 == 3 ? -(3 * A.ext_lim / 4) : -A.ext_lim) - 128);
+    c.neg1 = A.opaque[0]; c.four = A.opaque[1]; c.k64k = A.opaque[2]; c.k3q = A.opaque[3];
+    c.etT = dup2(A.et_threshold); c.et2T = dup2(2 * A.et_threshold); c.etmask = dup2(2 * A.et_threshold - 1);
+    const bool first_fixed = (t == 0), last_fixed = (t == P - 1);
+
+    // ---- boundary vectors.  [s][0..7]: s = SISO
+    w32 na[2][8], nb[2][8];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            na[s][j] = (first_fixed && j) ? dup2(kFxNeg) : 0u;  // known start state, :943-948
+            nb[s][j] = 0u;
+        }
+        if (last_fixed && active) {
+            // termination folded into beta(K): three tail steps back from state 0, :950-954
+            w32 bt[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) bt[j] = j ? dup2(kFxNeg) : 0u;
+            for (int m = 2; m >= 0; m--) {
+                const size_t o = (size_t)3 * K + 6 * s + 2 * m;
+                const w32 u = pack2(load1<LLR_T>(A.llr, cbA * row + o, scale, clip), load1<LLR_T>(A.llr, cbB * row + o, scale, clip));
+                const w32 v = pack2(load1<LLR_T>(A.llr, cbA * row + o + 1, scale, clip), load1<LLR_T>(A.llr, cbB * row + o + 1, scale, clip));
+                beta_step(bt, u, v);
+            }
+            norm8(bt);
+#pragma unroll
+            for (int j = 0; j < 8; j++) nb[s][j] = bt[j];
+        }
+    }
+    __syncthreads();
+
+    const bool want_soft = (A.llr2 != nullptr);
+    int used = A.n_iter, usedA = 0, usedB = 0;
+    for (int it = 0; it < A.n_iter; it++) {
+        const bool last = (it == A.n_iter - 1);
+        w32 weak = 0;
+        siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
+        if (A.early_term || last) {
+            // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
+            // (by then dead) parity-1 array
+            const w32 chg = siso_pass<true, true, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed,
+                                                               (want_soft && last) ? sm.par1 : nullptr, weak);
+            if (A.early_term) {
+                // stop: no decision of this iteration differs from the previous one and no
+                // a-posteriori value is weaker than the threshold -- per codeblock; a CTA leaves when
+                // all its codeblocks have stopped
+                int chA, chB;
+                if (KP) {
+                    chA = __syncthreads_or((int)((chg | weak) & 0xffffu));
+                    chB = __syncthreads_or((int)((chg | weak) >> 16));
+                } else {
+                    if (tid < NP) flags[tid] = 0u;
+                    __syncthreads();
+                    if (active && (chg | weak)) atomicOr(&flags[q], chg | weak);
+                    __syncthreads();
+                    const unsigned f = active ? flags[q] : 0u;
+                    chA = (int)(f & 0xffffu); chB = (int)(f >> 16);
+                }
+                if (it >= 1) {
+                    if (!chA && !usedA) usedA = it + 1;
+                    if (!chB && !usedB) usedB = it + 1;
+                }
+                const bool done = (usedA && usedB) || !active;
+                if (KP ? done : (__syncthreads_and((int)done) != 0)) { used = it + 1; break; }
+            }
+        } else {
+            siso_pass<true, false, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed, nullptr, weak);
+        }
+    }
+    if (!usedA) usedA = used;
+    if (!usedB) usedB = used;
+
+    // ---- hard decisions, natural order: decision() :862-879 is the sign bit kept in sm.dec,
+    //      random_deinterlvr_int :1264 is the scatter of those bits to byte n = pi(i) of a staging
+    //      array (the dead parity-2 region), which then leaves with coalesced 32-bit stores
+    if (A.bits) {
+        if (active) {
+            uint8_t *byA = reinterpret_cast<uint8_t *>(sm.par2), *byB = byA + K;
+            for (int w2 = 0; w2 < (NW + 1) / 2; w2++) {
+                const w32 word = sm.dec[w2 * P + t];
+#pragma unroll
+                for (int kk = 0; kk < 16; kk++) {
+                    const int j = 16 * w2 + (kk & 8) + 7 - (kk & 7);  // step k of a window sits in bit 7-k of its byte
+                    if (j < L) {
+                        const int e = sm.tab[j * PP + t];
+                        const int jj = e / PP, tt = e - jj * PP;
+                        const int n = tt * L + jj;
+                        byA[n] = (uint8_t)(((word >> kk) & 1u) ^ 1u);
+                        byB[n] = (uint8_t)(((word >> (16 + kk)) & 1u) ^ 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int p = 0; p < NP; p++) {
+            const int pr = blockIdx.x * NP + p;
+            if (pr >= n_pairs) break;
+            const Smem smp = pair_smem(smem_raw, g, P, NW, Wp, NP, p);
+            const uint32_t *wa = reinterpret_cast<const uint32_t *>(smp.par2), *wb = wa + K / 4;
+            const bool pB = 2 * pr + 1 < A.n_cb;
+            uint32_t *oa = reinterpret_cast<uint32_t *>(A.bits + (size_t)(2 * pr) * K), *ob = oa + K / 4;
+            for (int i = tid; i < K / 4; i += nthr) {
+                oa[i] = wa[i];
+                if (pB) ob[i] = wb[i];
+            }
+        }
+    }
+    if (A.iters_used && active && t == 0) {
+        A.iters_used[cbA] = usedA;
+        if (hasB) A.iters_used[cbB] = usedB;
+    }
+    if (want_soft || A.ext2) {
+        const float inv = 1.0f / scale;
+        const int T = K + kTail;
+        __syncthreads();
+        for (int p = 0; p < NP; p++) {
+            const int pr = blockIdx.x * NP + p;
+            if (pr >= n_pairs) break;
+            const Smem smp = pair_smem(smem_raw, g, P, NW, Wp, NP, p);
+            const int a_cb = 2 * pr;
+            const bool pB = a_cb + 1 < A.n_cb;
+            for (int i = tid; i < T; i += nthr) {
+                float la = 0.f, lb = 0.f, ea = 0.f, eb = 0.f;
+                if (i < K) {
+                    const int tt = i / L, j = i - tt * L;
+                    const int e = smp.tab[j * PP + tt];
+                    const w32 lam = smp.par1[e];
+                    const w32 ysb = (w32)smp.sysA[e] | ((w32)smp.sysB[e] << 16);
+                    const w32 ex = vadd(vadd(smp.X[e], vneg(ysb)), 0x00800080u);
+                    la = (float)(int16_t)(lam & 0xffff) * inv; lb = (float)(int16_t)(lam >> 16) * inv;
+                    ea = (float)(int16_t)(ex & 0xffff) * inv; eb = (float)(int16_t)(ex >> 16) * inv;
+                }
+                if (A.llr2) { A.llr2[(size_t)a_cb * T + i] = la; if (pB) A.llr2[(size_t)(a_cb + 1) * T + i] = lb; }
+                if (A.ext2) { A.ext2[(size_t)a_cb * T + i] = ea; if (pB) A.ext2[(size_t)(a_cb + 1) * T + i] = eb; }
+            }
+        }
+    }
+}
+
+typedef void (*kernel_fn)(FastArgs);
+
+template <int LLR_T, int KP>
+kernel_fn pick_nw(int NW)
+{
+    if (NW == 6) return fast_s16_kernel<LLR_T, KP, 6, 16>;
+    if (NW == 5) return fast_s16_kernel<LLR_T, KP, 5, 16>;
+    return fast_s16_kernel<LLR_T, KP, 4, 16>;
+}
+
+template <int LLR_T>
+kernel_fn pick_kernel_t(const FastGeom &g)
+{
+    if (fast_spec_pn(g)) return g.P == 128 ? pick_nw<LLR_T, 128>(g.NW) : (g.P == 64 ? pick_nw<LLR_T, 64>(g.NW) : pick_nw<LLR_T, 32>(g.NW));
+    if (fast_spec128g8(g)) return fast_s16_kernel<LLR_T, 128, 6, 8>;
+    if (fast_spec192(g)) return fast_s16_kernel<LLR_T, 192, 4, 16>;
+    return fast_s16_kernel<LLR_T, 0, 0, 0>;
+}
+
+}  // namespace
+}  // namespace tdb200

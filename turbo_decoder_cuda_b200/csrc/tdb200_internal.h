@@ -99,7 +99,7 @@ struct FastArgs {
     int n_iter;
     int frac_bits, llr_clip, ext_lim /* Ce+1, multiple of 4 */, q2;
     int early_term, et_threshold;
-    uint32_t opaque[4];  // {0xffffffff, 4, 65536, 0xC0000000}: see PassCfg in tdb200_fast.cu
+    uint32_t opaque[4];  // {0xffffffff, 4, 65536, 0xC0000000}: see PassCfg in tdb200_fast_kernel.cuh
     const uint16_t *tab2;  // [L*PP] device: smem word of element pi(tL+j), stored at index j*PP+t
     int prefetch_stride;   // CTAs resident on the device at once (0 = no L2 prefetch of the next pair)
     int pairs_per_cta;     // filled in by launch_fast_s16
@@ -129,6 +129,13 @@ struct F32Args {
 cudaError_t f32_configure(const FastGeom &g);
 cudaError_t launch_f32(const F32Args &a, cudaStream_t st, int *n_launches);
 int f32_smem_bytes(const FastGeom &g);
+
+// Compile-time geometry exists for P sub-blocks of 8*NW steps with guard 16, P in {32, 64, 128}, NW in {4, 5, 6}
+// (K = 1024 ... 6144 in nine sizes -- the BASELINE size is P=128, NW=6), plus two alternative plans
+// for K = 6144: guard 8 (-0.04 dB, +4 %), and 192 sub-blocks of 32 steps.  Everything else runs the generic kernel.
+inline bool fast_spec_pn(const FastGeom &g) { return (g.P == 32 || g.P == 64 || g.P == 128) && g.NW >= 4 && g.NW <= 6 && g.G == 16 && g.PP == (g.P | 1); }
+inline bool fast_spec128g8(const FastGeom &g) { return g.P == 128 && g.NW == 6 && g.G == 8 && g.PP == 129; }
+inline bool fast_spec192(const FastGeom &g) { return g.P == 192 && g.NW == 4 && g.G == 16 && g.PP == 193; }
 
 cudaError_t fast_s16_configure(FastGeom &g, int sm_count);  // opt in to the dynamic shared memory size
 cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches);
