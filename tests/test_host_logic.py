@@ -192,3 +192,22 @@ def test_reference_main_links_against_compat(lib, tmp_path):
     subprocess.check_call(["g++", "-o", exe] + objs + ["-L", libdir, "-ltdb200_compat", "-ltdb200", "-Wl,-rpath," + libdir])
     syms = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
     assert "_Z13TurboDecodingPdPii" in syms, "main.cpp's TurboDecoding call must resolve to the compat library"
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference runs without a GPU (it times the reference's CPU decoder) and prints one
+    JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-sample", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "Gbit/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["ber"] == 0.0   # two codeblocks at 1.0 dB decode cleanly
