@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TDB200_VERSION 3
+#define TDB200_VERSION 4
 
 typedef enum tdb200_status {
     TDB200_OK = 0,
@@ -156,6 +156,45 @@ int tdb200_encode_batch(tdb200_decoder *dec, const uint8_t *bits, uint8_t *coded
  * not reproducible, so the agreement is statistical.  llr_type: TDB200_LLR_F32 or TDB200_LLR_F64. */
 int tdb200_channel_batch(tdb200_decoder *dec, const uint8_t *coded, void *llr, int llr_type, int mem, int n_cb,
                          double sigma, uint64_t seed, void *stream);
+
+/* ---- higher-order mapping: the reference's module()/demodule() pair (ITTC/modanddem.cpp:175,674) ----
+ * `modulation` is the reference's modu_index = bits per symbol (MODULATION, ITTC/main.cpp:29):
+ * 1 BPSK, 2 QPSK, 3 8PSK, 4 16QAM, 6 64QAM, with the reference's own constellation tables
+ * (modanddem.cpp:7-71) and bit order.  Symbols are planar like the reference's symbol_i / symbol_q:
+ * two arrays [n_cb][(3K+12)/modulation] of sym_type (TDB200_LLR_F32, _F64 or _F16). */
+typedef enum tdb200_modulation {
+    TDB200_MOD_BPSK = 1, TDB200_MOD_QPSK = 2, TDB200_MOD_8PSK = 3, TDB200_MOD_16QAM = 4, TDB200_MOD_64QAM = 6
+} tdb200_modulation;
+
+/* Replaces module(int *a, double *outi, double *outq, int N, int modu_index) for a batch:
+ * coded [n_cb][3K+12] bits (one byte per bit) -> constellation points.  Exact (table look-up). */
+int tdb200_modulate_batch(tdb200_decoder *dec, const uint8_t *coded, void *sym_i, void *sym_q, int sym_type,
+                          int mem, int n_cb, int modulation, void *stream);
+
+/* Replaces AWGN(double *in, double *out, double sigma, int len) (ITTC/log_map.cpp:1388): y = x + sigma*n
+ * over n values of `type`; n is standard normal from Philox4x32-10, a pure function of (seed, index). */
+int tdb200_awgn_batch(tdb200_decoder *dec, const void *x, void *y, int type, int mem, size_t n,
+                      double sigma, uint64_t seed, void *stream);
+
+/* Replaces demodule(double *symbol_i, double *symbol_q, int symbol_len, double *out, double Kf,
+ * int modu_index) for a batch: received symbols -> llr [n_cb][3K+12], max-log,
+ * LLR_b = -Kf * (min_{points with bit b = 1} d - min_{points with bit b = 0} d), Kf = 1/(2 sigma^2)
+ * (ITTC/main.cpp:202).  llr_type TDB200_LLR_F64: fp64 in the reference's order of operations,
+ * bit-identical to demodule().  TDB200_LLR_F32 / _F16: the same metric in fp32 (per axis for the
+ * product constellations).  TDB200_LLR_S8: the fp32 metric quantised to the throughput decoder's
+ * fixed-point channel values, clamp(rint(LLR * 2^frac_bits), +-127) -- what tdb200_decode_batch
+ * computes itself from float LLRs, so decoding these bytes equals decoding the float LLRs. */
+int tdb200_demap_batch(tdb200_decoder *dec, const void *sym_i, const void *sym_q, int sym_type,
+                       void *llr, int llr_type, int mem, int n_cb, int modulation, double kf, void *stream);
+
+/* demodule() + TurboDecoding() in one call (ITTC/main.cpp:202,221): received symbols in, decisions
+ * out.  The demapped values stay on the device in the decoder's own input format (fp64 for
+ * TDB200_ALGO_LOGMAP_F64, 8-bit fixed point for TDB200_ALGO_MAXLOG_S16, float for the fp32 modes),
+ * so a host caller moves 2*sizeof(sym)/modulation bytes per LLR over PCIe instead of sizeof(llr).
+ * Results equal tdb200_demap_batch followed by tdb200_decode_batch.  `out` as for tdb200_decode_batch. */
+int tdb200_decode_symbols_batch(tdb200_decoder *dec, const void *sym_i, const void *sym_q, int sym_type,
+                                int mem, int n_cb, int modulation, double kf,
+                                const tdb200_outputs *out, void *stream);
 
 /* Introspection (what the plan resolved to). */
 typedef struct tdb200_plan_info {

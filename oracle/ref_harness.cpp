@@ -107,6 +107,10 @@ void ref_channel(int *coded, double sigma, unsigned seed, double *llr)
     demodule(ri.data(), rq.data(), n, llr, 1 / (2 * sigma * sigma), 1);
 }
 
+/* The reference's mapper and soft demapper, ITTC/modanddem.cpp:175,674 (M = modu_index). */
+void ref_module(int *bits, double *si, double *sq, int n_bits, int M) { module(bits, si, sq, n_bits, M); }
+void ref_demodule(double *si, double *sq, int n_sym, double *out, double kf, int M) { demodule(si, sq, n_sym, out, kf, M); }
+
 /* The reference's own TurboDecoding(): N_ITERATION = 15 iterations, mutates llr (x0.5). */
 void ref_turbo_decoding(double *llr, int *flow_decoded)
 {

@@ -120,6 +120,16 @@ typedef struct tdo_f32_params {
 int tdo_f32_decode(const float *llr_in, const int *pi, const tdo_f32_params *p,
                    int *bits_out, float *llr_out, float *le_out);
 
+/* ------------------------------------------------------------------------
+ * Mapper / soft demapper (turbo_oracle_mod.c; ITTC/modanddem.cpp).  M = bits per symbol =
+ * the reference's modu_index: 1 BPSK, 2 QPSK, 3 8PSK, 4 16QAM, 6 64QAM. */
+int tdo_mod_point(int M, int j, double *pi, double *pq);
+int tdo_modulate(const int *bits, int n_bits, int M, double *si, double *sq);                 /* module(), :175 */
+int tdo_demap_f64(const double *si, const double *sq, int n_sym, int M, double kf, double *out); /* demodule(), :674 */
+/* fp32 model of the device demapper and of the 8-bit hand-over to the s16 decoder */
+int tdo_demap_f32(const float *si, const float *sq, int n_sym, int M, float kf, float *out);
+void tdo_quant_s8(const float *llr, int n, int frac_bits, int clip, signed char *out);
+
 #ifdef __cplusplus
 }
 #endif

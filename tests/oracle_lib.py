@@ -28,7 +28,7 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build_oracle(force=False):
     """Compile oracle/'s C restatement (and oracle/_ref when /root/reference is present)."""
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("turbo_oracle.c", "turbo_oracle_fx.c", "turbo_oracle.h")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in sorted(os.listdir(ORACLE_DIR)) if f.endswith((".c", ".h"))]
     stale = force or not os.path.exists(ORACLE_SO) or any(
         os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in srcs)
     if stale:
@@ -79,6 +79,38 @@ class Oracle:
         L.tdo_fx_decode.restype = C.c_int
         L.tdo_f32_decode.argtypes = [_fp, _ip, C.POINTER(F32Params), _ip, C.c_void_p, C.c_void_p]
         L.tdo_f32_decode.restype = C.c_int
+        L.tdo_modulate.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp]
+        L.tdo_demap_f64.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_double, _dp]
+        L.tdo_demap_f32.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_float, _fp]
+        L.tdo_quant_s8.argtypes = [_fp, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(dtype=np.int8, flags="C_CONTIGUOUS")]
+
+    # ---- mapper / soft demapper (turbo_oracle_mod.c)
+    def modulate(self, bits, M):
+        bits = np.ascontiguousarray(bits, np.int32).ravel()
+        si, sq = np.zeros(bits.size // M), np.zeros(bits.size // M)
+        if self.lib.tdo_modulate(bits, bits.size, M, si, sq):
+            raise ValueError("modulate: M=%d, %d bits" % (M, bits.size))
+        return si, sq
+
+    def demap_f64(self, si, sq, M, kf):
+        si, sq = np.ascontiguousarray(si, np.float64).ravel(), np.ascontiguousarray(sq, np.float64).ravel()
+        out = np.zeros(si.size * M)
+        if self.lib.tdo_demap_f64(si, sq, si.size, M, kf, out):
+            raise ValueError("demap: M=%d" % M)
+        return out
+
+    def demap_f32(self, si, sq, M, kf):
+        si, sq = np.ascontiguousarray(si, np.float32).ravel(), np.ascontiguousarray(sq, np.float32).ravel()
+        out = np.zeros(si.size * M, np.float32)
+        if self.lib.tdo_demap_f32(si, sq, si.size, M, kf, out):
+            raise ValueError("demap: M=%d" % M)
+        return out
+
+    def quant_s8(self, llr, frac_bits=3, clip=127):
+        llr = np.ascontiguousarray(llr, np.float32).ravel()
+        out = np.zeros(llr.size, np.int8)
+        self.lib.tdo_quant_s8(llr, llr.size, frac_bits, clip, out)
+        return out
 
     # ---- constants
     def trellis(self):
@@ -201,6 +233,8 @@ class RefLib:
         L.ref_decode_iters.argtypes = [_dp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_decode_batch.argtypes = [_dp, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.ref_decode_batch.restype = C.c_double
+        L.ref_module.argtypes = [_ip, _dp, _dp, C.c_int, C.c_int]
+        L.ref_demodule.argtypes = [_dp, _dp, C.c_int, _dp, C.c_double, C.c_int]
         L.ref_init(K, f1, f2)
 
     def qpp(self):
@@ -225,6 +259,20 @@ class RefLib:
         llr = np.zeros(3 * self.K + 12, np.float64)
         self.lib.ref_channel(np.ascontiguousarray(coded, np.int32), sigma, seed, llr)
         return llr
+
+    def module(self, bits, M):
+        """The reference's module(): bits -> (I, Q) constellation points."""
+        bits = np.ascontiguousarray(bits, np.int32).ravel()
+        si, sq = np.zeros(bits.size // M), np.zeros(bits.size // M)
+        self.lib.ref_module(bits, si, sq, bits.size, M)
+        return si, sq
+
+    def demodule(self, si, sq, M, kf):
+        """The reference's demodule(): max-log soft demapper."""
+        si, sq = np.array(si, np.float64).ravel(), np.array(sq, np.float64).ravel()
+        out = np.zeros(si.size * M)
+        self.lib.ref_demodule(si, sq, si.size, out, kf, M)
+        return out
 
     def turbo_decoding(self, llr):
         """The reference's TurboDecoding(): 15 iterations; returns bits[15,K]."""

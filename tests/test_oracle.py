@@ -136,3 +136,45 @@ def test_batch_threads_agree(oracle):
     assert np.array_equal(b1, b4)
     for c in range(6):
         assert np.array_equal(oracle.decode(llr[c], pi, 4)[-1], b1[c])
+
+
+# ---- mapper / soft demapper: oracle/turbo_oracle_mod.c against the reference's
+#      module()/demodule() -- golden vectors always, the live reference build where it exists
+MODS = (1, 2, 3, 4, 6)
+
+
+@pytest.mark.parametrize("M", MODS)
+def test_modem_matches_reference_golden(oracle, M):
+    g = np.load(os.path.join(GOLD, "modem_golden.npz"))
+    si, sq = oracle.modulate(g["bits_%d" % M], M)
+    assert np.array_equal(si, g["si_%d" % M]) and np.array_equal(sq, g["sq_%d" % M])
+    llr = oracle.demap_f64(g["ri_%d" % M], g["rq_%d" % M], M, float(g["kf_%d" % M]))
+    assert np.array_equal(llr, g["llr_%d" % M]), "demodule() restatement must be bit-identical"
+    # the fp32 model of the device demapper: same metric, float rounding only
+    l32 = oracle.demap_f32(g["ri_%d" % M], g["rq_%d" % M], M, float(g["kf_%d" % M]))
+    assert np.abs(l32 - llr).max() <= 2e-5 * max(1.0, np.abs(llr).max())
+    # and its 8-bit hand-over differs from quantising the reference's doubles by at most one step
+    q = oracle.quant_s8(l32).astype(int)
+    qref = np.clip(np.rint(llr * 8), -127, 127).astype(int)
+    assert np.abs(q - qref).max() <= 1 and np.mean(q != qref) < 0.01
+    if M == 6:
+        si, sq = oracle.modulate(g["all_bits_6"], 6)
+        assert np.array_equal(si, g["all_si_6"]) and np.array_equal(sq, g["all_sq_6"])
+
+
+@pytest.mark.skipif(not RefLib.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("M", MODS)
+def test_modem_vs_live_reference(oracle, M):
+    ref = RefLib(40, 3, 10)
+    rng = np.random.default_rng(100 + M)
+    bits = rng.integers(0, 2, 12 * 500).astype(np.int32)
+    si, sq = oracle.modulate(bits, M)
+    ri, rq = ref.module(bits, M)
+    assert np.array_equal(si, ri) and np.array_equal(sq, rq)
+    for sigma in (0.05, 0.3, 1.5):   # also far outside the constellation
+        xi = si + sigma * rng.standard_normal(si.size)
+        xq = sq + sigma * rng.standard_normal(si.size)
+        kf = 1 / (2 * sigma ** 2)
+        assert np.array_equal(oracle.demap_f64(xi, xq, M, kf), ref.demodule(xi, xq, M, kf))
+    # noiseless: the hard decision of every LLR is the transmitted bit
+    assert np.array_equal(oracle.demap_f64(si, sq, M, 1.0) > 0, bits == 1)

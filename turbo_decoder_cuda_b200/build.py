@@ -35,6 +35,7 @@ KERNEL_TUS = [
     ("tdb200_fast_inst_f16.cu", ["-Xptxas", "-v"]),
     ("tdb200_f32.cu", ["-fmad=false", "-Xptxas", "-v"]),
     ("tdb200_encode.cu", []),
+    ("tdb200_modem.cu", ["-fmad=false"]),
 ]
 
 

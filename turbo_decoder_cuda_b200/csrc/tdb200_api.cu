@@ -119,6 +119,8 @@ struct tdb200_decoder {
     struct Slot {
         void *d_in = nullptr;
         size_t d_in_bytes = 0;
+        void *d_dem = nullptr;  // demapped channel values of this chunk (tdb200_decode_symbols_batch)
+        size_t d_dem_bytes = 0;
         uint8_t *d_bits = nullptr;
         int32_t *d_bits_iters = nullptr;
         int32_t *d_iters_used = nullptr;
@@ -130,6 +132,8 @@ struct tdb200_decoder {
     cudaEvent_t ev_start = nullptr;
     void *siso_in = nullptr, *siso_out = nullptr;  // staging of tdb200_siso_batch (host callers)
     size_t siso_in_bytes = 0;
+    void *dem = nullptr;  // demapped channel values, device callers of tdb200_decode_symbols_batch
+    size_t dem_bytes = 0;
     int launches_last = 0;
 };
 
@@ -197,9 +201,9 @@ void tdb200_destroy(tdb200_decoder *d)
     if (!d) return;
     cudaSetDevice(d->cfg.device);
     cudaFree(d->d_pi); cudaFree(d->d_pi_inv); cudaFree(d->ws64_block); cudaFree(d->d_tab2);
-    cudaFree(d->siso_in); cudaFree(d->siso_out);
+    cudaFree(d->siso_in); cudaFree(d->siso_out); cudaFree(d->dem);
     for (auto &sl : d->slot) {
-        cudaFree(sl.d_in); cudaFree(sl.d_bits); cudaFree(sl.d_bits_iters); cudaFree(sl.d_iters_used);
+        cudaFree(sl.d_in); cudaFree(sl.d_dem); cudaFree(sl.d_bits); cudaFree(sl.d_bits_iters); cudaFree(sl.d_iters_used);
         cudaFree(sl.d_llr1); cudaFree(sl.d_llr2); cudaFree(sl.d_ext2);
         if (sl.in_ready) cudaEventDestroy(sl.in_ready);
         if (sl.k_done) cudaEventDestroy(sl.k_done);
@@ -437,12 +441,38 @@ static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int 
     return TDB200_OK;
 }
 
-int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int mem, int n_cb,
-                        const tdb200_outputs *out, void *stream)
+// Where the channel values of a decode call come from: LLRs as they are, or received symbols that
+// are demapped on the device into the decoder's own input format first.
+struct Source {
+    const void *llr = nullptr;
+    int llr_type = 0;
+    const void *sym_i = nullptr, *sym_q = nullptr;
+    int sym_type = 0, modulation = 0;
+    double kf = 0.0;
+    bool symbols() const { return sym_i != nullptr; }
+};
+
+// the channel-value format the decoder consumes without conversion loss
+static int native_llr_type(const tdb200_config &c)
 {
-    if (!d || !llr || !out) return fail(TDB200_ERR_INVALID_ARG, "dec/llr/out is NULL");
+    return c.algo == TDB200_ALGO_LOGMAP_F64 ? TDB200_LLR_F64 : (c.algo == TDB200_ALGO_MAXLOG_S16 ? TDB200_LLR_S8 : TDB200_LLR_F32);
+}
+
+static int launch_demap_chunk(tdb200_decoder *d, const Source &src, const void *si, const void *sq, void *llr, int n, cudaStream_t st)
+{
+    DemapArgs a{};
+    a.sym_i = si; a.sym_q = sq; a.sym_type = src.sym_type;
+    a.llr = llr; a.llr_type = native_llr_type(d->cfg);
+    a.n_llr = (size_t)n * d->NL; a.modulation = src.modulation; a.kf = src.kf;
+    a.frac_bits = d->cfg.frac_bits; a.clip = std::min((1 << (d->cfg.frac_bits + 4)) - 1, 127);
+    TDB_CUDA(launch_demap(a, st));
+    d->launches_last += 1;
+    return TDB200_OK;
+}
+
+static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, const tdb200_outputs *out, void *stream)
+{
     if (n_cb < 0) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d", n_cb);
-    if (llr_type < TDB200_LLR_F64 || llr_type > TDB200_LLR_F16) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d", llr_type);
     if (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE) return fail(TDB200_ERR_INVALID_ARG, "mem=%d", mem);
     d->launches_last = 0;
     if (n_cb == 0) return TDB200_OK;
@@ -450,7 +480,12 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDB_CUDA(cudaSetDevice(c.device));
     const int K = c.K, T = d->T, NL = d->NL;
+    const bool sym = src.symbols();
+    const int llr_type = sym ? native_llr_type(c) : src.llr_type;
+    const void *llr = src.llr;
     const size_t esz = llr_elem_size(llr_type);
+    const size_t ssz = sym ? llr_elem_size(src.sym_type) : 0;
+    const size_t NS = sym ? (size_t)NL / src.modulation : 0;  // symbols per codeblock
 
     const bool f64 = (c.algo == TDB200_ALGO_LOGMAP_F64);
     const size_t fsz = f64 ? sizeof(double) : sizeof(float);  // native float type of the LLR outputs
@@ -461,9 +496,18 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
 
     if (mem == TDB200_MEM_DEVICE) {
         // ---- device buffers: chunks of max_batch (the fp64 workspace is sized for that), all on `stream`
+        if (sym) {
+            int s = ensure(d->dem, d->dem_bytes, (size_t)std::min(c.max_batch, n_cb) * NL * esz);
+            if (s) return s;
+        }
         for (int c0 = 0; c0 < n_cb; c0 += c.max_batch) {
             const int n = std::min(c.max_batch, n_cb - c0);
-            int s = launch_chunk(d, static_cast<const char *>(llr) + (size_t)c0 * NL * esz, llr_type, n,
+            if (sym) {
+                int s = launch_demap_chunk(d, src, static_cast<const char *>(src.sym_i) + (size_t)c0 * NS * ssz,
+                                           static_cast<const char *>(src.sym_q) + (size_t)c0 * NS * ssz, d->dem, n, st);
+                if (s) return s;
+            }
+            int s = launch_chunk(d, sym ? d->dem : static_cast<const char *>(llr) + (size_t)c0 * NL * esz, llr_type, n,
                                  out->bits ? out->bits + (size_t)c0 * K : nullptr,
                                  out->bits_iters ? out->bits_iters + (size_t)c0 * c.n_iter * K : nullptr,
                                  out->iters_used ? out->iters_used + c0 : nullptr,
@@ -493,7 +537,8 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
     }
     const int cap = d->slot_cap;
     for (auto &sl : d->slot) {
-        if ((s = ensure(sl.d_in, sl.d_in_bytes, (size_t)cap * NL * esz))) return s;
+        if ((s = ensure(sl.d_in, sl.d_in_bytes, sym ? 2 * (size_t)cap * NS * ssz : (size_t)cap * NL * esz))) return s;
+        if (sym && (s = ensure(sl.d_dem, sl.d_dem_bytes, (size_t)cap * NL * esz))) return s;
         if (out->bits && (s = ensure_once(sl.d_bits, (size_t)cap * K))) return s;
         if (out->bits_iters && (s = ensure_once(sl.d_bits_iters, sizeof(int32_t) * (size_t)cap * c.n_iter * K))) return s;
         if (out->iters_used && !f64 && (s = ensure_once(sl.d_iters_used, sizeof(int32_t) * (size_t)cap))) return s;
@@ -512,12 +557,21 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
         tdb200_decoder::Slot &sl = d->slot[i % tdb200_decoder::kSlots];
         const bool reused = i >= tdb200_decoder::kSlots;
         if (reused) TDB_CUDA(cudaStreamWaitEvent(d->s_h2d, sl.k_done, 0));  // the kernel that read this slot's input
-        TDB_CUDA(cudaMemcpyAsync(sl.d_in, static_cast<const char *>(llr) + (size_t)c0 * NL * esz, (size_t)n * NL * esz,
-                                 cudaMemcpyHostToDevice, d->s_h2d));
+        char *d_q = static_cast<char *>(sl.d_in) + (size_t)cap * NS * ssz;  // the slot's Q plane
+        if (sym) {
+            TDB_CUDA(cudaMemcpyAsync(sl.d_in, static_cast<const char *>(src.sym_i) + (size_t)c0 * NS * ssz, (size_t)n * NS * ssz,
+                                     cudaMemcpyHostToDevice, d->s_h2d));
+            TDB_CUDA(cudaMemcpyAsync(d_q, static_cast<const char *>(src.sym_q) + (size_t)c0 * NS * ssz, (size_t)n * NS * ssz,
+                                     cudaMemcpyHostToDevice, d->s_h2d));
+        } else {
+            TDB_CUDA(cudaMemcpyAsync(sl.d_in, static_cast<const char *>(llr) + (size_t)c0 * NL * esz, (size_t)n * NL * esz,
+                                     cudaMemcpyHostToDevice, d->s_h2d));
+        }
         TDB_CUDA(cudaEventRecord(sl.in_ready, d->s_h2d));
         TDB_CUDA(cudaStreamWaitEvent(d->s_k, sl.in_ready, 0));
         if (reused) TDB_CUDA(cudaStreamWaitEvent(d->s_k, sl.out_done, 0));  // the copy-out of this slot's previous results
-        s = launch_chunk(d, sl.d_in, llr_type, n, out->bits ? sl.d_bits : nullptr, out->bits_iters ? sl.d_bits_iters : nullptr,
+        if (sym && (s = launch_demap_chunk(d, src, sl.d_in, d_q, sl.d_dem, n, d->s_k))) return s;
+        s = launch_chunk(d, sym ? sl.d_dem : sl.d_in, llr_type, n, out->bits ? sl.d_bits : nullptr, out->bits_iters ? sl.d_bits_iters : nullptr,
                          (out->iters_used && !f64) ? sl.d_iters_used : nullptr, out->llr_siso1 ? sl.d_llr1 : nullptr,
                          out->llr_siso2 ? sl.d_llr2 : nullptr, out->ext_siso2 ? sl.d_ext2 : nullptr, d->s_k);
         if (s) return s;
@@ -537,6 +591,136 @@ int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int me
     TDB_CUDA(cudaStreamSynchronize(d->s_d2h));
     if (f64 && out->iters_used)
         for (int k = 0; k < n_cb; k++) out->iters_used[k] = c.n_iter;  // the fp64 mode always runs every iteration
+    return TDB200_OK;
+}
+
+int tdb200_decode_batch(tdb200_decoder *d, const void *llr, int llr_type, int mem, int n_cb,
+                        const tdb200_outputs *out, void *stream)
+{
+    if (!d || !llr || !out) return fail(TDB200_ERR_INVALID_ARG, "dec/llr/out is NULL");
+    if (llr_type < TDB200_LLR_F64 || llr_type > TDB200_LLR_F16) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d", llr_type);
+    Source src;
+    src.llr = llr; src.llr_type = llr_type;
+    return decode_core(d, src, mem, n_cb, out, stream);
+}
+
+static int check_sym(const char *fn, const tdb200_decoder *d, int sym_type, int modulation)
+{
+    if (sym_type != TDB200_LLR_F32 && sym_type != TDB200_LLR_F64 && sym_type != TDB200_LLR_F16)
+        return fail(TDB200_ERR_INVALID_ARG, "%s: sym_type=%d (F32, F64 or F16)", fn, sym_type);
+    if (!modulation_ok(modulation)) return fail(TDB200_ERR_INVALID_ARG, "%s: modulation=%d (1, 2, 3, 4 or 6 bits per symbol)", fn, modulation);
+    if (d->NL % 12) return fail(TDB200_ERR_UNSUPPORTED, "%s: 3K+12 = %d is not a multiple of 12 (K must be a multiple of 4)", fn, d->NL);
+    return TDB200_OK;
+}
+
+int tdb200_decode_symbols_batch(tdb200_decoder *d, const void *sym_i, const void *sym_q, int sym_type, int mem, int n_cb,
+                                int modulation, double kf, const tdb200_outputs *out, void *stream)
+{
+    if (!d || !sym_i || !sym_q || !out) return fail(TDB200_ERR_INVALID_ARG, "dec/sym/out is NULL");
+    int s = check_sym("tdb200_decode_symbols_batch", d, sym_type, modulation);
+    if (s) return s;
+    if (!(kf > 0.0)) return fail(TDB200_ERR_INVALID_ARG, "kf must be positive");
+    Source src;
+    src.sym_i = sym_i; src.sym_q = sym_q; src.sym_type = sym_type; src.modulation = modulation; src.kf = kf;
+    return decode_core(d, src, mem, n_cb, out, stream);
+}
+
+// A flat element-wise stage with host buffers: stage in, run, stage out (test-harness convenience;
+// device callers are asynchronous on `stream`).
+struct HostStage {
+    std::vector<void *> dev;
+    ~HostStage() { for (void *p : dev) cudaFree(p); }
+    void *alloc(size_t bytes)
+    {
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        dev.push_back(p);
+        return p;
+    }
+};
+
+int tdb200_modulate_batch(tdb200_decoder *d, const uint8_t *coded, void *sym_i, void *sym_q, int sym_type, int mem, int n_cb,
+                          int modulation, void *stream)
+{
+    if (!d || !coded || !sym_i || !sym_q) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (n_cb < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d mem=%d", n_cb, mem);
+    int s = check_sym("tdb200_modulate_batch", d, sym_type, modulation);
+    if (s) return s;
+    if (n_cb == 0) return TDB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    const size_t nb = (size_t)n_cb * d->NL, ns = nb / modulation, ssz = llr_elem_size(sym_type);
+    if (mem == TDB200_MEM_DEVICE) {
+        TDB_CUDA(launch_modulate(coded, sym_i, sym_q, sym_type, nb, modulation, st));
+        return TDB200_OK;
+    }
+    HostStage hs;
+    uint8_t *dc = static_cast<uint8_t *>(hs.alloc(nb));
+    void *di = hs.alloc(ns * ssz), *dq = hs.alloc(ns * ssz);
+    if (!dc || !di || !dq) return fail(TDB200_ERR_ALLOC, "device allocation failed");
+    TDB_CUDA(cudaMemcpyAsync(dc, coded, nb, cudaMemcpyHostToDevice, st));
+    TDB_CUDA(launch_modulate(dc, di, dq, sym_type, nb, modulation, st));
+    TDB_CUDA(cudaMemcpyAsync(sym_i, di, ns * ssz, cudaMemcpyDeviceToHost, st));
+    TDB_CUDA(cudaMemcpyAsync(sym_q, dq, ns * ssz, cudaMemcpyDeviceToHost, st));
+    TDB_CUDA(cudaStreamSynchronize(st));
+    return TDB200_OK;
+}
+
+int tdb200_awgn_batch(tdb200_decoder *d, const void *x, void *y, int type, int mem, size_t n, double sigma, uint64_t seed, void *stream)
+{
+    if (!d || !x || !y) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE) return fail(TDB200_ERR_INVALID_ARG, "mem=%d", mem);
+    if (type != TDB200_LLR_F32 && type != TDB200_LLR_F64 && type != TDB200_LLR_F16) return fail(TDB200_ERR_INVALID_ARG, "type=%d (F32, F64 or F16)", type);
+    if (!(sigma >= 0.0)) return fail(TDB200_ERR_INVALID_ARG, "sigma must not be negative");
+    if (n == 0) return TDB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    if (mem == TDB200_MEM_DEVICE) {
+        TDB_CUDA(launch_awgn(x, y, type, n, sigma, seed, st));
+        return TDB200_OK;
+    }
+    HostStage hs;
+    const size_t bytes = n * llr_elem_size(type);
+    void *dx = hs.alloc(bytes);
+    if (!dx) return fail(TDB200_ERR_ALLOC, "device allocation failed");
+    TDB_CUDA(cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, st));
+    TDB_CUDA(launch_awgn(dx, dx, type, n, sigma, seed, st));
+    TDB_CUDA(cudaMemcpyAsync(y, dx, bytes, cudaMemcpyDeviceToHost, st));
+    TDB_CUDA(cudaStreamSynchronize(st));
+    return TDB200_OK;
+}
+
+int tdb200_demap_batch(tdb200_decoder *d, const void *sym_i, const void *sym_q, int sym_type, void *llr, int llr_type, int mem,
+                       int n_cb, int modulation, double kf, void *stream)
+{
+    if (!d || !sym_i || !sym_q || !llr) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (n_cb < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d mem=%d", n_cb, mem);
+    if (llr_type < TDB200_LLR_F64 || llr_type > TDB200_LLR_F16) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d", llr_type);
+    int s = check_sym("tdb200_demap_batch", d, sym_type, modulation);
+    if (s) return s;
+    if (!(kf > 0.0)) return fail(TDB200_ERR_INVALID_ARG, "kf must be positive");
+    if (n_cb == 0) return TDB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    DemapArgs a{};
+    a.sym_type = sym_type; a.llr_type = llr_type; a.n_llr = (size_t)n_cb * d->NL; a.modulation = modulation; a.kf = kf;
+    a.frac_bits = d->cfg.frac_bits ? d->cfg.frac_bits : 3;
+    a.clip = std::min((1 << (a.frac_bits + 4)) - 1, 127);
+    if (mem == TDB200_MEM_DEVICE) {
+        a.sym_i = sym_i; a.sym_q = sym_q; a.llr = llr;
+        TDB_CUDA(launch_demap(a, st));
+        return TDB200_OK;
+    }
+    HostStage hs;
+    const size_t sb = a.n_llr / modulation * llr_elem_size(sym_type), lb = a.n_llr * llr_elem_size(llr_type);
+    void *di = hs.alloc(sb), *dq = hs.alloc(sb), *dl = hs.alloc(lb);
+    if (!di || !dq || !dl) return fail(TDB200_ERR_ALLOC, "device allocation failed");
+    TDB_CUDA(cudaMemcpyAsync(di, sym_i, sb, cudaMemcpyHostToDevice, st));
+    TDB_CUDA(cudaMemcpyAsync(dq, sym_q, sb, cudaMemcpyHostToDevice, st));
+    a.sym_i = di; a.sym_q = dq; a.llr = dl;
+    TDB_CUDA(launch_demap(a, st));
+    TDB_CUDA(cudaMemcpyAsync(llr, dl, lb, cudaMemcpyDeviceToHost, st));
+    TDB_CUDA(cudaStreamSynchronize(st));
     return TDB200_OK;
 }
 

@@ -161,4 +161,20 @@ struct ChannelArgs {
 cudaError_t launch_encode(const EncodeArgs &a, cudaStream_t st);
 cudaError_t launch_channel(const ChannelArgs &a, void *llr, int llr_type, cudaStream_t st);
 
+// ------------------------------------------------------------------ caller side: mapper / soft demapper (tdb200_modem.cu)
+struct DemapArgs {
+    const void *sym_i, *sym_q;  // [n_llr / modulation] each, device, element type sym_type
+    int sym_type;               // TDB200_LLR_F32 / F64 / F16
+    void *llr;                  // [n_llr] device, element type llr_type
+    int llr_type;               // F64: reference-order fp64 demapper; F32 / F16 / S8: fp32 demapper
+    size_t n_llr;               // multiple of 12
+    int modulation;             // bits per symbol: 1, 2, 3, 4, 6
+    double kf;                  // 1 / (2 sigma^2), ITTC/main.cpp:202
+    int frac_bits, clip;        // S8 output: clamp(rint(LLR * 2^frac_bits), +-clip)
+};
+bool modulation_ok(int M);
+cudaError_t launch_modulate(const uint8_t *coded, void *si, void *sq, int sym_type, size_t n_bits, int M, cudaStream_t st);
+cudaError_t launch_awgn(const void *x, void *y, int type, size_t n, double sigma, unsigned long long seed, cudaStream_t st);
+cudaError_t launch_demap(const DemapArgs &a, cudaStream_t st);
+
 }  // namespace tdb200

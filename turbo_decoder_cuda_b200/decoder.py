@@ -80,6 +80,14 @@ def load_library():
     L.tdb200_encode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.tdb200_channel_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                        C.c_double, C.c_uint64, C.c_void_p]
+    L.tdb200_modulate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p]
+    L.tdb200_awgn_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
+                                    C.c_double, C.c_uint64, C.c_void_p]
+    L.tdb200_demap_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_double, C.c_void_p]
+    L.tdb200_decode_symbols_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_double, C.POINTER(Outputs), C.c_void_p]
     _lib = L
     return L
 
@@ -214,6 +222,68 @@ class TurboDecoder:
         _check(self._L.tdb200_channel_batch(self._h, cp, _ptr_of(llr)[0], _LLR_TYPES[dtype], mem, n_cb,
                                             float(sigma), int(seed), stream))
         return llr
+
+    # ---- higher-order mapping (ITTC/modanddem.cpp module()/demodule()); symbols are planar (I, Q)
+    def _like(self, ref, shape, dtype):
+        if _is_torch(ref):
+            import torch
+            return torch.empty(shape, dtype=getattr(torch, dtype), device=ref.device)
+        return np.empty(shape, dtype=dtype)
+
+    def modulate(self, coded, modulation, dtype="float32", stream=0):
+        """tdb200_modulate_batch: coded [n_cb, 3K+12] uint8 -> (I, Q), each [n_cb, (3K+12)/modulation]."""
+        n_cb = int(coded.shape[0])
+        assert int(coded.shape[1]) == self.llr_len and str(coded.dtype).endswith("uint8")
+        ns = self.llr_len // modulation
+        si, sq = self._like(coded, (n_cb, ns), dtype), self._like(coded, (n_cb, ns), dtype)
+        cp, mem = _ptr_of(coded)
+        _check(self._L.tdb200_modulate_batch(self._h, cp, _ptr_of(si)[0], _ptr_of(sq)[0], _LLR_TYPES[dtype], mem, n_cb,
+                                             int(modulation), stream))
+        return si, sq
+
+    def awgn(self, x, sigma, seed, stream=0):
+        """tdb200_awgn_batch: x + sigma * N(0,1), same kind and dtype as x."""
+        tname = str(x.dtype).replace("torch.", "")
+        y = self._like(x, tuple(x.shape), tname)
+        xp, mem = _ptr_of(x)
+        n = int(np.prod(tuple(x.shape)))
+        _check(self._L.tdb200_awgn_batch(self._h, xp, _ptr_of(y)[0], _LLR_TYPES[tname], mem, n, float(sigma), int(seed), stream))
+        return y
+
+    def demap(self, sym_i, sym_q, modulation, kf, dtype="float32", stream=0):
+        """tdb200_demap_batch: received symbols -> llr [n_cb, 3K+12] of `dtype`
+        (float64: the reference's demodule() bit for bit; int8: the s16 decoder's channel values)."""
+        n_cb = int(sym_i.shape[0])
+        assert int(sym_i.shape[1]) * modulation == self.llr_len and tuple(sym_i.shape) == tuple(sym_q.shape)
+        tname = str(sym_i.dtype).replace("torch.", "")
+        llr = self._like(sym_i, (n_cb, self.llr_len), dtype)
+        ip, mem = _ptr_of(sym_i)
+        _check(self._L.tdb200_demap_batch(self._h, ip, _ptr_of(sym_q)[0], _LLR_TYPES[tname], _ptr_of(llr)[0], _LLR_TYPES[dtype],
+                                          mem, n_cb, int(modulation), float(kf), stream))
+        return llr
+
+    def decode_symbols_raw(self, i_ptr, q_ptr, sym_type, mem, n_cb, modulation, kf, bits=None, iters_used=None, stream=0):
+        """Thin call-through with raw pointers (timed loops)."""
+        o = Outputs(bits, None, iters_used, None, None, None)
+        _check(self._L.tdb200_decode_symbols_batch(self._h, i_ptr, q_ptr, sym_type, mem, n_cb, int(modulation), float(kf),
+                                                   C.byref(o), stream))
+
+    def decode_symbols(self, sym_i, sym_q, modulation, kf, want=("bits",), stream=0):
+        """tdb200_decode_symbols_batch: demodule() + TurboDecoding() in one call."""
+        n_cb = int(sym_i.shape[0])
+        assert int(sym_i.shape[1]) * modulation == self.llr_len and tuple(sym_i.shape) == tuple(sym_q.shape)
+        tname = str(sym_i.dtype).replace("torch.", "")
+        K, T = self.K, self.T
+        shapes = {"bits": ((n_cb, K), "uint8"), "bits_iters": ((n_cb, self.n_iter, K), "int32"),
+                  "iters_used": ((n_cb,), "int32"),
+                  "llr_siso1": ((n_cb, T), None), "llr_siso2": ((n_cb, T), None), "ext_siso2": ((n_cb, T), None)}
+        fl = "float64" if self.algo == ALGO_LOGMAP_F64 else "float32"
+        outs = {name: self._like(sym_i, shapes[name][0], shapes[name][1] or fl) for name in want}
+        o = Outputs(**{k: _ptr_of(v)[0] for k, v in outs.items()})
+        ip, mem = _ptr_of(sym_i)
+        _check(self._L.tdb200_decode_symbols_batch(self._h, ip, _ptr_of(sym_q)[0], _LLR_TYPES[tname], mem, n_cb,
+                                                   int(modulation), float(kf), C.byref(o), stream))
+        return outs
 
     def siso(self, recs, La, terminated=1, stream=0):
         """One BCJR pass (tdb200_siso_batch), the Log_MAP_decoder replacement; doubles only."""
