@@ -187,3 +187,28 @@ def test_every_lte_block_size(oracle):
             b, _, _, ovf = oracle.fx_decode(llr32[c], pi, prm)
             assert ovf == 0 and np.array_equal(out["bits"][c], b.astype(np.uint8)), "K=%d cb %d" % (K, c)
         dec.close()
+
+
+def test_int8_input_large_batch_and_alignment(oracle):
+    """8-bit channel values with more codeblocks than resident CTAs (the next-row L2 prefetch runs;
+    byte rows are only 4-byte aligned) and a row-offset view of the buffer; a misaligned device
+    pointer is refused, not faulted on."""
+    import torch
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    from turbo_decoder_cuda_b200.decoder import TdbError
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    K, n_cb = 6144, 1500
+    dec = TurboDecoder(K, n_iter=4, max_batch=2048)
+    from turbo_decoder_cuda_b200 import synth
+    bits, llr = synth.make_batch(K, 64, 1.5, seed=5, device="cuda")
+    q = torch.clamp(torch.round(llr * 8), -127, 127).to(torch.int8)
+    big = q.repeat((n_cb + 63) // 64 + 1, 1)[:n_cb + 1].contiguous()
+    want = dec.decode(q)["bits"]
+    got = dec.decode(big[:n_cb])["bits"]
+    assert torch.equal(got[:64], want) and torch.equal(got[640:704], want)
+    odd = dec.decode(big[1:n_cb + 1])["bits"]          # starts 18444 bytes in: 4-byte aligned only
+    assert torch.equal(odd[63:127], want)
+    flat = big.view(-1)
+    with pytest.raises(TdbError):
+        dec.decode_raw(flat.data_ptr() + 1, 2, 1, 4, bits=got.data_ptr())

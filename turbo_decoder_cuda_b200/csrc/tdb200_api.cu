@@ -481,6 +481,12 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
     TDB_CUDA(cudaSetDevice(c.device));
     const int K = c.K, T = d->T, NL = d->NL;
     const bool sym = src.symbols();
+    if (mem == TDB200_MEM_DEVICE && !sym) {
+        // the load stage reads 12 values at a time with the widest loads the row pitch allows
+        const uintptr_t need = src.llr_type == TDB200_LLR_S8 ? 4 : (src.llr_type == TDB200_LLR_F16 ? 8 : 16);
+        if (reinterpret_cast<uintptr_t>(src.llr) & (need - 1))
+            return fail(TDB200_ERR_INVALID_ARG, "device LLR buffer must be %d-byte aligned", (int)need);
+    }
     const int llr_type = sym ? native_llr_type(c) : src.llr_type;
     const void *llr = src.llr;
     const size_t esz = llr_elem_size(llr_type);

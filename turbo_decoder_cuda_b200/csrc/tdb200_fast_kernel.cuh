@@ -621,8 +621,11 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
         const long long nxt = (long long)2 * (blockIdx.x + A.prefetch_stride);
         if (nxt < A.n_cb) {
             const size_t esz = LLR_T == TDB200_LLR_F64 ? 8 : (LLR_T == TDB200_LLR_F32 ? 4 : (LLR_T == TDB200_LLR_F16 ? 2 : 1));
-            const char *p = static_cast<const char *>(A.llr) + (size_t)nxt * row * esz;
-            const size_t nbytes = ((nxt + 1 < A.n_cb ? 2 : 1) * row * esz) & ~(size_t)15;
+            // 16-byte granules: with one-byte channel values a row pair starts on an 8-byte boundary
+            const size_t b0 = reinterpret_cast<size_t>(A.llr) + (size_t)nxt * row * esz;
+            const size_t lo = b0 & ~(size_t)15, hi = (b0 + (nxt + 1 < A.n_cb ? 2 : 1) * row * esz) & ~(size_t)15;
+            const char *p = reinterpret_cast<const char *>(lo);
+            const size_t nbytes = hi - lo;
             const size_t chunk = 4096;
             for (size_t o = (size_t)tid * chunk; o < nbytes; o += (size_t)nthr * chunk) {
                 const unsigned sz = (unsigned)(nbytes - o < chunk ? nbytes - o : chunk);

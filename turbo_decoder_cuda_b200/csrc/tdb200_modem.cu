@@ -166,15 +166,17 @@ template <int M, typename T, int OUT_T>
 __global__ void __launch_bounds__(256) demap32_kernel(const T *__restrict__ si, const T *__restrict__ sq, void *__restrict__ out, size_t n_groups,
                                                       float kf, float scale, int clip)
 {
-    const size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= n_groups) return;
+    __shared__ __align__(16) unsigned stage[OUT_T == TDB200_LLR_S8 ? 3 * 256 : 4];
+    const size_t g0 = (size_t)blockIdx.x * blockDim.x;  // first group of this CTA
+    const size_t gi = g0 + threadIdx.x;
+    const bool live = gi < n_groups;
     constexpr int NS = 12 / M;
     float llr[12];
     float xs[NS], ys[NS];
 #pragma unroll
     for (int k = 0; k < NS; k++) {
-        xs[k] = ld_f(si, gi * NS + k);
-        ys[k] = (M == 1) ? 0.f : ld_f(sq, gi * NS + k);
+        xs[k] = live ? ld_f(si, gi * NS + k) : 0.f;
+        ys[k] = (M == 1 || !live) ? 0.f : ld_f(sq, gi * NS + k);
     }
 #pragma unroll
     for (int k = 0; k < NS; k++) {
@@ -200,17 +202,26 @@ __global__ void __launch_bounds__(256) demap32_kernel(const T *__restrict__ si, 
         }
     }
     if (OUT_T == TDB200_LLR_S8) {
-        int w[3];
+        // 12 bytes per thread: staged through shared memory (word stride 3: conflict-free) so that the
+        // CTA's 3072 contiguous output bytes leave as 16-byte stores
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             unsigned v = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) v |= ((unsigned)quant8(llr[4 * k + j], scale, clip) & 0xffu) << (8 * j);
-            w[k] = (int)v;
+            stage[3 * threadIdx.x + k] = v;
         }
-        int *o = reinterpret_cast<int *>(static_cast<int8_t *>(out) + 12 * gi);
-        o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+        __syncthreads();
+        const size_t left = n_groups - g0;
+        const int words = 3 * (int)(left < 256 ? left : 256);
+        unsigned *o = reinterpret_cast<unsigned *>(static_cast<int8_t *>(out) + 12 * g0);  // 3072 * blockIdx: 16-byte aligned
+        const int t = threadIdx.x;
+        const bool al16 = (reinterpret_cast<size_t>(o) & 15) == 0;  // caller-supplied buffers may be row-offset views
+        if (al16 && 4 * t + 3 < words) reinterpret_cast<uint4 *>(o)[t] = reinterpret_cast<const uint4 *>(stage)[t];
+        else
+            for (int w = 4 * t; w < min(words, 4 * t + 4); w++) o[w] = stage[w];
     } else if (OUT_T == TDB200_LLR_F16) {
+        if (!live) return;
         uint2 *o = reinterpret_cast<uint2 *>(static_cast<__half *>(out) + 12 * gi);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -218,6 +229,7 @@ __global__ void __launch_bounds__(256) demap32_kernel(const T *__restrict__ si, 
             o[k] = make_uint2(*reinterpret_cast<const unsigned *>(&a), *reinterpret_cast<const unsigned *>(&b));
         }
     } else {
+        if (!live) return;
         float4 *o = reinterpret_cast<float4 *>(static_cast<float *>(out) + 12 * gi);
 #pragma unroll
         for (int k = 0; k < 3; k++) o[k] = make_float4(llr[4 * k], llr[4 * k + 1], llr[4 * k + 2], llr[4 * k + 3]);
