@@ -196,6 +196,31 @@ int tdb200_decode_symbols_batch(tdb200_decoder *dec, const void *sym_i, const vo
                                 int mem, int n_cb, int modulation, double kf,
                                 const tdb200_outputs *out, void *stream);
 
+/* ---- TS 36.212 rate matching: the stage the reference declares and never wrote -------------------
+ * void rate_match(int *input, int in_len, int *output, int out_len) and
+ * void de_rate_match(double *input, double *output, int in_len, int out_len)  (ITTC/main.h:23-24,
+ * call sites commented out at ITTC/main.cpp:196,204).  Implemented per TS 36.212: tail-bit
+ * multiplexing into d0/d1/d2 (5.1.3.2.2), sub-block interleavers, circular buffer and bit selection
+ * from k0(rv) with <NULL> pruning (5.1.4.1).  The turbo-code side keeps the reference's multiplex
+ * order [n_cb][3K+12]; the channel side is [n_cb][E].  rv = redundancy version 0..3; ncb = soft
+ * buffer size N_cb (0: the full circular buffer K_w = 3 * 32 * ceil((K+4)/32)). */
+int tdb200_rate_match_batch(tdb200_decoder *dec, const uint8_t *coded, uint8_t *e_bits, int mem, int n_cb,
+                            int E, int rv, int ncb, void *stream);
+
+/* Soft inverse: e_llr [n_cb][E] -> llr [n_cb][3K+12], both of llr_type.  Bits sent more than once
+ * (E beyond one wrap of the buffer) are summed in transmission order, bits not sent come out as 0.
+ * accumulate != 0 adds to what `llr` already holds (HARQ combining of a retransmission with another
+ * rv).  Sums are fp32 (fp64 for TDB200_LLR_F64, saturating integers for TDB200_LLR_S8). */
+int tdb200_rate_dematch_batch(tdb200_decoder *dec, const void *e_llr, void *llr, int llr_type, int mem, int n_cb,
+                              int E, int rv, int ncb, int accumulate, void *stream);
+
+/* de_rate_match() + TurboDecoding() in one call (ITTC/main.cpp:204,221): rate-matched LLRs in,
+ * decisions out; the de-rate-matched values stay on the device (for TDB200_ALGO_MAXLOG_S16 already
+ * in the decoder's 8-bit channel format).  Results equal tdb200_rate_dematch_batch followed by
+ * tdb200_decode_batch.  `out` as for tdb200_decode_batch. */
+int tdb200_decode_rm_batch(tdb200_decoder *dec, const void *e_llr, int llr_type, int mem, int n_cb,
+                           int E, int rv, int ncb, const tdb200_outputs *out, void *stream);
+
 /* Introspection (what the plan resolved to). */
 typedef struct tdb200_plan_info {
     int K, f1, f2, n_iter, algo;

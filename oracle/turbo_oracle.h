@@ -130,6 +130,18 @@ int tdo_demap_f64(const double *si, const double *sq, int n_sym, int M, double k
 int tdo_demap_f32(const float *si, const float *sq, int n_sym, int M, float kf, float *out);
 void tdo_quant_s8(const float *llr, int n, int frac_bits, int clip, signed char *out);
 
+/* ------------------------------------------------------------------------
+ * TS 36.212 rate matching for turbo-coded blocks (turbo_oracle_rm.c; parity UNPINNED -- the
+ * reference only declares rate_match()/de_rate_match(), ITTC/main.h:23-24).  Turbo-code side in the
+ * reference's multiplex order; Ncb <= 0 means the full circular buffer K_w. */
+int tdo_rm_geometry(int K, int *R, int *Kpi, int *ND);          /* returns K_w */
+void tdo_rm_circular_buffer(int K, int *w /*K_w: multiplex position or -1 for <NULL>*/);
+int tdo_rm_k0(int K, int rv, int Ncb);
+int tdo_rm_selection(int K, int E, int rv, int Ncb, int *sel /*E*/);
+int tdo_rate_match(const int *coded, int K, int E, int rv, int Ncb, int *e_bits);
+int tdo_rate_dematch(const double *e_llr, int K, int E, int rv, int Ncb, int accumulate, double *llr);
+int tdo_rate_dematch_f32(const float *e_llr, int K, int E, int rv, int Ncb, int accumulate, float *llr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,10 +79,54 @@ class Oracle:
         L.tdo_fx_decode.restype = C.c_int
         L.tdo_f32_decode.argtypes = [_fp, _ip, C.POINTER(F32Params), _ip, C.c_void_p, C.c_void_p]
         L.tdo_f32_decode.restype = C.c_int
+        L.tdo_rm_geometry.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.tdo_rm_circular_buffer.argtypes = [C.c_int, _ip]
+        L.tdo_rm_k0.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.tdo_rm_selection.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip]
+        L.tdo_rate_match.argtypes = [_ip, C.c_int, C.c_int, C.c_int, C.c_int, _ip]
+        L.tdo_rate_dematch.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+        L.tdo_rate_dematch_f32.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]
         L.tdo_modulate.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp]
         L.tdo_demap_f64.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_double, _dp]
         L.tdo_demap_f32.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_float, _fp]
         L.tdo_quant_s8.argtypes = [_fp, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(dtype=np.int8, flags="C_CONTIGUOUS")]
+
+    # ---- TS 36.212 rate matching (turbo_oracle_rm.c)
+    def rm_geometry(self, K):
+        R, Kpi, ND = C.c_int(), C.c_int(), C.c_int()
+        Kw = self.lib.tdo_rm_geometry(K, C.byref(R), C.byref(Kpi), C.byref(ND))
+        return {"R": R.value, "Kpi": Kpi.value, "ND": ND.value, "Kw": Kw}
+
+    def rm_circular_buffer(self, K):
+        w = np.zeros(self.rm_geometry(K)["Kw"], np.int32)
+        self.lib.tdo_rm_circular_buffer(K, w)
+        return w
+
+    def rm_k0(self, K, rv, Ncb=0):
+        return self.lib.tdo_rm_k0(K, rv, Ncb)
+
+    def rm_selection(self, K, E, rv, Ncb=0):
+        sel = np.zeros(max(E, 1), np.int32)
+        if self.lib.tdo_rm_selection(K, E, rv, Ncb, sel):
+            raise ValueError("rate matching: empty circular buffer")
+        return sel[:E]
+
+    def rate_match(self, coded, K, E, rv, Ncb=0):
+        out = np.zeros(max(E, 1), np.int32)
+        if self.lib.tdo_rate_match(np.ascontiguousarray(coded, np.int32), K, E, rv, Ncb, out):
+            raise ValueError("rate matching: empty circular buffer")
+        return out[:E]
+
+    def rate_dematch(self, e_llr, K, rv, Ncb=0, into=None):
+        """double accumulation for float64 input, float accumulation otherwise (as on the device)."""
+        f32 = np.asarray(e_llr).dtype != np.float64
+        dt = np.float32 if f32 else np.float64
+        e = np.ascontiguousarray(e_llr, dt)
+        llr = np.zeros(3 * K + 12, dt) if into is None else np.array(into, dt)
+        fn = self.lib.tdo_rate_dematch_f32 if f32 else self.lib.tdo_rate_dematch
+        if fn(e if e.size else np.zeros(1, dt), K, e.size, rv, Ncb, 0 if into is None else 1, llr):
+            raise ValueError("rate matching: empty circular buffer")
+        return llr
 
     # ---- mapper / soft demapper (turbo_oracle_mod.c)
     def modulate(self, bits, M):

@@ -178,3 +178,77 @@ def test_modem_vs_live_reference(oracle, M):
         assert np.array_equal(oracle.demap_f64(xi, xq, M, kf), ref.demodule(xi, xq, M, kf))
     # noiseless: the hard decision of every LLR is the transmitted bit
     assert np.array_equal(oracle.demap_f64(si, sq, M, 1.0) > 0, bits == 1)
+
+
+# ---- TS 36.212 rate matching: oracle/turbo_oracle_rm.c.  The reference only declares
+#      rate_match()/de_rate_match() (ITTC/main.h:23-24), so these are structural checks of the literal
+#      restatement of the specification -- parity with 3GPP test vectors is UNPINNED (none offline).
+def test_rate_matching_structure(oracle):
+    assert oracle.rm_geometry(40) == {"R": 2, "Kpi": 64, "ND": 20, "Kw": 192}
+    assert oracle.rm_geometry(6144) == {"R": 193, "Kpi": 6176, "ND": 28, "Kw": 18528}
+    for K in oracle.lte_sizes():
+        g = oracle.rm_geometry(K)
+        w = oracle.rm_circular_buffer(K)
+        assert np.array_equal(np.sort(w[w >= 0]), np.arange(3 * K + 12)), "every coded bit sits in the buffer exactly once"
+        assert np.count_nonzero(w < 0) == 3 * g["ND"]
+        assert [oracle.rm_k0(K, rv) for rv in range(4)] == [g["R"] * (2 * -(-g["Kw"] // (8 * g["R"])) * rv + 2) for rv in range(4)]
+        # systematic part first: the first K_pi entries hold d0 = the systematic bits and four tail bits
+        s = w[:g["Kpi"]]
+        s = s[s >= 0]
+        tails = {3 * K + 0, 3 * K + 3, 3 * K + 6, 3 * K + 9}         # x_K, z_K+1, x'_K, z'_K+1
+        assert all((v % 3 == 0 and v < 3 * K) or v in tails for v in s) and s.size == K + 4
+        # then d1 and d2 interlaced: parity 1 of step i next to parity 2 of a neighbouring step
+        p = w[g["Kpi"]:]
+        assert all(v < 0 or v >= 3 * K or v % 3 == 1 for v in p[0::2]) and all(v < 0 or v >= 3 * K or v % 3 == 2 for v in p[1::2])
+
+
+def test_rate_matching_round_trips(oracle):
+    rng = np.random.default_rng(3)
+    K = 512
+    NL = 3 * K + 12
+    coded = rng.integers(0, 2, NL).astype(np.int32)
+    for rv in range(4):
+        full = oracle.rm_selection(K, NL, rv)
+        assert np.array_equal(np.sort(full), np.arange(NL)), "one wrap sends every bit once, whatever the start"
+        assert np.array_equal(oracle.rate_match(coded, K, NL, rv), coded[full])
+    # puncturing: what was not sent comes back as 0, what was sent comes back unchanged
+    E = K + 300
+    sel = oracle.rm_selection(K, E, 0)
+    e = rng.standard_normal(E)
+    back = oracle.rate_dematch(e, K, 0)
+    assert np.array_equal(back[sel], e) and np.count_nonzero(back) == E
+    # repetition: the second wrap lands on the same positions and is summed
+    E = NL + 100
+    sel = oracle.rm_selection(K, E, 1)
+    assert np.array_equal(sel[NL:], sel[:100])
+    e = rng.standard_normal(E)
+    back = oracle.rate_dematch(e, K, 1)
+    want = np.zeros(NL)
+    np.add.at(want, sel, e)
+    assert np.allclose(back, want, rtol=0, atol=1e-12)
+    # HARQ: a second transmission with another rv accumulates into the first
+    e2 = rng.standard_normal(700)
+    both = oracle.rate_dematch(e2, K, 2, into=back)
+    np.add.at(want, oracle.rm_selection(K, 700, 2), e2)
+    assert np.allclose(both, want, rtol=0, atol=1e-12)
+    # limited soft buffer: positions beyond N_cb are never sent
+    Ncb = 1200
+    sel = oracle.rm_selection(K, 5000, 0, Ncb)
+    w = oracle.rm_circular_buffer(K)
+    assert set(sel) == set(w[:Ncb][w[:Ncb] >= 0])
+
+
+def test_rate_matched_block_decodes(oracle):
+    """rate 1/2 by puncturing (E = 2K) at 2.5 dB: encode -> rate match -> BPSK/AWGN -> de-rate-match -> decode."""
+    K, rv = 512, 0
+    pi = oracle.qpp(K)
+    rng = np.random.default_rng(9)
+    bits = rng.integers(0, 2, K).astype(np.int32)
+    coded = oracle.encode(bits, pi)
+    E = 2 * K
+    e = oracle.rate_match(coded, K, E, rv)
+    sigma = 10 ** (-2.5 / 20) * np.sqrt(0.5 / 0.5)
+    r = (2.0 * e - 1.0) + sigma * rng.standard_normal(E)
+    llr = oracle.rate_dematch(2 * r / sigma ** 2, K, rv)
+    out = oracle.decode(llr, pi, 8)
+    assert np.array_equal(out[-1], bits)

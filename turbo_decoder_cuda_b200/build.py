@@ -36,6 +36,7 @@ KERNEL_TUS = [
     ("tdb200_f32.cu", ["-fmad=false", "-Xptxas", "-v"]),
     ("tdb200_encode.cu", []),
     ("tdb200_modem.cu", ["-fmad=false"]),
+    ("tdb200_ratematch.cu", ["-fmad=false"]),
 ]
 
 

@@ -132,8 +132,13 @@ struct tdb200_decoder {
     cudaEvent_t ev_start = nullptr;
     void *siso_in = nullptr, *siso_out = nullptr;  // staging of tdb200_siso_batch (host callers)
     size_t siso_in_bytes = 0;
-    void *dem = nullptr;  // demapped channel values, device callers of tdb200_decode_symbols_batch
+    void *dem = nullptr;  // demapped / de-rate-matched channel values, device callers of tdb200_decode_{symbols,rm}_batch
     size_t dem_bytes = 0;
+    struct RmTable {
+        int rv = 0, ncb = 0, nnn = 0;
+        int *d_perm = nullptr, *d_inv = nullptr;
+    };
+    std::vector<RmTable> rm_tables;  // one per (rv, N_cb) used so far
     int launches_last = 0;
 };
 
@@ -202,6 +207,7 @@ void tdb200_destroy(tdb200_decoder *d)
     cudaSetDevice(d->cfg.device);
     cudaFree(d->d_pi); cudaFree(d->d_pi_inv); cudaFree(d->ws64_block); cudaFree(d->d_tab2);
     cudaFree(d->siso_in); cudaFree(d->siso_out); cudaFree(d->dem);
+    for (auto &t : d->rm_tables) { cudaFree(t.d_perm); cudaFree(t.d_inv); }
     for (auto &sl : d->slot) {
         cudaFree(sl.d_in); cudaFree(sl.d_dem); cudaFree(sl.d_bits); cudaFree(sl.d_bits_iters); cudaFree(sl.d_iters_used);
         cudaFree(sl.d_llr1); cudaFree(sl.d_llr2); cudaFree(sl.d_ext2);
@@ -450,6 +456,9 @@ struct Source {
     int sym_type = 0, modulation = 0;
     double kf = 0.0;
     bool symbols() const { return sym_i != nullptr; }
+    // rate-matched LLRs: `llr` holds [n_cb][rm_E] values that are de-rate-matched on the device first
+    const tdb200_decoder::RmTable *rm = nullptr;
+    int rm_E = 0;
 };
 
 // the channel-value format the decoder consumes without conversion loss
@@ -470,6 +479,44 @@ static int launch_demap_chunk(tdb200_decoder *d, const Source &src, const void *
     return TDB200_OK;
 }
 
+static int launch_dematch_chunk(tdb200_decoder *d, const Source &src, const void *e_llr, void *llr, int out_type, int n, cudaStream_t st)
+{
+    RmArgs a{};
+    a.e_llr = e_llr; a.llr = llr; a.in_type = src.llr_type; a.out_type = out_type;
+    a.inv = src.rm->d_inv; a.nnn = src.rm->nnn; a.NL = d->NL; a.E = src.rm_E; a.n_cb = n; a.accumulate = 0;
+    a.frac_bits = d->cfg.frac_bits ? d->cfg.frac_bits : 3;
+    a.clip = std::min((1 << (a.frac_bits + 4)) - 1, 127);
+    TDB_CUDA(launch_rate_dematch(a, st));
+    d->launches_last += 1;
+    return TDB200_OK;
+}
+
+// The (rv, N_cb) permutation of a handle, built on first use.
+static int rm_table(tdb200_decoder *d, int rv, int ncb, const tdb200_decoder::RmTable **out)
+{
+    if (rv < 0 || rv > 3) return fail(TDB200_ERR_INVALID_ARG, "rv=%d (0..3)", rv);
+    const int Kw = 3 * 32 * ((d->cfg.K + 4 + 31) / 32);
+    if (ncb < 0) return fail(TDB200_ERR_INVALID_ARG, "ncb=%d", ncb);
+    if (ncb == 0 || ncb > Kw) ncb = Kw;
+    for (auto &t : d->rm_tables)
+        if (t.rv == rv && t.ncb == ncb) { *out = &t; return TDB200_OK; }
+    std::vector<int> perm, inv;
+    if (!build_rm_table(d->cfg.K, rv, ncb, perm, inv)) return fail(TDB200_ERR_INVALID_ARG, "ncb=%d leaves no transmittable bit", ncb);
+    tdb200_decoder::RmTable t;
+    t.rv = rv; t.ncb = ncb; t.nnn = (int)perm.size();
+    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_CUDA(cudaMalloc(&t.d_perm, sizeof(int) * perm.size()));
+    if (cudaMalloc(&t.d_inv, sizeof(int) * inv.size()) != cudaSuccess) { cudaFree(t.d_perm); return fail(TDB200_ERR_ALLOC, "device allocation failed"); }
+    cudaError_t e = cudaMemcpy(t.d_perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(t.d_inv, inv.data(), sizeof(int) * inv.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(t.d_perm); cudaFree(t.d_inv); return fail(TDB200_ERR_CUDA, "rate-matching table upload: %s", cudaGetErrorString(e)); }
+    d->rm_tables.reserve(64);  // pointers into the vector are handed out: keep them stable
+    if (d->rm_tables.size() >= 64) { cudaFree(t.d_perm); cudaFree(t.d_inv); return fail(TDB200_ERR_UNSUPPORTED, "more than 64 distinct (rv, ncb) pairs on one handle"); }
+    d->rm_tables.push_back(t);
+    *out = &d->rm_tables.back();
+    return TDB200_OK;
+}
+
 static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, const tdb200_outputs *out, void *stream)
 {
     if (n_cb < 0) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d", n_cb);
@@ -480,18 +527,21 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDB_CUDA(cudaSetDevice(c.device));
     const int K = c.K, T = d->T, NL = d->NL;
-    const bool sym = src.symbols();
-    if (mem == TDB200_MEM_DEVICE && !sym) {
+    const bool sym = src.symbols(), rm = (src.rm != nullptr);
+    if (mem == TDB200_MEM_DEVICE && !sym && !rm) {
         // the load stage reads 12 values at a time with the widest loads the row pitch allows
         const uintptr_t need = src.llr_type == TDB200_LLR_S8 ? 4 : (src.llr_type == TDB200_LLR_F16 ? 8 : 16);
         if (reinterpret_cast<uintptr_t>(src.llr) & (need - 1))
             return fail(TDB200_ERR_INVALID_ARG, "device LLR buffer must be %d-byte aligned", (int)need);
     }
-    const int llr_type = sym ? native_llr_type(c) : src.llr_type;
+    // what the decode kernel reads: the caller's LLRs, or the staged output of the demapper / de-rate-matcher
+    const int llr_type = sym ? native_llr_type(c) : ((rm && c.algo == TDB200_ALGO_MAXLOG_S16) ? TDB200_LLR_S8 : src.llr_type);
     const void *llr = src.llr;
     const size_t esz = llr_elem_size(llr_type);
     const size_t ssz = sym ? llr_elem_size(src.sym_type) : 0;
     const size_t NS = sym ? (size_t)NL / src.modulation : 0;  // symbols per codeblock
+    const size_t rsz = rm ? llr_elem_size(src.llr_type) : 0, RE = rm ? (size_t)src.rm_E : 0;  // rate-matched row
+    const bool staged = sym || rm;
 
     const bool f64 = (c.algo == TDB200_ALGO_LOGMAP_F64);
     const size_t fsz = f64 ? sizeof(double) : sizeof(float);  // native float type of the LLR outputs
@@ -502,7 +552,7 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
 
     if (mem == TDB200_MEM_DEVICE) {
         // ---- device buffers: chunks of max_batch (the fp64 workspace is sized for that), all on `stream`
-        if (sym) {
+        if (staged) {
             int s = ensure(d->dem, d->dem_bytes, (size_t)std::min(c.max_batch, n_cb) * NL * esz);
             if (s) return s;
         }
@@ -512,8 +562,11 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
                 int s = launch_demap_chunk(d, src, static_cast<const char *>(src.sym_i) + (size_t)c0 * NS * ssz,
                                            static_cast<const char *>(src.sym_q) + (size_t)c0 * NS * ssz, d->dem, n, st);
                 if (s) return s;
+            } else if (rm) {
+                int s = launch_dematch_chunk(d, src, static_cast<const char *>(llr) + (size_t)c0 * RE * rsz, d->dem, llr_type, n, st);
+                if (s) return s;
             }
-            int s = launch_chunk(d, sym ? d->dem : static_cast<const char *>(llr) + (size_t)c0 * NL * esz, llr_type, n,
+            int s = launch_chunk(d, staged ? d->dem : static_cast<const char *>(llr) + (size_t)c0 * NL * esz, llr_type, n,
                                  out->bits ? out->bits + (size_t)c0 * K : nullptr,
                                  out->bits_iters ? out->bits_iters + (size_t)c0 * c.n_iter * K : nullptr,
                                  out->iters_used ? out->iters_used + c0 : nullptr,
@@ -543,8 +596,8 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
     }
     const int cap = d->slot_cap;
     for (auto &sl : d->slot) {
-        if ((s = ensure(sl.d_in, sl.d_in_bytes, sym ? 2 * (size_t)cap * NS * ssz : (size_t)cap * NL * esz))) return s;
-        if (sym && (s = ensure(sl.d_dem, sl.d_dem_bytes, (size_t)cap * NL * esz))) return s;
+        if ((s = ensure(sl.d_in, sl.d_in_bytes, sym ? 2 * (size_t)cap * NS * ssz : (rm ? (size_t)cap * RE * rsz : (size_t)cap * NL * esz)))) return s;
+        if (staged && (s = ensure(sl.d_dem, sl.d_dem_bytes, (size_t)cap * NL * esz))) return s;
         if (out->bits && (s = ensure_once(sl.d_bits, (size_t)cap * K))) return s;
         if (out->bits_iters && (s = ensure_once(sl.d_bits_iters, sizeof(int32_t) * (size_t)cap * c.n_iter * K))) return s;
         if (out->iters_used && !f64 && (s = ensure_once(sl.d_iters_used, sizeof(int32_t) * (size_t)cap))) return s;
@@ -569,6 +622,9 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
                                      cudaMemcpyHostToDevice, d->s_h2d));
             TDB_CUDA(cudaMemcpyAsync(d_q, static_cast<const char *>(src.sym_q) + (size_t)c0 * NS * ssz, (size_t)n * NS * ssz,
                                      cudaMemcpyHostToDevice, d->s_h2d));
+        } else if (rm) {
+            TDB_CUDA(cudaMemcpyAsync(sl.d_in, static_cast<const char *>(llr) + (size_t)c0 * RE * rsz, (size_t)n * RE * rsz,
+                                     cudaMemcpyHostToDevice, d->s_h2d));
         } else {
             TDB_CUDA(cudaMemcpyAsync(sl.d_in, static_cast<const char *>(llr) + (size_t)c0 * NL * esz, (size_t)n * NL * esz,
                                      cudaMemcpyHostToDevice, d->s_h2d));
@@ -577,7 +633,8 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
         TDB_CUDA(cudaStreamWaitEvent(d->s_k, sl.in_ready, 0));
         if (reused) TDB_CUDA(cudaStreamWaitEvent(d->s_k, sl.out_done, 0));  // the copy-out of this slot's previous results
         if (sym && (s = launch_demap_chunk(d, src, sl.d_in, d_q, sl.d_dem, n, d->s_k))) return s;
-        s = launch_chunk(d, sym ? sl.d_dem : sl.d_in, llr_type, n, out->bits ? sl.d_bits : nullptr, out->bits_iters ? sl.d_bits_iters : nullptr,
+        if (rm && (s = launch_dematch_chunk(d, src, sl.d_in, sl.d_dem, llr_type, n, d->s_k))) return s;
+        s = launch_chunk(d, staged ? sl.d_dem : sl.d_in, llr_type, n, out->bits ? sl.d_bits : nullptr, out->bits_iters ? sl.d_bits_iters : nullptr,
                          (out->iters_used && !f64) ? sl.d_iters_used : nullptr, out->llr_siso1 ? sl.d_llr1 : nullptr,
                          out->llr_siso2 ? sl.d_llr2 : nullptr, out->ext_siso2 ? sl.d_ext2 : nullptr, d->s_k);
         if (s) return s;
@@ -628,6 +685,19 @@ int tdb200_decode_symbols_batch(tdb200_decoder *d, const void *sym_i, const void
     if (!(kf > 0.0)) return fail(TDB200_ERR_INVALID_ARG, "kf must be positive");
     Source src;
     src.sym_i = sym_i; src.sym_q = sym_q; src.sym_type = sym_type; src.modulation = modulation; src.kf = kf;
+    return decode_core(d, src, mem, n_cb, out, stream);
+}
+
+int tdb200_decode_rm_batch(tdb200_decoder *d, const void *e_llr, int llr_type, int mem, int n_cb, int E, int rv, int ncb,
+                           const tdb200_outputs *out, void *stream)
+{
+    if (!d || !out || (!e_llr && n_cb > 0 && E > 0)) return fail(TDB200_ERR_INVALID_ARG, "dec/e_llr/out is NULL");
+    if (llr_type < TDB200_LLR_F64 || llr_type > TDB200_LLR_F16) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d", llr_type);
+    if (E < 0) return fail(TDB200_ERR_INVALID_ARG, "E=%d", E);
+    Source src;
+    src.llr = e_llr; src.llr_type = llr_type; src.rm_E = E;
+    int s = rm_table(d, rv, ncb, &src.rm);
+    if (s) return s;
     return decode_core(d, src, mem, n_cb, out, stream);
 }
 
@@ -725,6 +795,63 @@ int tdb200_demap_batch(tdb200_decoder *d, const void *sym_i, const void *sym_q, 
     TDB_CUDA(cudaMemcpyAsync(dq, sym_q, sb, cudaMemcpyHostToDevice, st));
     a.sym_i = di; a.sym_q = dq; a.llr = dl;
     TDB_CUDA(launch_demap(a, st));
+    TDB_CUDA(cudaMemcpyAsync(llr, dl, lb, cudaMemcpyDeviceToHost, st));
+    TDB_CUDA(cudaStreamSynchronize(st));
+    return TDB200_OK;
+}
+
+int tdb200_rate_match_batch(tdb200_decoder *d, const uint8_t *coded, uint8_t *e_bits, int mem, int n_cb, int E, int rv, int ncb, void *stream)
+{
+    if (!d || !coded || (!e_bits && n_cb > 0 && E > 0)) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (n_cb < 0 || E < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d E=%d mem=%d", n_cb, E, mem);
+    const tdb200_decoder::RmTable *t = nullptr;
+    int s = rm_table(d, rv, ncb, &t);
+    if (s) return s;
+    if (n_cb == 0 || E == 0) return TDB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    if (mem == TDB200_MEM_DEVICE) {
+        TDB_CUDA(launch_rate_match(coded, e_bits, t->d_perm, t->nnn, d->NL, E, n_cb, st));
+        return TDB200_OK;
+    }
+    HostStage hs;
+    uint8_t *dc = static_cast<uint8_t *>(hs.alloc((size_t)n_cb * d->NL)), *de = static_cast<uint8_t *>(hs.alloc((size_t)n_cb * E));
+    if (!dc || !de) return fail(TDB200_ERR_ALLOC, "device allocation failed");
+    TDB_CUDA(cudaMemcpyAsync(dc, coded, (size_t)n_cb * d->NL, cudaMemcpyHostToDevice, st));
+    TDB_CUDA(launch_rate_match(dc, de, t->d_perm, t->nnn, d->NL, E, n_cb, st));
+    TDB_CUDA(cudaMemcpyAsync(e_bits, de, (size_t)n_cb * E, cudaMemcpyDeviceToHost, st));
+    TDB_CUDA(cudaStreamSynchronize(st));
+    return TDB200_OK;
+}
+
+int tdb200_rate_dematch_batch(tdb200_decoder *d, const void *e_llr, void *llr, int llr_type, int mem, int n_cb, int E, int rv, int ncb,
+                              int accumulate, void *stream)
+{
+    if (!d || !llr || (!e_llr && n_cb > 0 && E > 0)) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (n_cb < 0 || E < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d E=%d mem=%d", n_cb, E, mem);
+    if (llr_type < TDB200_LLR_F64 || llr_type > TDB200_LLR_F16) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d", llr_type);
+    const tdb200_decoder::RmTable *t = nullptr;
+    int s = rm_table(d, rv, ncb, &t);
+    if (s) return s;
+    if (n_cb == 0) return TDB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    RmArgs a{};
+    a.in_type = a.out_type = llr_type; a.inv = t->d_inv; a.nnn = t->nnn; a.NL = d->NL; a.E = E; a.n_cb = n_cb; a.accumulate = accumulate ? 1 : 0;
+    a.frac_bits = d->cfg.frac_bits ? d->cfg.frac_bits : 3; a.clip = 127;
+    if (mem == TDB200_MEM_DEVICE) {
+        a.e_llr = e_llr; a.llr = llr;
+        TDB_CUDA(launch_rate_dematch(a, st));
+        return TDB200_OK;
+    }
+    HostStage hs;
+    const size_t esz = llr_elem_size(llr_type), eb = (size_t)n_cb * E * esz, lb = (size_t)n_cb * d->NL * esz;
+    void *de = hs.alloc(eb), *dl = hs.alloc(lb);
+    if (!de || !dl) return fail(TDB200_ERR_ALLOC, "device allocation failed");
+    TDB_CUDA(cudaMemcpyAsync(de, e_llr, eb, cudaMemcpyHostToDevice, st));
+    if (accumulate) TDB_CUDA(cudaMemcpyAsync(dl, llr, lb, cudaMemcpyHostToDevice, st));
+    a.e_llr = de; a.llr = dl;
+    TDB_CUDA(launch_rate_dematch(a, st));
     TDB_CUDA(cudaMemcpyAsync(llr, dl, lb, cudaMemcpyDeviceToHost, st));
     TDB_CUDA(cudaStreamSynchronize(st));
     return TDB200_OK;

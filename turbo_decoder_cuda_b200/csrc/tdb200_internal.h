@@ -3,6 +3,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+
+#include <vector>
 #include <stdint.h>
 
 #include "tdb200.h"
@@ -176,5 +178,19 @@ bool modulation_ok(int M);
 cudaError_t launch_modulate(const uint8_t *coded, void *si, void *sq, int sym_type, size_t n_bits, int M, cudaStream_t st);
 cudaError_t launch_awgn(const void *x, void *y, int type, size_t n, double sigma, unsigned long long seed, cudaStream_t st);
 cudaError_t launch_demap(const DemapArgs &a, cudaStream_t st);
+
+// ------------------------------------------------------------------ caller side: TS 36.212 rate matching (tdb200_ratematch.cu)
+struct RmArgs {
+    const void *e_llr;  // [n_cb][E] device, element type in_type
+    void *llr;          // [n_cb][3K+12] device, element type out_type (== in_type, or S8 for the s16 decoder)
+    int in_type, out_type;
+    const int *inv;     // [3K+12] device: first transmission index of each multiplex position, -1 if never sent
+    int nnn;            // transmitted positions per wrap of the circular buffer
+    int NL, E, n_cb, accumulate;
+    int frac_bits, clip;
+};
+bool build_rm_table(int K, int rv, int Ncb, std::vector<int> &perm, std::vector<int> &inv);
+cudaError_t launch_rate_match(const uint8_t *coded, uint8_t *e_bits, const int *perm, int nnn, int NL, int E, int n_cb, cudaStream_t st);
+cudaError_t launch_rate_dematch(const RmArgs &a, cudaStream_t st);
 
 }  // namespace tdb200

@@ -88,6 +88,11 @@ def load_library():
                                      C.c_int, C.c_int, C.c_double, C.c_void_p]
     L.tdb200_decode_symbols_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_double, C.POINTER(Outputs), C.c_void_p]
+    L.tdb200_rate_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.tdb200_rate_dematch_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_void_p]
+    L.tdb200_decode_rm_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(Outputs), C.c_void_p]
     _lib = L
     return L
 
@@ -283,6 +288,42 @@ class TurboDecoder:
         ip, mem = _ptr_of(sym_i)
         _check(self._L.tdb200_decode_symbols_batch(self._h, ip, _ptr_of(sym_q)[0], _LLR_TYPES[tname], mem, n_cb,
                                                    int(modulation), float(kf), C.byref(o), stream))
+        return outs
+
+    # ---- TS 36.212 rate matching (the reference's declared-only rate_match / de_rate_match)
+    def rate_match(self, coded, E, rv=0, ncb=0, stream=0):
+        """tdb200_rate_match_batch: coded [n_cb, 3K+12] uint8 -> transmitted bits [n_cb, E]."""
+        n_cb = int(coded.shape[0])
+        assert int(coded.shape[1]) == self.llr_len and str(coded.dtype).endswith("uint8")
+        e = self._like(coded, (n_cb, E), "uint8")
+        cp, mem = _ptr_of(coded)
+        _check(self._L.tdb200_rate_match_batch(self._h, cp, _ptr_of(e)[0], mem, n_cb, int(E), int(rv), int(ncb), stream))
+        return e
+
+    def rate_dematch(self, e_llr, rv=0, ncb=0, into=None, stream=0):
+        """tdb200_rate_dematch_batch: e_llr [n_cb, E] -> llr [n_cb, 3K+12] of the same dtype;
+        `into` (same kind, shape [n_cb, 3K+12]) is combined in place (HARQ) and returned."""
+        n_cb, E = int(e_llr.shape[0]), int(e_llr.shape[1])
+        tname = str(e_llr.dtype).replace("torch.", "")
+        llr = into if into is not None else self._like(e_llr, (n_cb, self.llr_len), tname)
+        ep, mem = _ptr_of(e_llr)
+        _check(self._L.tdb200_rate_dematch_batch(self._h, ep, _ptr_of(llr)[0], _LLR_TYPES[tname], mem, n_cb, E, int(rv), int(ncb),
+                                                 0 if into is None else 1, stream))
+        return llr
+
+    def decode_rm(self, e_llr, rv=0, ncb=0, want=("bits",), stream=0):
+        """tdb200_decode_rm_batch: de_rate_match() + TurboDecoding() in one call."""
+        n_cb, E = int(e_llr.shape[0]), int(e_llr.shape[1])
+        tname = str(e_llr.dtype).replace("torch.", "")
+        K, T = self.K, self.T
+        shapes = {"bits": ((n_cb, K), "uint8"), "bits_iters": ((n_cb, self.n_iter, K), "int32"),
+                  "iters_used": ((n_cb,), "int32"),
+                  "llr_siso1": ((n_cb, T), None), "llr_siso2": ((n_cb, T), None), "ext_siso2": ((n_cb, T), None)}
+        fl = "float64" if self.algo == ALGO_LOGMAP_F64 else "float32"
+        outs = {name: self._like(e_llr, shapes[name][0], shapes[name][1] or fl) for name in want}
+        o = Outputs(**{k: _ptr_of(v)[0] for k, v in outs.items()})
+        ep, mem = _ptr_of(e_llr)
+        _check(self._L.tdb200_decode_rm_batch(self._h, ep, _LLR_TYPES[tname], mem, n_cb, E, int(rv), int(ncb), C.byref(o), stream))
         return outs
 
     def siso(self, recs, La, terminated=1, stream=0):
