@@ -114,13 +114,16 @@ int tdo_rate_match(const int *coded, int K, int E, int rv, int Ncb, int *e_bits)
 }
 
 /* soft inverse: repeated positions are summed in transmission order, punctured ones stay 0
- * (accumulate != 0: add to what llr[] already holds -- HARQ combining of retransmissions) */
+ * (accumulate != 0: new = old + this transmission's sums -- HARQ combining of retransmissions) */
 int tdo_rate_dematch(const double *e_llr, int K, int E, int rv, int Ncb, int accumulate, double *llr)
 {
     int *sel = (int *)malloc(sizeof(int) * (E > 0 ? E : 1));
     if (tdo_rm_selection(K, E, rv, Ncb, sel)) { free(sel); return -1; }
-    if (!accumulate) memset(llr, 0, sizeof(double) * (3 * K + 12));
-    for (int e = 0; e < E; e++) llr[sel[e]] += e_llr[e];
+    const int NL = 3 * K + 12;
+    double *sum = (double *)calloc(NL, sizeof(double));
+    for (int e = 0; e < E; e++) sum[sel[e]] += e_llr[e];
+    for (int n = 0; n < NL; n++) llr[n] = accumulate ? llr[n] + sum[n] : sum[n];
+    free(sum);
     free(sel);
     return 0;
 }
@@ -130,8 +133,11 @@ int tdo_rate_dematch_f32(const float *e_llr, int K, int E, int rv, int Ncb, int 
 {
     int *sel = (int *)malloc(sizeof(int) * (E > 0 ? E : 1));
     if (tdo_rm_selection(K, E, rv, Ncb, sel)) { free(sel); return -1; }
-    if (!accumulate) memset(llr, 0, sizeof(float) * (3 * K + 12));
-    for (int e = 0; e < E; e++) llr[sel[e]] += e_llr[e];
+    const int NL = 3 * K + 12;
+    float *sum = (float *)calloc(NL, sizeof(float));
+    for (int e = 0; e < E; e++) sum[sel[e]] += e_llr[e];
+    for (int n = 0; n < NL; n++) llr[n] = accumulate ? llr[n] + sum[n] : sum[n];
+    free(sum);
     free(sel);
     return 0;
 }

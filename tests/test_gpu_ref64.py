@@ -138,6 +138,22 @@ def test_compat_layer_is_the_reference_call(oracle):
     g(recs, La, 1, got, T)
     want = oracle.siso(recs, La, terminated=1)
     assert np.abs(got - want).max() < LLR_TOL
+    # the declared-only pair rate_match / de_rate_match (ITTC/main.h:23-24, call sites main.cpp:196,204)
+    coded = oracle.encode(bits[0].astype(np.int32), pi)
+    E = 2 * K
+    tx = np.zeros(E, np.int32)
+    rmf = getattr(lib, "_Z10rate_matchPiiS_i")
+    rmf.argtypes = [ip, C.c_int, ip, C.c_int]
+    rmf.restype = None
+    rmf(np.ascontiguousarray(coded, np.int32), 3 * K + 12, tx, E)
+    assert np.array_equal(tx, oracle.rate_match(coded, K, E, 0))
+    rx = np.random.default_rng(5).standard_normal(E)
+    back = np.zeros(3 * K + 12)
+    dmf = getattr(lib, "_Z13de_rate_matchPdS_ii")
+    dmf.argtypes = [dp, dp, C.c_int, C.c_int]
+    dmf.restype = None
+    dmf(rx, back, E, 3 * K + 12)
+    assert np.array_equal(back, oracle.rate_dematch(rx, K, 0))
 
 
 def test_error_paths_and_concurrent_handles(oracle):

@@ -4,6 +4,8 @@
 // _Z13TurboDecodingPdPii and _Z15Log_MAP_decoderPdS_iS_i):
 //     void TurboDecoding(double *flow_for_decode, int *flow_decoded, int flow_length);   log_map.cpp:1146
 //     void Log_MAP_decoder(double *recs, double *La, int terminated, double *LLR, int len_total);  :898
+//     void rate_match(int *input, int in_len, int *output, int out_len);                 main.h:23 (declared only)
+//     void de_rate_match(double *input, double *output, int in_len, int out_len);        main.h:24 (declared only)
 // and weak versions of TurboCodingInit / TurboCodingRelease / M_num_reg (log_map.cpp:349,1330,28) so
 // that a build which still links the reference's log_map.cpp for the ENCODER side keeps those, and a
 // build which drops log_map.cpp entirely still links.  See INTEGRATION.md for both recipes.
@@ -121,4 +123,27 @@ void Log_MAP_decoder(double *recs_turbo, double *La_turbo, int terminated, doubl
     }
     int s = tdb200_siso_batch(g.siso, recs_turbo, La_turbo, terminated, LLR_all_turbo, TDB200_MEM_HOST, 1, nullptr);
     if (s != TDB200_OK) die("tdb200_siso_batch", s);
+}
+
+// The two stages the reference declares (ITTC/main.h:23-24) and calls from comments only
+// (ITTC/main.cpp:196,204): with these definitions a maintainer can un-comment both call sites.
+// TS 36.212 circular-buffer rate matching on the reference's multiplex order; redundancy version from
+// TDB200_COMPAT_RV (default 0).  `in_len` / `out_len` are 3K+12 on the turbo-code side.
+void rate_match(int *input, int in_len, int *output, int out_len)
+{
+    const int K = (in_len - 12) / 3;
+    ensure_decoder(K);
+    std::vector<uint8_t> c(in_len), e(out_len > 0 ? out_len : 1);
+    for (int i = 0; i < in_len; i++) c[i] = (uint8_t)(input[i] & 1);
+    int s = tdb200_rate_match_batch(g.dec, c.data(), e.data(), TDB200_MEM_HOST, 1, out_len, env_int("TDB200_COMPAT_RV", 0), 0, nullptr);
+    if (s != TDB200_OK) die("tdb200_rate_match_batch", s);
+    for (int i = 0; i < out_len; i++) output[i] = e[i];
+}
+
+void de_rate_match(double *input, double *output, int in_len, int out_len)
+{
+    const int K = (out_len - 12) / 3;
+    ensure_decoder(K);
+    int s = tdb200_rate_dematch_batch(g.dec, input, output, TDB200_LLR_F64, TDB200_MEM_HOST, 1, in_len, env_int("TDB200_COMPAT_RV", 0), 0, 0, nullptr);
+    if (s != TDB200_OK) die("tdb200_rate_dematch_batch", s);
 }

@@ -16,7 +16,8 @@
 // of the received row in shared memory with coalesced loads and gathers from there, so HBM sees each
 // byte once and every global store is coalesced.  Repeated bits (E > nnn) are combined in
 // transmission order; punctured ones come out as 0 (no information); `accumulate` adds to what the
-// output already holds (HARQ combining of retransmissions with other rv).  Accumulation is fp32
+// output already holds (HARQ combining of retransmissions with other rv): new = old + (this
+// transmission's sum).  Accumulation is fp32
 // (fp64 for double input, saturating integers for 8-bit input).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -101,50 +102,92 @@ __device__ __forceinline__ void store_as(void *p, size_t i, A acc, float scale, 
     else static_cast<int8_t *>(p)[i] = (int8_t)quant8((float)acc, scale, clip);
 }
 
+// One CTA per codeblock: the coded row is staged in shared memory (coalesced 16-byte loads when the
+// row is aligned), the transmitted bits are gathered from there and leave four per store.
 __global__ void __launch_bounds__(256) rate_match_kernel(const uint8_t *__restrict__ coded, uint8_t *__restrict__ e_bits, const int *__restrict__ perm,
                                                          int nnn, int NL, int E)
 {
-    const int cb = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= E) return;
-    e_bits[(size_t)cb * E + k] = coded[(size_t)cb * NL + __ldg(perm + k % nnn)];
+    extern __shared__ __align__(16) unsigned char rm_smem[];
+    const size_t cb = blockIdx.x;
+    const uint8_t *row = coded + cb * (size_t)NL;
+    if ((reinterpret_cast<size_t>(row) & 3) == 0) {  // NL is a multiple of 4
+        const unsigned *src = reinterpret_cast<const unsigned *>(row);
+        unsigned *dst = reinterpret_cast<unsigned *>(rm_smem);
+#pragma unroll 8
+        for (int i = threadIdx.x; i < NL / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    } else {
+        for (int i = threadIdx.x; i < NL; i += blockDim.x) rm_smem[i] = row[i];
+    }
+    __syncthreads();
+    uint8_t *out = e_bits + cb * (size_t)E;
+    if ((reinterpret_cast<size_t>(out) & 3) == 0) {
+#pragma unroll 4
+        for (int k4 = threadIdx.x; k4 < E / 4; k4 += blockDim.x) {
+            unsigned v = 0;
+            int j = (4 * k4) % nnn;  // one division per four bits; the wrap is a compare
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                v |= (unsigned)rm_smem[__ldg(perm + j)] << (8 * b);
+                j = (j + 1 == nnn) ? 0 : j + 1;
+            }
+            reinterpret_cast<unsigned *>(out)[k4] = v;
+        }
+        for (int k = (E & ~3) + threadIdx.x; k < E; k += blockDim.x) out[k] = rm_smem[__ldg(perm + k % nnn)];
+    } else {
+        for (int k = threadIdx.x; k < E; k += blockDim.x) out[k] = rm_smem[__ldg(perm + k % nnn)];
+    }
 }
 
-constexpr int kRmThreads = 1024, kRmMaxPerThread = 25;  // 1024 * 25 >= 3 * 8192 + 12
+constexpr int kRmThreads = 512;
 
+// One CTA per codeblock.  `tile[j]` collects the soft value of transmitted position j: the first wrap
+// of the circular buffer is loaded, later wraps (repetition) are added in place -- transmission order,
+// coalesced loads.  Then every multiplex position n gathers tile[inv[n]] (0 if never sent), four
+// consecutive n per thread so that the stores are 4 to 32 bytes wide.
 template <int IN_T, int OUT_T>
 __global__ void __launch_bounds__(kRmThreads) rate_dematch_kernel(const void *__restrict__ e_llr, void *llr, const int *__restrict__ inv, int nnn, int NL,
                                                                   int E, int accumulate, float scale, int clip)
 {
     using A = typename std::conditional<IN_T == TDB200_LLR_F64, double, typename std::conditional<IN_T == TDB200_LLR_S8, int, float>::type>::type;
     extern __shared__ __align__(16) unsigned char rm_smem[];
-    A *tile = reinterpret_cast<A *>(rm_smem);  // one wrap of the circular buffer: up to nnn received values
+    A *tile = reinterpret_cast<A *>(rm_smem);
     const size_t cb = blockIdx.x;
     const size_t in0 = cb * (size_t)E, out0 = cb * (size_t)NL;
-    A acc[kRmMaxPerThread];  // sums of positions n = tid + i * 1024, kept in registers across wraps
-#pragma unroll
-    for (int i = 0; i < kRmMaxPerThread; i++) {
-        const int n = threadIdx.x + i * kRmThreads;
-        acc[i] = (accumulate && n < NL) ? load_as<A, OUT_T>(llr, out0 + n) : (A)0;
+    const int len = min(nnn, E);
+    // both phases are latency-bound streams: keep eight (four) independent loads in flight per thread
+#pragma unroll 8
+    for (int k = threadIdx.x; k < len; k += kRmThreads) tile[k] = load_as<A, IN_T>(e_llr, in0 + k);
+    for (int w0 = nnn; w0 < E; w0 += nnn) {  // repetition: position k stays with the thread that loaded it
+        const int wl = min(nnn, E - w0);
+#pragma unroll 8
+        for (int k = threadIdx.x; k < wl; k += kRmThreads) tile[k] += load_as<A, IN_T>(e_llr, in0 + w0 + k);
     }
-    for (int w0 = 0; w0 < E; w0 += nnn) {
-        const int len = min(nnn, E - w0);
-        for (int k = threadIdx.x; k < len; k += kRmThreads) tile[k] = load_as<A, IN_T>(e_llr, in0 + w0 + k);
-        __syncthreads();
+    __syncthreads();
+#pragma unroll 4
+    for (int n4 = threadIdx.x; n4 < NL / 4; n4 += kRmThreads) {  // NL is a multiple of 4
+        const int4 j4 = __ldg(reinterpret_cast<const int4 *>(inv) + n4);
+        const int js[4] = {j4.x, j4.y, j4.z, j4.w};
+        A v[4];
 #pragma unroll
-        for (int i = 0; i < kRmMaxPerThread; i++) {
-            const int n = threadIdx.x + i * kRmThreads;
-            if (n < NL) {
-                const int j = __ldg(inv + n);
-                if (j >= 0 && j < len) acc[i] += tile[j];
-            }
+        for (int b = 0; b < 4; b++) {
+            v[b] = (js[b] >= 0 && js[b] < len) ? tile[js[b]] : (A)0;
+            if (accumulate) v[b] = load_as<A, OUT_T>(llr, out0 + 4 * n4 + b) + v[b];
         }
-        __syncthreads();
-    }
+        if constexpr (OUT_T == TDB200_LLR_S8) {
+            unsigned w = 0;
 #pragma unroll
-    for (int i = 0; i < kRmMaxPerThread; i++) {
-        const int n = threadIdx.x + i * kRmThreads;
-        if (n < NL) store_as<IN_T, OUT_T, A>(llr, out0 + n, acc[i], scale, clip);
+            for (int b = 0; b < 4; b++) {
+                int q;
+                if constexpr (IN_T == TDB200_LLR_S8) q = max(min((int)v[b], 127), -127);
+                else if constexpr (IN_T == TDB200_LLR_F16) q = quant8(__half2float(__float2half_rn((float)v[b])), scale, clip);
+                else q = quant8((float)v[b], scale, clip);
+                w |= ((unsigned)q & 0xffu) << (8 * b);
+            }
+            reinterpret_cast<unsigned *>(static_cast<int8_t *>(llr) + out0)[n4] = w;
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; b++) store_as<IN_T, OUT_T, A>(llr, out0 + 4 * n4 + b, v[b], scale, clip);
+        }
     }
 }
 
@@ -170,17 +213,14 @@ cudaError_t dematch_launch(const RmArgs &a, cudaStream_t st)
 cudaError_t launch_rate_match(const uint8_t *coded, uint8_t *e_bits, const int *perm, int nnn, int NL, int E, int n_cb, cudaStream_t st)
 {
     if (n_cb == 0 || E == 0) return cudaSuccess;
-    for (int c0 = 0; c0 < n_cb; c0 += 65535) {  // grid.y limit
-        const int n = std::min(65535, n_cb - c0);
-        rate_match_kernel<<<dim3((E + 255) / 256, n), 256, 0, st>>>(coded + (size_t)c0 * NL, e_bits + (size_t)c0 * E, perm, nnn, NL, E);
-    }
+    rate_match_kernel<<<n_cb, 256, (NL + 15) & ~15, st>>>(coded, e_bits, perm, nnn, NL, E);
     return cudaGetLastError();
 }
 
 cudaError_t launch_rate_dematch(const RmArgs &a, cudaStream_t st)
 {
     if (a.n_cb == 0) return cudaSuccess;
-    if (a.NL > kRmThreads * kRmMaxPerThread) return cudaErrorInvalidValue;
+    if (a.NL % 4) return cudaErrorInvalidValue;
     const int in = a.in_type, out = a.out_type;
     if (in == out) {
         switch (in) {
