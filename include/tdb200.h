@@ -221,6 +221,27 @@ int tdb200_rate_dematch_batch(tdb200_decoder *dec, const void *e_llr, void *llr,
 int tdb200_decode_rm_batch(tdb200_decoder *dec, const void *e_llr, int llr_type, int mem, int n_cb,
                            int E, int rv, int ncb, const tdb200_outputs *out, void *stream);
 
+/* ---- transport-block stage above the decoder (TS 36.212 5.1.1 / 5.1.2) ----------------------------
+ * The reference has a placeholder only (previous/Decoder.cc:1026 "stoprule ... 1=CRC", :1098-1099).
+ * `which`: TDB200_CRC24A (transport block, g = 0x1864CFB) or TDB200_CRC24B (code block, g = 0x1800063).
+ * bits are [n_rows][row_bits], one byte per bit (the decoder's own output format); row_bits = 0 means
+ * the handle's K (code blocks), any other length >= 25 serves transport blocks. */
+typedef enum tdb200_crc { TDB200_CRC24A = 0, TDB200_CRC24B = 1 } tdb200_crc;
+
+/* Overwrites the last 24 bits of every row with the CRC of the bits before them. */
+int tdb200_crc24_attach_batch(tdb200_decoder *dec, uint8_t *bits, int row_bits, int which, int mem, int n_rows, void *stream);
+
+/* ok[c] = 1 if row c divides by the generator (payload + CRC intact); remainder (may be NULL) gets the
+ * 24-bit remainder.  Runs on decoded blocks without leaving the device: the ACK/NACK of a code block. */
+int tdb200_crc24_check_batch(tdb200_decoder *dec, const uint8_t *bits, int row_bits, int which, uint8_t *ok,
+                             int32_t *remainder, int mem, int n_rows, void *stream);
+
+/* Code-block segmentation of a transport block of B bits (its CRC24A included), 5.1.2: C blocks,
+ * C_plus of size K_plus and C_minus of size K_minus, F filler bits at the head of the first block,
+ * L = 24 CRC24B bits per block when C > 1.  Host-only arithmetic (no device needed). */
+typedef struct tdb200_seg_info { int C, K_plus, K_minus, C_plus, C_minus, F, L; } tdb200_seg_info;
+int tdb200_segmentation(int B, tdb200_seg_info *info);
+
 /* Introspection (what the plan resolved to). */
 typedef struct tdb200_plan_info {
     int K, f1, f2, n_iter, algo;

@@ -142,6 +142,13 @@ int tdo_rate_match(const int *coded, int K, int E, int rv, int Ncb, int *e_bits)
 int tdo_rate_dematch(const double *e_llr, int K, int E, int rv, int Ncb, int accumulate, double *llr);
 int tdo_rate_dematch_f32(const float *e_llr, int K, int E, int rv, int Ncb, int accumulate, float *llr);
 
+/* ------------------------------------------------------------------------
+ * LTE CRC24A / CRC24B and code-block segmentation (turbo_oracle_crc.c; TS 36.212 5.1.1, 5.1.2). */
+#define TDO_CRC24A_POLY 0x864CFBu
+#define TDO_CRC24B_POLY 0x800063u
+unsigned tdo_crc24(const unsigned char *bits, int n, unsigned poly);
+int tdo_segmentation(int B, int *out /*C, K_plus, K_minus, C_plus, C_minus, F, L*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,9 @@ class Oracle:
         L.tdo_rate_match.argtypes = [_ip, C.c_int, C.c_int, C.c_int, C.c_int, _ip]
         L.tdo_rate_dematch.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
         L.tdo_rate_dematch_f32.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]
+        L.tdo_crc24.argtypes = [np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"), C.c_int, C.c_uint]
+        L.tdo_crc24.restype = C.c_uint
+        L.tdo_segmentation.argtypes = [C.c_int, _ip]
         L.tdo_modulate.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp]
         L.tdo_demap_f64.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_double, _dp]
         L.tdo_demap_f32.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_float, _fp]
@@ -127,6 +130,19 @@ class Oracle:
         if fn(e if e.size else np.zeros(1, dt), K, e.size, rv, Ncb, 0 if into is None else 1, llr):
             raise ValueError("rate matching: empty circular buffer")
         return llr
+
+    # ---- CRC24 / segmentation (turbo_oracle_crc.c)
+    CRC24A, CRC24B = 0x864CFB, 0x800063
+
+    def crc24(self, bits, poly):
+        bits = np.ascontiguousarray(bits, np.uint8).ravel()
+        return int(self.lib.tdo_crc24(bits if bits.size else np.zeros(1, np.uint8), bits.size, poly))
+
+    def segmentation(self, B):
+        out = np.zeros(7, np.int32)
+        if self.lib.tdo_segmentation(B, out):
+            raise ValueError("segmentation: B=%d" % B)
+        return dict(zip(("C", "K_plus", "K_minus", "C_plus", "C_minus", "F", "L"), map(int, out)))
 
     # ---- mapper / soft demapper (turbo_oracle_mod.c)
     def modulate(self, bits, M):

@@ -212,3 +212,25 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["ber"] == 0.0   # two codeblocks at 1.0 dB decode cleanly
+
+
+def test_segmentation_known_cases_and_abi(oracle, lib):
+    import ctypes as C
+    assert oracle.segmentation(6144) == dict(C=1, K_plus=6144, K_minus=0, C_plus=1, C_minus=0, F=0, L=0)
+    # the largest LTE transport block (75376 bits + CRC24A): 13 blocks of 5824
+    assert oracle.segmentation(75376 + 24) == dict(C=13, K_plus=5824, K_minus=5760, C_plus=13, C_minus=0, F=0, L=24)
+    assert oracle.segmentation(6145) == dict(C=2, K_plus=3136, K_minus=3072, C_plus=1, C_minus=1, F=15, L=24)
+
+    class Seg(C.Structure):
+        _fields_ = [(n, C.c_int) for n in ("C", "K_plus", "K_minus", "C_plus", "C_minus", "F", "L")]
+    lib.tdb200_segmentation.argtypes = [C.c_int, C.POINTER(Seg)]
+    sizes = oracle.lte_sizes()
+    for B in list(range(25, 400)) + list(range(6000, 6400)) + [12000, 12257, 30000, 61664, 75400, 100000, 150000]:
+        s = Seg()
+        assert lib.tdb200_segmentation(B, C.byref(s)) == 0      # host arithmetic: no device needed
+        got = {n: getattr(s, n) for n, _ in Seg._fields_}
+        assert got == oracle.segmentation(B), B
+        Bp = B + got["C"] * got["L"]
+        assert got["C_plus"] * got["K_plus"] + got["C_minus"] * got["K_minus"] == Bp + got["F"]
+        assert got["K_plus"] in sizes and (got["C_minus"] == 0 or got["K_minus"] in sizes) and 0 <= got["F"] < 64 * got["C"]
+    assert lib.tdb200_segmentation(0, C.byref(Seg())) != 0

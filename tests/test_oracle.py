@@ -252,3 +252,19 @@ def test_rate_matched_block_decodes(oracle):
     llr = oracle.rate_dematch(2 * r / sigma ** 2, K, rv)
     out = oracle.decode(llr, pi, 8)
     assert np.array_equal(out[-1], bits)
+
+
+# ---- CRC24A / CRC24B and code-block segmentation: oracle/turbo_oracle_crc.c
+def test_crc24_catalogue_check_values(oracle):
+    msg = np.unpackbits(np.frombuffer(b"123456789", np.uint8))
+    assert oracle.crc24(msg, oracle.CRC24A) == 0xCDE703      # CRC-24/LTE-A
+    assert oracle.crc24(msg, oracle.CRC24B) == 0x23EF52      # CRC-24/LTE-B
+    rng = np.random.default_rng(0)
+    for poly in (oracle.CRC24A, oracle.CRC24B):
+        a = rng.integers(0, 2, 1000).astype(np.uint8)
+        c = oracle.crc24(a, poly)
+        full = np.concatenate([a, [(c >> (23 - i)) & 1 for i in range(24)]]).astype(np.uint8)
+        assert oracle.crc24(full, poly) == 0, "payload || CRC divides by the generator"
+        full[17] ^= 1
+        assert oracle.crc24(full, poly) != 0
+        assert oracle.crc24(np.concatenate([np.zeros(77, np.uint8), a]), poly) == c, "leading zeros (filler bits) are free"

@@ -37,6 +37,7 @@ KERNEL_TUS = [
     ("tdb200_encode.cu", []),
     ("tdb200_modem.cu", ["-fmad=false"]),
     ("tdb200_ratematch.cu", ["-fmad=false"]),
+    ("tdb200_crc.cu", []),
 ]
 
 

@@ -857,6 +857,76 @@ int tdb200_rate_dematch_batch(tdb200_decoder *d, const void *e_llr, void *llr, i
     return TDB200_OK;
 }
 
+static int crc_common(tdb200_decoder *d, uint8_t *bits, int row_bits, int which, int attach, uint8_t *ok, int32_t *rem, int mem, int n_cb, void *stream)
+{
+    if (!d || !bits) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (n_cb < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d mem=%d", n_cb, mem);
+    if (which != TDB200_CRC24A && which != TDB200_CRC24B) return fail(TDB200_ERR_INVALID_ARG, "which=%d (TDB200_CRC24A or TDB200_CRC24B)", which);
+    const int K = row_bits ? row_bits : d->cfg.K;
+    if (K <= 24 || K > (1 << 24)) return fail(TDB200_ERR_INVALID_ARG, "row_bits=%d: need 24 < row_bits <= 2^24", K);
+    if (n_cb == 0) return TDB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    CrcArgs a{};
+    a.K = K; a.n_cb = n_cb; a.poly = (which == TDB200_CRC24A) ? 0x864CFBu : 0x800063u; a.attach = attach;
+    if (mem == TDB200_MEM_DEVICE) {
+        a.bits = bits; a.ok = ok; a.remainder = rem;
+        TDB_CUDA(launch_crc24(a, st));
+        return TDB200_OK;
+    }
+    HostStage hs;
+    uint8_t *db = static_cast<uint8_t *>(hs.alloc((size_t)n_cb * K));
+    uint8_t *dk = ok ? static_cast<uint8_t *>(hs.alloc(n_cb)) : nullptr;
+    int32_t *dr = rem ? static_cast<int32_t *>(hs.alloc(sizeof(int32_t) * (size_t)n_cb)) : nullptr;
+    if (!db || (ok && !dk) || (rem && !dr)) return fail(TDB200_ERR_ALLOC, "device allocation failed");
+    TDB_CUDA(cudaMemcpyAsync(db, bits, (size_t)n_cb * K, cudaMemcpyHostToDevice, st));
+    a.bits = db; a.ok = dk; a.remainder = dr;
+    TDB_CUDA(launch_crc24(a, st));
+    if (attach) TDB_CUDA(cudaMemcpyAsync(bits, db, (size_t)n_cb * K, cudaMemcpyDeviceToHost, st));
+    if (ok) TDB_CUDA(cudaMemcpyAsync(ok, dk, n_cb, cudaMemcpyDeviceToHost, st));
+    if (rem) TDB_CUDA(cudaMemcpyAsync(rem, dr, sizeof(int32_t) * (size_t)n_cb, cudaMemcpyDeviceToHost, st));
+    TDB_CUDA(cudaStreamSynchronize(st));
+    return TDB200_OK;
+}
+
+int tdb200_crc24_attach_batch(tdb200_decoder *d, uint8_t *bits, int row_bits, int which, int mem, int n_rows, void *stream)
+{
+    return crc_common(d, bits, row_bits, which, 1, nullptr, nullptr, mem, n_rows, stream);
+}
+
+int tdb200_crc24_check_batch(tdb200_decoder *d, const uint8_t *bits, int row_bits, int which, uint8_t *ok, int32_t *remainder, int mem,
+                             int n_rows, void *stream)
+{
+    if (!ok && !remainder) return fail(TDB200_ERR_INVALID_ARG, "ok and remainder are both NULL");
+    return crc_common(d, const_cast<uint8_t *>(bits), row_bits, which, 0, ok, remainder, mem, n_rows, stream);
+}
+
+int tdb200_segmentation(int B, tdb200_seg_info *info)
+{
+    if (!info) return fail(TDB200_ERR_INVALID_ARG, "info is NULL");
+    if (B <= 0) return fail(TDB200_ERR_INVALID_ARG, "B=%d", B);
+    const int Z = 6144;
+    int L = 0, C = 1;
+    long Bp = B;
+    if (B > Z) { L = 24; C = (B + (Z - L) - 1) / (Z - L); Bp = (long)B + (long)C * L; }
+    // K_plus: the smallest block size with C * K >= B'; K_minus: the next smaller one
+    int Kp = 0, Km = 0;
+    for (auto &r : kLte) {
+        if ((long)C * r[0] >= Bp) { Kp = r[0]; break; }
+        Km = r[0];
+    }
+    if (!Kp) return fail(TDB200_ERR_INVALID_ARG, "B=%d does not fit %d code blocks", B, C);
+    info->C = C; info->K_plus = Kp; info->L = L;
+    if (C == 1) { info->K_minus = 0; info->C_plus = 1; info->C_minus = 0; }
+    else {
+        info->K_minus = Km;
+        info->C_minus = (int)(((long)C * Kp - Bp) / (Kp - Km));
+        info->C_plus = C - info->C_minus;
+    }
+    info->F = (int)((long)info->C_plus * Kp + (long)info->C_minus * info->K_minus - Bp);
+    return TDB200_OK;
+}
+
 int tdb200_encode_batch(tdb200_decoder *d, const uint8_t *bits, uint8_t *coded, int mem, int n_cb, void *stream)
 {
     if (!d || !bits || !coded) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");

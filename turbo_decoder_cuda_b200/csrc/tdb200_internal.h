@@ -193,4 +193,17 @@ bool build_rm_table(int K, int rv, int Ncb, std::vector<int> &perm, std::vector<
 cudaError_t launch_rate_match(const uint8_t *coded, uint8_t *e_bits, const int *perm, int nnn, int NL, int E, int n_cb, cudaStream_t st);
 cudaError_t launch_rate_dematch(const RmArgs &a, cudaStream_t st);
 
+// ------------------------------------------------------------------ transport-block side: CRC24A / CRC24B (tdb200_crc.cu)
+struct CrcArgs {
+    uint8_t *bits;       // [n_cb][K] device, one byte per bit (attach: the last 24 are written)
+    int K, n_cb;
+    unsigned poly;       // low 24 bits of the generator
+    int attach;          // 1: write the parity of the first K-24 bits; 0: divide all K bits
+    uint8_t *ok;         // [n_cb] check: remainder == 0 (may be NULL)
+    int32_t *remainder;  // [n_cb] check: the remainder (may be NULL)
+    int chunk;           // filled in by launch_crc24
+    unsigned xpow[5];
+};
+cudaError_t launch_crc24(const CrcArgs &a, cudaStream_t st);
+
 }  // namespace tdb200

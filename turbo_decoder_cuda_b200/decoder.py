@@ -45,6 +45,10 @@ class Outputs(C.Structure):
                 ("llr_siso1", C.c_void_p), ("llr_siso2", C.c_void_p), ("ext_siso2", C.c_void_p)]
 
 
+class SegInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("C", "K_plus", "K_minus", "C_plus", "C_minus", "F", "L")]
+
+
 class PlanInfo(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "K", "f1", "f2", "n_iter", "algo", "sub_block", "n_sub_blocks", "warmup", "cb_per_cta",
@@ -93,6 +97,9 @@ def load_library():
                                             C.c_int, C.c_void_p]
     L.tdb200_decode_rm_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(Outputs), C.c_void_p]
+    L.tdb200_crc24_attach_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.tdb200_crc24_check_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.tdb200_segmentation.argtypes = [C.c_int, C.POINTER(SegInfo)]
     _lib = L
     return L
 
@@ -100,6 +107,17 @@ def load_library():
 def _check(status):
     if status != 0:
         raise TdbError(status, load_library().tdb200_last_error().decode())
+
+
+CRC24A, CRC24B = 0, 1
+
+
+def segmentation(B):
+    """tdb200_segmentation: code-block segmentation of a transport block of B bits (CRC24A included),
+    TS 36.212 5.1.2 -> dict(C, K_plus, K_minus, C_plus, C_minus, F, L).  Host arithmetic only."""
+    info = SegInfo()
+    _check(load_library().tdb200_segmentation(int(B), C.byref(info)))
+    return {n: getattr(info, n) for n, _ in SegInfo._fields_}
 
 
 def lte_qpp_params(K):
@@ -325,6 +343,25 @@ class TurboDecoder:
         ep, mem = _ptr_of(e_llr)
         _check(self._L.tdb200_decode_rm_batch(self._h, ep, _LLR_TYPES[tname], mem, n_cb, E, int(rv), int(ncb), C.byref(o), stream))
         return outs
+
+    # ---- transport-block stage: CRC24A / CRC24B (TS 36.212 5.1.1)
+    def crc24_attach(self, bits, which=CRC24B, stream=0):
+        """tdb200_crc24_attach_batch: overwrite the last 24 bits of every row of bits [n_rows, n] with the
+        CRC of the rest (in place); rows are code blocks (n = K) or transport blocks (any n > 24)."""
+        assert str(bits.dtype).endswith("uint8")
+        bp, mem = _ptr_of(bits)
+        _check(self._L.tdb200_crc24_attach_batch(self._h, bp, int(bits.shape[1]), int(which), mem, int(bits.shape[0]), stream))
+        return bits
+
+    def crc24_check(self, bits, which=CRC24B, want_remainder=False, stream=0):
+        """tdb200_crc24_check_batch: ok [n_rows] uint8 (and the 24-bit remainders) of bits [n_rows, n]."""
+        n_cb = int(bits.shape[0])
+        assert str(bits.dtype).endswith("uint8")
+        ok = self._like(bits, (n_cb,), "uint8")
+        rem = self._like(bits, (n_cb,), "int32") if want_remainder else None
+        bp, mem = _ptr_of(bits)
+        _check(self._L.tdb200_crc24_check_batch(self._h, bp, int(bits.shape[1]), int(which), _ptr_of(ok)[0], _ptr_of(rem)[0], mem, n_cb, stream))
+        return (ok, rem) if want_remainder else ok
 
     def siso(self, recs, La, terminated=1, stream=0):
         """One BCJR pass (tdb200_siso_batch), the Log_MAP_decoder replacement; doubles only."""
