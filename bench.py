@@ -276,6 +276,21 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_e2e16 = 1e3 * (time.perf_counter() - t16) / n16
 
+    # ---- informational: 8-bit fixed-point LLRs (the decoder's own channel format: a quarter of the bytes)
+    h8 = torch.empty(llr.shape, dtype=torch.int8, pin_memory=True)
+    h8.copy_(torch.clamp(torch.round(llr * 8.0), -127, 127).to(torch.int8))
+
+    def step_host8():
+        dec.decode_raw(h8.data_ptr(), tdb.LLR_S8, tdb.MEM_HOST, batch, bits=h_bits.data_ptr(), stream=sp)
+    step_host8()
+    torch.cuda.synchronize()
+    e2e8_ok = bool((h_bits.to(dev) == out_bits).all().item())  # same quantiser: same decisions as the float path
+    t8 = time.perf_counter()
+    for _ in range(n16):
+        step_host8()
+    torch.cuda.synchronize()
+    ms_e2e8 = 1e3 * (time.perf_counter() - t8) / n16
+
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -306,7 +321,9 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": batch * (3 * K + 12) * 4,
                     "d2h_bytes_per_step": batch * K, "matches_device_path": e2e_ok,
                     "with_float16_llrs_this_rank": {"value": batch * K / (ms_e2e16 * 1e-3) / 1e9, "unit": "Gbit/s",
-                                                    "h2d_bytes_per_step": batch * (3 * K + 12) * 2}},
+                                                    "h2d_bytes_per_step": batch * (3 * K + 12) * 2},
+                    "with_int8_llrs_this_rank": {"value": batch * K / (ms_e2e8 * 1e-3) / 1e9, "unit": "Gbit/s",
+                                                 "h2d_bytes_per_step": batch * (3 * K + 12), "matches_device_path": e2e8_ok}},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak,

@@ -1,2 +1,5 @@
-python -m pytest tests/test_gpu_ratematch.py tests/test_gpu_ref64.py -x -q 2>&1 | tail -3
-python tools/time_ratematch.py --json gpurun_out/ratematch_timing.json 2>&1 | tail -6
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 30 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import sys, json
+r = json.loads(sys.stdin.read())
+print(json.dumps({'value': r['value'], 'e2e': r['e2e'], 'frac_alu': r['roofline']['alu']['frac']}))"
