@@ -153,12 +153,12 @@ __device__ __forceinline__ void axis32(float v, const double *lv, float kf, floa
     }
 }
 
+// clamp(rint(x * scale), +-clip), NaN -> 0, for clip <= 127: cvt.rni.sat.s8 rounds to nearest even, saturates to
+// [-128, 127] and maps NaN to 0 -- the decoder's quantiser (quant() in tdb200_fast_kernel.cuh) in two fewer steps
 __device__ __forceinline__ int quant8(float x, float scale, int clip)
 {
-    float s = x * scale;
-    if (!(s == s)) return 0;
-    s = fminf(fmaxf(s, -32767.0f), 32767.0f);
-    const int q = __float2int_rn(s);
+    int q;
+    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(x * scale));
     return max(min(q, clip), -clip);
 }
 

@@ -79,14 +79,19 @@ template <typename A, int T> __device__ __forceinline__ A load_as(const void *p,
     else return (A)v;
 }
 
+// clamp(rint(x * scale), +-clip), NaN -> 0, for clip <= 127: cvt.rni.sat.s8 rounds to nearest even, saturates to
+// [-128, 127] and maps NaN to 0 -- the decoder's quantiser (quant() in tdb200_fast_kernel.cuh) in two fewer steps
 __device__ __forceinline__ int quant8(float x, float scale, int clip)
 {
-    float s = x * scale;
-    if (!(s == s)) return 0;
-    s = fminf(fmaxf(s, -32767.0f), 32767.0f);
-    const int q = __float2int_rn(s);
+    int q;
+    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(x * scale));
     return max(min(q, clip), -clip);
 }
+
+// Shared-memory word index of logical word j: the sub-block interleaver sends the 32 lanes of a gather to
+// addresses that differ by multiples of R (eight-way bank conflicts on average at K = 6144); XOR-ing the
+// row number into the bank spreads them (2.2-way), and a linear fill stays conflict-free.
+__device__ __forceinline__ int swz(int j) { return j ^ ((j >> 5) & 31); }
 
 // acc (in the accumulation type of IN_T) -> element of OUT_T.  IN_T == OUT_T is the plain inverse;
 // OUT_T == S8 from a float type applies the throughput decoder's channel quantiser to exactly the
@@ -102,6 +107,8 @@ __device__ __forceinline__ void store_as(void *p, size_t i, A acc, float scale, 
     else static_cast<int8_t *>(p)[i] = (int8_t)quant8((float)acc, scale, clip);
 }
 
+__device__ __forceinline__ unsigned char coded_at(const unsigned char *sm, int n) { return sm[4 * swz(n >> 2) + (n & 3)]; }
+
 // One CTA per codeblock: the coded row is staged in shared memory (coalesced 16-byte loads when the
 // row is aligned), the transmitted bits are gathered from there and leave four per store.
 __global__ void __launch_bounds__(256) rate_match_kernel(const uint8_t *__restrict__ coded, uint8_t *__restrict__ e_bits, const int *__restrict__ perm,
@@ -110,13 +117,13 @@ __global__ void __launch_bounds__(256) rate_match_kernel(const uint8_t *__restri
     extern __shared__ __align__(16) unsigned char rm_smem[];
     const size_t cb = blockIdx.x;
     const uint8_t *row = coded + cb * (size_t)NL;
+    unsigned *stage = reinterpret_cast<unsigned *>(rm_smem);  // words swizzled like the soft inverse's tile
     if ((reinterpret_cast<size_t>(row) & 3) == 0) {  // NL is a multiple of 4
         const unsigned *src = reinterpret_cast<const unsigned *>(row);
-        unsigned *dst = reinterpret_cast<unsigned *>(rm_smem);
 #pragma unroll 8
-        for (int i = threadIdx.x; i < NL / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < NL / 4; i += blockDim.x) stage[swz(i)] = __ldg(src + i);
     } else {
-        for (int i = threadIdx.x; i < NL; i += blockDim.x) rm_smem[i] = row[i];
+        for (int i = threadIdx.x; i < NL; i += blockDim.x) rm_smem[4 * swz(i >> 2) + (i & 3)] = row[i];
     }
     __syncthreads();
     uint8_t *out = e_bits + cb * (size_t)E;
@@ -127,14 +134,14 @@ __global__ void __launch_bounds__(256) rate_match_kernel(const uint8_t *__restri
             int j = (4 * k4) % nnn;  // one division per four bits; the wrap is a compare
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-                v |= (unsigned)rm_smem[__ldg(perm + j)] << (8 * b);
+                v |= (unsigned)coded_at(rm_smem, __ldg(perm + j)) << (8 * b);
                 j = (j + 1 == nnn) ? 0 : j + 1;
             }
             reinterpret_cast<unsigned *>(out)[k4] = v;
         }
-        for (int k = (E & ~3) + threadIdx.x; k < E; k += blockDim.x) out[k] = rm_smem[__ldg(perm + k % nnn)];
+        for (int k = (E & ~3) + threadIdx.x; k < E; k += blockDim.x) out[k] = coded_at(rm_smem, __ldg(perm + k % nnn));
     } else {
-        for (int k = threadIdx.x; k < E; k += blockDim.x) out[k] = rm_smem[__ldg(perm + k % nnn)];
+        for (int k = threadIdx.x; k < E; k += blockDim.x) out[k] = coded_at(rm_smem, __ldg(perm + k % nnn));
     }
 }
 
@@ -156,11 +163,11 @@ __global__ void __launch_bounds__(kRmThreads) rate_dematch_kernel(const void *__
     const int len = min(nnn, E);
     // both phases are latency-bound streams: keep eight (four) independent loads in flight per thread
 #pragma unroll 8
-    for (int k = threadIdx.x; k < len; k += kRmThreads) tile[k] = load_as<A, IN_T>(e_llr, in0 + k);
+    for (int k = threadIdx.x; k < len; k += kRmThreads) tile[swz(k)] = load_as<A, IN_T>(e_llr, in0 + k);
     for (int w0 = nnn; w0 < E; w0 += nnn) {  // repetition: position k stays with the thread that loaded it
         const int wl = min(nnn, E - w0);
 #pragma unroll 8
-        for (int k = threadIdx.x; k < wl; k += kRmThreads) tile[k] += load_as<A, IN_T>(e_llr, in0 + w0 + k);
+        for (int k = threadIdx.x; k < wl; k += kRmThreads) tile[swz(k)] += load_as<A, IN_T>(e_llr, in0 + w0 + k);
     }
     __syncthreads();
 #pragma unroll 4
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(kRmThreads) rate_dematch_kernel(const void *__
         A v[4];
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            v[b] = (js[b] >= 0 && js[b] < len) ? tile[js[b]] : (A)0;
+            v[b] = (js[b] >= 0 && js[b] < len) ? tile[swz(js[b])] : (A)0;
             if (accumulate) v[b] = load_as<A, OUT_T>(llr, out0 + 4 * n4 + b) + v[b];
         }
         if constexpr (OUT_T == TDB200_LLR_S8) {
@@ -195,7 +202,7 @@ template <int IN_T, int OUT_T>
 cudaError_t dematch_launch(const RmArgs &a, cudaStream_t st)
 {
     using A = typename std::conditional<IN_T == TDB200_LLR_F64, double, typename std::conditional<IN_T == TDB200_LLR_S8, int, float>::type>::type;
-    const size_t smem = sizeof(A) * (size_t)std::min(a.nnn, std::max(a.E, 1));
+    const size_t smem = sizeof(A) * (size_t)((std::min(a.nnn, std::max(a.E, 1)) + 31) & ~31);  // swz() permutes within rows of 32 words
     // the attribute belongs to the kernel, not to a call: always opt in to the device maximum
     int dev = 0, optin = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -213,7 +220,7 @@ cudaError_t dematch_launch(const RmArgs &a, cudaStream_t st)
 cudaError_t launch_rate_match(const uint8_t *coded, uint8_t *e_bits, const int *perm, int nnn, int NL, int E, int n_cb, cudaStream_t st)
 {
     if (n_cb == 0 || E == 0) return cudaSuccess;
-    rate_match_kernel<<<n_cb, 256, (NL + 15) & ~15, st>>>(coded, e_bits, perm, nnn, NL, E);
+    rate_match_kernel<<<n_cb, 256, (NL + 127) & ~127, st>>>(coded, e_bits, perm, nnn, NL, E);
     return cudaGetLastError();
 }
 
