@@ -187,6 +187,14 @@ int tdb200_awgn_batch(tdb200_decoder *dec, const void *x, void *y, int type, int
 int tdb200_demap_batch(tdb200_decoder *dec, const void *sym_i, const void *sym_q, int sym_type,
                        void *llr, int llr_type, int mem, int n_cb, int modulation, double kf, void *stream);
 
+/* The same two stages on flat arrays of any length (n_bits / n_llr a multiple of `modulation`), for
+ * rows that are not 3K+12 long -- rate-matched blocks: tdb200_rate_match_batch -> tdb200_modulate_flat
+ * on the way out, tdb200_demap_flat -> tdb200_decode_rm_batch on the way in. */
+int tdb200_modulate_flat(tdb200_decoder *dec, const uint8_t *bits, void *sym_i, void *sym_q, int sym_type,
+                         int mem, size_t n_bits, int modulation, void *stream);
+int tdb200_demap_flat(tdb200_decoder *dec, const void *sym_i, const void *sym_q, int sym_type,
+                      void *llr, int llr_type, int mem, size_t n_llr, int modulation, double kf, void *stream);
+
 /* demodule() + TurboDecoding() in one call (ITTC/main.cpp:202,221): received symbols in, decisions
  * out.  The demapped values stay on the device in the decoder's own input format (fp64 for
  * TDB200_ALGO_LOGMAP_F64, 8-bit fixed point for TDB200_ALGO_MAXLOG_S16, float for the fp32 modes),

@@ -169,3 +169,39 @@ def test_rate_matching_error_paths():
         dec.rate_match(coded, 100, rv=0, ncb=1)       # the first buffer entry is <NULL>: nothing to send
     assert dec.rate_match(coded, 0).shape == (1, 0)
     assert dec.decode_rm(np.zeros((0, 77), np.float32))["bits"].shape == (0, 40)
+
+
+@pytest.mark.parametrize("M,E", [(2, 12290), (4, 9164), (6, 8190), (3, 12291)])
+def test_rate_matched_and_modulated_chain(oracle, M, E):
+    """The whole transmit / receive chain around the decoder on the device: encode -> rate match ->
+    map (rows of E bits, not a multiple of 12: the flat mapper / demapper and its tail path) -> AWGN ->
+    soft demap -> decode from rate-matched LLRs."""
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_cb = 6144, 5
+    dec = TurboDecoder(K, n_iter=8, max_batch=8)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(M)
+    bits = torch.randint(0, 2, (n_cb, K), dtype=torch.uint8, device="cuda", generator=g)
+    tx = dec.rate_match(dec.encode(bits), E, 0)
+    si, sq = dec.modulate(tx, M)
+    assert tuple(si.shape) == (n_cb, E // M)
+    want_i, want_q = oracle.modulate(tx.cpu().numpy().ravel(), M)
+    assert np.array_equal(si.cpu().numpy().ravel(), want_i.astype(np.float32)) and np.array_equal(sq.cpu().numpy().ravel(), want_q.astype(np.float32))
+    ebn0 = {2: 3.0, 3: 5.5, 4: 6.5, 6: 10.0}[M]
+    sigma = 10 ** (-ebn0 / 20) * np.sqrt(0.5 / ((K / E) * M))
+    ri, rq = dec.awgn(si, sigma, seed=1), dec.awgn(sq, sigma, seed=2)
+    kf = 1.0 / (2 * sigma * sigma)
+    e_llr = dec.demap(ri, rq, M, kf)
+    want = oracle.demap_f32(ri.cpu().numpy().ravel(), rq.cpu().numpy().ravel(), M, np.float32(kf))
+    assert np.array_equal(e_llr.cpu().numpy().ravel(), want), "flat demapper incl. the tail of each call"
+    e8 = dec.demap(ri, rq, M, kf, dtype="int8")
+    assert np.array_equal(e8.cpu().numpy().ravel(), oracle.quant_s8(want))
+    # an unaligned output buffer takes the symbol-by-symbol path: same values
+    buf = torch.empty(n_cb * E + 1, dtype=torch.float32, device="cuda")
+    from turbo_decoder_cuda_b200.decoder import _check
+    _check(dec._L.tdb200_demap_flat(dec._h, ri.data_ptr(), rq.data_ptr(), 1, buf.data_ptr() + 4, 1, 1, n_cb * E, M, kf, None))
+    assert torch.equal(buf[1:], e_llr.view(-1))
+    out = dec.decode_rm(e_llr, 0)["bits"]
+    assert torch.equal(out, bits)
+    assert torch.equal(dec.decode_rm(e8, 0)["bits"], out), "8-bit hand-over: same decisions"

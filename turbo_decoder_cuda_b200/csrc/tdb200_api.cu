@@ -672,7 +672,7 @@ static int check_sym(const char *fn, const tdb200_decoder *d, int sym_type, int 
     if (sym_type != TDB200_LLR_F32 && sym_type != TDB200_LLR_F64 && sym_type != TDB200_LLR_F16)
         return fail(TDB200_ERR_INVALID_ARG, "%s: sym_type=%d (F32, F64 or F16)", fn, sym_type);
     if (!modulation_ok(modulation)) return fail(TDB200_ERR_INVALID_ARG, "%s: modulation=%d (1, 2, 3, 4 or 6 bits per symbol)", fn, modulation);
-    if (d->NL % 12) return fail(TDB200_ERR_UNSUPPORTED, "%s: 3K+12 = %d is not a multiple of 12 (K must be a multiple of 4)", fn, d->NL);
+    if (d->NL % modulation) return fail(TDB200_ERR_UNSUPPORTED, "%s: 3K+12 = %d is not a multiple of %d", fn, d->NL, modulation);
     return TDB200_OK;
 }
 
@@ -715,17 +715,18 @@ struct HostStage {
     }
 };
 
-int tdb200_modulate_batch(tdb200_decoder *d, const uint8_t *coded, void *sym_i, void *sym_q, int sym_type, int mem, int n_cb,
-                          int modulation, void *stream)
+int tdb200_modulate_flat(tdb200_decoder *d, const uint8_t *coded, void *sym_i, void *sym_q, int sym_type, int mem, size_t nb,
+                         int modulation, void *stream)
 {
     if (!d || !coded || !sym_i || !sym_q) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
-    if (n_cb < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d mem=%d", n_cb, mem);
-    int s = check_sym("tdb200_modulate_batch", d, sym_type, modulation);
+    if (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE) return fail(TDB200_ERR_INVALID_ARG, "mem=%d", mem);
+    int s = check_sym("tdb200_modulate", d, sym_type, modulation);
     if (s) return s;
-    if (n_cb == 0) return TDB200_OK;
+    if (nb % modulation) return fail(TDB200_ERR_INVALID_ARG, "%zu bits are not a whole number of %d-bit symbols", nb, modulation);
+    if (nb == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDB_CUDA(cudaSetDevice(d->cfg.device));
-    const size_t nb = (size_t)n_cb * d->NL, ns = nb / modulation, ssz = llr_elem_size(sym_type);
+    const size_t ns = nb / modulation, ssz = llr_elem_size(sym_type);
     if (mem == TDB200_MEM_DEVICE) {
         TDB_CUDA(launch_modulate(coded, sym_i, sym_q, sym_type, nb, modulation, st));
         return TDB200_OK;
@@ -740,6 +741,14 @@ int tdb200_modulate_batch(tdb200_decoder *d, const uint8_t *coded, void *sym_i, 
     TDB_CUDA(cudaMemcpyAsync(sym_q, dq, ns * ssz, cudaMemcpyDeviceToHost, st));
     TDB_CUDA(cudaStreamSynchronize(st));
     return TDB200_OK;
+}
+
+int tdb200_modulate_batch(tdb200_decoder *d, const uint8_t *coded, void *sym_i, void *sym_q, int sym_type, int mem, int n_cb,
+                          int modulation, void *stream)
+{
+    if (!d) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (n_cb < 0) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d", n_cb);
+    return tdb200_modulate_flat(d, coded, sym_i, sym_q, sym_type, mem, (size_t)n_cb * d->NL, modulation, stream);
 }
 
 int tdb200_awgn_batch(tdb200_decoder *d, const void *x, void *y, int type, int mem, size_t n, double sigma, uint64_t seed, void *stream)
@@ -766,20 +775,21 @@ int tdb200_awgn_batch(tdb200_decoder *d, const void *x, void *y, int type, int m
     return TDB200_OK;
 }
 
-int tdb200_demap_batch(tdb200_decoder *d, const void *sym_i, const void *sym_q, int sym_type, void *llr, int llr_type, int mem,
-                       int n_cb, int modulation, double kf, void *stream)
+int tdb200_demap_flat(tdb200_decoder *d, const void *sym_i, const void *sym_q, int sym_type, void *llr, int llr_type, int mem,
+                      size_t n_llr, int modulation, double kf, void *stream)
 {
     if (!d || !sym_i || !sym_q || !llr) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
-    if (n_cb < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d mem=%d", n_cb, mem);
+    if (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE) return fail(TDB200_ERR_INVALID_ARG, "mem=%d", mem);
     if (llr_type < TDB200_LLR_F64 || llr_type > TDB200_LLR_F16) return fail(TDB200_ERR_INVALID_ARG, "llr_type=%d", llr_type);
-    int s = check_sym("tdb200_demap_batch", d, sym_type, modulation);
+    int s = check_sym("tdb200_demap", d, sym_type, modulation);
     if (s) return s;
     if (!(kf > 0.0)) return fail(TDB200_ERR_INVALID_ARG, "kf must be positive");
-    if (n_cb == 0) return TDB200_OK;
+    if (n_llr % modulation) return fail(TDB200_ERR_INVALID_ARG, "%zu soft bits are not a whole number of %d-bit symbols", n_llr, modulation);
+    if (n_llr == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDB_CUDA(cudaSetDevice(d->cfg.device));
     DemapArgs a{};
-    a.sym_type = sym_type; a.llr_type = llr_type; a.n_llr = (size_t)n_cb * d->NL; a.modulation = modulation; a.kf = kf;
+    a.sym_type = sym_type; a.llr_type = llr_type; a.n_llr = n_llr; a.modulation = modulation; a.kf = kf;
     a.frac_bits = d->cfg.frac_bits ? d->cfg.frac_bits : 3;
     a.clip = std::min((1 << (a.frac_bits + 4)) - 1, 127);
     if (mem == TDB200_MEM_DEVICE) {
@@ -798,6 +808,14 @@ int tdb200_demap_batch(tdb200_decoder *d, const void *sym_i, const void *sym_q, 
     TDB_CUDA(cudaMemcpyAsync(llr, dl, lb, cudaMemcpyDeviceToHost, st));
     TDB_CUDA(cudaStreamSynchronize(st));
     return TDB200_OK;
+}
+
+int tdb200_demap_batch(tdb200_decoder *d, const void *sym_i, const void *sym_q, int sym_type, void *llr, int llr_type, int mem,
+                       int n_cb, int modulation, double kf, void *stream)
+{
+    if (!d) return fail(TDB200_ERR_INVALID_ARG, "NULL argument");
+    if (n_cb < 0) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d", n_cb);
+    return tdb200_demap_flat(d, sym_i, sym_q, sym_type, llr, llr_type, mem, (size_t)n_cb * d->NL, modulation, kf, stream);
 }
 
 int tdb200_rate_match_batch(tdb200_decoder *d, const uint8_t *coded, uint8_t *e_bits, int mem, int n_cb, int E, int rv, int ncb, void *stream)

@@ -19,6 +19,8 @@
 // (rows are contiguous, and 3K+12 is a multiple of 12 for every K that is a multiple of 8, so a group
 // of 12 LLRs never straddles a symbol or a row).  HBM-bound: a thread of demap32_kernel produces 12
 // LLRs from 12/M symbols -- 16-byte stores, all sectors of the loads used by the warp.
+#include <algorithm>
+
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <curand_kernel.h>
@@ -162,6 +164,50 @@ __device__ __forceinline__ int quant8(float x, float scale, int clip)
     return max(min(q, clip), -clip);
 }
 
+// the M soft bits of one received symbol (x, y)
+template <int M>
+__device__ __forceinline__ void demap_symbol(float x, float y, float kf, float *llr)
+{
+    if (M == 3) {
+        float d[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) d[j] = sqf(x - (float)c_psk_i[j]) + sqf(y - (float)c_psk_q[j]);
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            float m1 = 0.f, m0 = 0.f;
+            bool h1 = false, h0 = false;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (j & (1 << b)) { m1 = h1 ? fminf(m1, d[j]) : d[j]; h1 = true; }
+                else              { m0 = h0 ? fminf(m0, d[j]) : d[j]; h0 = true; }
+            }
+            llr[b] = -kf * (m1 - m0);
+        }
+    } else {
+        constexpr int nq = q_bits(M), ni = M - nq;
+        axis32<ni>(x, c_lv[lv_row(M)], kf, llr);
+        if (nq) axis32<(nq ? nq : 1)>(y, c_lv[lv_row(M)], kf, llr + ni);
+    }
+}
+
+// the last n_llr % 12 soft bits of a flat call (rows of arbitrary length): one thread per symbol
+template <int M, typename T>
+__global__ void __launch_bounds__(256) demap32_tail_kernel(const T *__restrict__ si, const T *__restrict__ sq, void *__restrict__ out, int out_type,
+                                                           size_t first_sym, size_t n_sym, float kf, float scale, int clip)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_sym) return;
+    float llr[M];
+    demap_symbol<M>(ld_f(si, first_sym + t), (M == 1) ? 0.f : ld_f(sq, first_sym + t), kf, llr);
+#pragma unroll
+    for (int b = 0; b < M; b++) {
+        const size_t o = (first_sym + t) * M + b;
+        if (out_type == TDB200_LLR_S8) static_cast<int8_t *>(out)[o] = (int8_t)quant8(llr[b], scale, clip);
+        else if (out_type == TDB200_LLR_F16) static_cast<__half *>(out)[o] = __float2half_rn(llr[b]);
+        else static_cast<float *>(out)[o] = llr[b];
+    }
+}
+
 template <int M, typename T, int OUT_T>
 __global__ void __launch_bounds__(256) demap32_kernel(const T *__restrict__ si, const T *__restrict__ sq, void *__restrict__ out, size_t n_groups,
                                                       float kf, float scale, int clip)
@@ -179,28 +225,7 @@ __global__ void __launch_bounds__(256) demap32_kernel(const T *__restrict__ si, 
         ys[k] = (M == 1 || !live) ? 0.f : ld_f(sq, gi * NS + k);
     }
 #pragma unroll
-    for (int k = 0; k < NS; k++) {
-        if (M == 3) {
-            float d[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) d[j] = sqf(xs[k] - (float)c_psk_i[j]) + sqf(ys[k] - (float)c_psk_q[j]);
-#pragma unroll
-            for (int b = 0; b < 3; b++) {
-                float m1 = 0.f, m0 = 0.f;
-                bool h1 = false, h0 = false;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (j & (1 << b)) { m1 = h1 ? fminf(m1, d[j]) : d[j]; h1 = true; }
-                    else              { m0 = h0 ? fminf(m0, d[j]) : d[j]; h0 = true; }
-                }
-                llr[3 * k + b] = -kf * (m1 - m0);
-            }
-        } else {
-            constexpr int nq = q_bits(M), ni = M - nq;
-            axis32<ni>(xs[k], c_lv[lv_row(M)], kf, llr + M * k);
-            if (nq) axis32<(nq ? nq : 1)>(ys[k], c_lv[lv_row(M)], kf, llr + M * k + ni);
-        }
-    }
+    for (int k = 0; k < NS; k++) demap_symbol<M>(xs[k], ys[k], kf, llr + M * k);
     if (OUT_T == TDB200_LLR_S8) {
         // 12 bytes per thread: staged through shared memory (word stride 3: conflict-free) so that the
         // CTA's 3072 contiguous output bytes leave as 16-byte stores
@@ -247,9 +272,19 @@ cudaError_t demap_m(const DemapArgs &a, cudaStream_t st)
         const size_t ng = a.n_llr / 12;
         const unsigned grid = (unsigned)((ng + 255) / 256);
         const float kf = (float)a.kf, scale = (float)(1 << a.frac_bits);
-        if (a.llr_type == TDB200_LLR_S8) demap32_kernel<M, T, TDB200_LLR_S8><<<grid, 256, 0, st>>>(si, sq, a.llr, ng, kf, scale, a.clip);
-        else if (a.llr_type == TDB200_LLR_F16) demap32_kernel<M, T, TDB200_LLR_F16><<<grid, 256, 0, st>>>(si, sq, a.llr, ng, kf, scale, a.clip);
-        else demap32_kernel<M, T, TDB200_LLR_F32><<<grid, 256, 0, st>>>(si, sq, a.llr, ng, kf, scale, a.clip);
+        // the 12-at-a-time kernel needs 16-byte aligned output groups; anything else goes symbol by symbol
+        const size_t osz = a.llr_type == TDB200_LLR_S8 ? 1 : (a.llr_type == TDB200_LLR_F16 ? 2 : 4);
+        const bool wide = ng > 0 && (reinterpret_cast<size_t>(a.llr) & (osz == 1 ? 3 : (osz == 2 ? 7 : 15))) == 0;
+        if (wide) {
+            if (a.llr_type == TDB200_LLR_S8) demap32_kernel<M, T, TDB200_LLR_S8><<<grid, 256, 0, st>>>(si, sq, a.llr, ng, kf, scale, a.clip);
+            else if (a.llr_type == TDB200_LLR_F16) demap32_kernel<M, T, TDB200_LLR_F16><<<grid, 256, 0, st>>>(si, sq, a.llr, ng, kf, scale, a.clip);
+            else demap32_kernel<M, T, TDB200_LLR_F32><<<grid, 256, 0, st>>>(si, sq, a.llr, ng, kf, scale, a.clip);
+        }
+        const size_t done = wide ? ng * 12 : 0;
+        if (done < a.n_llr) {  // the tail (at most 11 values), or everything for an unaligned buffer
+            const size_t n_sym = (a.n_llr - done) / M;
+            demap32_tail_kernel<M, T><<<(unsigned)((n_sym + 255) / 256), 256, 0, st>>>(si, sq, a.llr, a.llr_type, done / M, n_sym, kf, scale, a.clip);
+        }
     }
     return cudaGetLastError();
 }

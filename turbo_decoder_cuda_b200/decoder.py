@@ -92,6 +92,10 @@ def load_library():
                                      C.c_int, C.c_int, C.c_double, C.c_void_p]
     L.tdb200_decode_symbols_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_double, C.POINTER(Outputs), C.c_void_p]
+    L.tdb200_modulate_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
+                                       C.c_int, C.c_void_p]
+    L.tdb200_demap_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_size_t, C.c_int, C.c_double, C.c_void_p]
     L.tdb200_rate_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.tdb200_rate_dematch_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_void_p]
@@ -254,14 +258,14 @@ class TurboDecoder:
         return np.empty(shape, dtype=dtype)
 
     def modulate(self, coded, modulation, dtype="float32", stream=0):
-        """tdb200_modulate_batch: coded [n_cb, 3K+12] uint8 -> (I, Q), each [n_cb, (3K+12)/modulation]."""
-        n_cb = int(coded.shape[0])
-        assert int(coded.shape[1]) == self.llr_len and str(coded.dtype).endswith("uint8")
-        ns = self.llr_len // modulation
-        si, sq = self._like(coded, (n_cb, ns), dtype), self._like(coded, (n_cb, ns), dtype)
+        """tdb200_modulate_flat: bits [n_cb, n] uint8 -> (I, Q), each [n_cb, n / modulation]
+        (n = 3K+12 for whole coded blocks, E for rate-matched ones)."""
+        n_cb, n = int(coded.shape[0]), int(coded.shape[1])
+        assert n % modulation == 0 and str(coded.dtype).endswith("uint8")
+        si, sq = self._like(coded, (n_cb, n // modulation), dtype), self._like(coded, (n_cb, n // modulation), dtype)
         cp, mem = _ptr_of(coded)
-        _check(self._L.tdb200_modulate_batch(self._h, cp, _ptr_of(si)[0], _ptr_of(sq)[0], _LLR_TYPES[dtype], mem, n_cb,
-                                             int(modulation), stream))
+        _check(self._L.tdb200_modulate_flat(self._h, cp, _ptr_of(si)[0], _ptr_of(sq)[0], _LLR_TYPES[dtype], mem, n_cb * n,
+                                            int(modulation), stream))
         return si, sq
 
     def awgn(self, x, sigma, seed, stream=0):
@@ -274,15 +278,15 @@ class TurboDecoder:
         return y
 
     def demap(self, sym_i, sym_q, modulation, kf, dtype="float32", stream=0):
-        """tdb200_demap_batch: received symbols -> llr [n_cb, 3K+12] of `dtype`
+        """tdb200_demap_flat: received symbols [n_cb, ns] -> llr [n_cb, ns * modulation] of `dtype`
         (float64: the reference's demodule() bit for bit; int8: the s16 decoder's channel values)."""
-        n_cb = int(sym_i.shape[0])
-        assert int(sym_i.shape[1]) * modulation == self.llr_len and tuple(sym_i.shape) == tuple(sym_q.shape)
+        n_cb, ns = int(sym_i.shape[0]), int(sym_i.shape[1])
+        assert tuple(sym_i.shape) == tuple(sym_q.shape)
         tname = str(sym_i.dtype).replace("torch.", "")
-        llr = self._like(sym_i, (n_cb, self.llr_len), dtype)
+        llr = self._like(sym_i, (n_cb, ns * modulation), dtype)
         ip, mem = _ptr_of(sym_i)
-        _check(self._L.tdb200_demap_batch(self._h, ip, _ptr_of(sym_q)[0], _LLR_TYPES[tname], _ptr_of(llr)[0], _LLR_TYPES[dtype],
-                                          mem, n_cb, int(modulation), float(kf), stream))
+        _check(self._L.tdb200_demap_flat(self._h, ip, _ptr_of(sym_q)[0], _LLR_TYPES[tname], _ptr_of(llr)[0], _LLR_TYPES[dtype],
+                                         mem, n_cb * ns * modulation, int(modulation), float(kf), stream))
         return llr
 
     def decode_symbols_raw(self, i_ptr, q_ptr, sym_type, mem, n_cb, modulation, kf, bits=None, iters_used=None, stream=0):
