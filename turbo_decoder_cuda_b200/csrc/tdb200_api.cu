@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "tdb200_internal.h"
+#include "tdb200_plan_table.h"
 
 namespace tdb200 {
 
@@ -304,6 +305,13 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         // ---- sub-block geometry: K = P * L, L = 8 * NW, P <= 256 threads
         FastGeom &g = d->geom;
         int L = c.sub_block;
+        if (s16 && L == 0 && c.warmup == 0) {
+            // measured on a B200 for every LTE block size (tools/tune_subblock.py): which admissible L is fastest
+            // depends on how the sub-block count fills warps and how many CTAs fit an SM, not on L alone
+            for (int i = 0; i < 188; i++)
+                if (kLte[i][0] == K && kTunedL8[i]) { L = 8 * kTunedL8[i]; break; }
+            if (L && (K % L || K / L > 256)) L = 0;
+        }
         if (L == 0 && K <= 56) L = K;  // shortest blocks: one thread walks the whole trellis (shared memory admits >= 256 threads per SM only for L <= 56)
         if (L == 0) {
             static const int pref[] = {48, 40, 56, 32, 64, 24, 72, 80, 96, 16, 128, 8};

@@ -347,7 +347,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
                                          const int t, const bool active, const bool first_fixed, const bool last_fixed, w32 *stage,
                                          w32 &weak)
 {
-    const int P = KP ? KP : g.P, PP = KP ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW, G = KP ? KG : g.G;
+    const int P = KP > 0 ? KP : g.P, PP = KP > 0 ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW, G = KP ? KG : g.G;  // KP < 0: run-time P
     const int L = 8 * NW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int w_sa = (L - G) >> 3, w_sb = G >> 3;
@@ -554,11 +554,12 @@ __device__ __forceinline__ Smem pair_smem(unsigned char *raw, const FastGeom &g,
 }
 
 template <int LLR_T, int KP, int KNW, int KG>
-__global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) fast_s16_kernel(FastArgs A)
+__global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP < 0 ? 128 : 256), KP ? 2 : 1) fast_s16_kernel(FastArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FastGeom &g = A.g;
-    const int P = KP ? KP : g.P, PP = KP ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW;
+    // KP > 0: P, NW, G all compile-time; KP < 0: P <= 128 at run time, NW and G compile-time; KP == 0: all run-time
+    const int P = KP > 0 ? KP : g.P, PP = KP > 0 ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW;
     const int L = 8 * NW, K = P * L;
     const int W = L * PP;            // words per array
     const int Wp = (W + 7) & ~7;     // every region starts 16-byte aligned
@@ -568,7 +569,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
     // thread -> (pair slot q, sub-block t)
     const int q = KP ? 0 : tid / P, t = KP ? tid : tid - q * P;
     const int pair = blockIdx.x * NP + q;
-    const bool active = KP ? true : (q < NP && pair < n_pairs);
+    const bool active = KP > 0 ? true : (KP < 0 ? tid < P : (q < NP && pair < n_pairs));
     const Smem sm = pair_smem(smem_raw, g, P, NW, Wp, NP, active ? q : 0);
     unsigned *flags = reinterpret_cast<unsigned *>(sm.edge + 16 * (nthr >> 5));
     const int cbA = 2 * (active ? pair : 0);
@@ -701,7 +702,7 @@ __global__ void __launch_bounds__(KP ? ((KP + 31) / 32) * 32 : 256, KP ? 2 : 1) 
                     if (!chA && !usedA) usedA = it + 1;
                     if (!chB && !usedB) usedB = it + 1;
                 }
-                const bool done = (usedA && usedB) || !active;
+                const bool done = (usedA && usedB) || (!KP && !active);  // with one pair per CTA the flags are CTA-uniform
                 if (KP ? done : (__syncthreads_and((int)done) != 0)) { used = it + 1; break; }
             }
         } else {
@@ -789,11 +790,24 @@ kernel_fn pick_nw(int NW)
 }
 
 template <int LLR_T>
+kernel_fn pick_rt(int NW)
+{
+    switch (NW) {
+        case 4: return fast_s16_kernel<LLR_T, -1, 4, 16>;
+        case 5: return fast_s16_kernel<LLR_T, -1, 5, 16>;
+        case 6: return fast_s16_kernel<LLR_T, -1, 6, 16>;
+        case 7: return fast_s16_kernel<LLR_T, -1, 7, 16>;
+        default: return fast_s16_kernel<LLR_T, -1, 8, 16>;
+    }
+}
+
+template <int LLR_T>
 kernel_fn pick_kernel_t(const FastGeom &g)
 {
     if (fast_spec_pn(g)) return g.P == 128 ? pick_nw<LLR_T, 128>(g.NW) : (g.P == 64 ? pick_nw<LLR_T, 64>(g.NW) : pick_nw<LLR_T, 32>(g.NW));
     if (fast_spec128g8(g)) return fast_s16_kernel<LLR_T, 128, 6, 8>;
     if (fast_spec192(g)) return fast_s16_kernel<LLR_T, 192, 4, 16>;
+    if (fast_spec_rt(g)) return pick_rt<LLR_T>(g.NW);
     return fast_s16_kernel<LLR_T, 0, 0, 0>;
 }
 
