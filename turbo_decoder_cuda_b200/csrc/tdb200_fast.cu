@@ -28,7 +28,7 @@ fast_kernel_fn pick_kernel(const FastGeom &g, int llr_type)
 
 }  // namespace
 
-bool fast_s16_specialised(const FastGeom &g) { return fast_spec_pn(g) || fast_spec128g8(g) || fast_spec192(g) || fast_spec_rt(g); }
+bool fast_s16_specialised(const FastGeom &g) { return fast_spec_pn(g) || fast_spec128g8(g) || fast_spec192(g) || fast_spec_rt(g) || fast_spec_rt192(g); }
 
 // bytes of one codeblock-pair region / of the part shared by the pairs of a CTA of `threads` threads
 int fast_s16_pair_bytes(const FastGeom &g)

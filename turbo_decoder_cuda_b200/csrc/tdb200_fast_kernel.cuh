@@ -554,11 +554,11 @@ __device__ __forceinline__ Smem pair_smem(unsigned char *raw, const FastGeom &g,
 }
 
 template <int LLR_T, int KP, int KNW, int KG>
-__global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP < 0 ? 128 : 256), KP ? 2 : 1) fast_s16_kernel(FastArgs A)
+__global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 128 : (KP == -2 ? 192 : 256)), KP ? 2 : 1) fast_s16_kernel(FastArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FastGeom &g = A.g;
-    // KP > 0: P, NW, G all compile-time; KP < 0: P <= 128 at run time, NW and G compile-time; KP == 0: all run-time
+    // KP > 0: P, NW, G all compile-time; KP < 0: P at run time (-1: P <= 128, -2: P <= 192), NW and G compile-time; KP == 0: all run-time
     const int P = KP > 0 ? KP : g.P, PP = KP > 0 ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW;
     const int L = 8 * NW, K = P * L;
     const int W = L * PP;            // words per array
@@ -808,6 +808,7 @@ kernel_fn pick_kernel_t(const FastGeom &g)
     if (fast_spec128g8(g)) return fast_s16_kernel<LLR_T, 128, 6, 8>;
     if (fast_spec192(g)) return fast_s16_kernel<LLR_T, 192, 4, 16>;
     if (fast_spec_rt(g)) return pick_rt<LLR_T>(g.NW);
+    if (fast_spec_rt192(g)) return g.NW == 4 ? fast_s16_kernel<LLR_T, -2, 4, 16> : fast_s16_kernel<LLR_T, -2, 5, 16>;
     return fast_s16_kernel<LLR_T, 0, 0, 0>;
 }
 

@@ -140,6 +140,8 @@ inline bool fast_spec128g8(const FastGeom &g) { return g.P == 128 && g.NW == 6 &
 inline bool fast_spec192(const FastGeom &g) { return g.P == 192 && g.NW == 4 && g.G == 16 && g.PP == 193; }
 // every other plan with 33..128 sub-blocks of 32..64 steps and guard 16: P at run time, NW and G compile-time
 inline bool fast_spec_rt(const FastGeom &g) { return !fast_spec_pn(g) && g.P > 32 && g.P <= 128 && g.NW >= 4 && g.NW <= 8 && g.G == 16 && g.PP == (g.P | 1); }
+// 129..192 sub-blocks of 32 or 40 steps: six warps per CTA at 168 registers, two CTAs per SM
+inline bool fast_spec_rt192(const FastGeom &g) { return !fast_spec192(g) && g.P > 128 && g.P <= 192 && (g.NW == 4 || g.NW == 5) && g.G == 16 && g.PP == (g.P | 1); }
 
 cudaError_t fast_s16_configure(FastGeom &g, int sm_count);  // opt in to the dynamic shared memory size
 cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches);
