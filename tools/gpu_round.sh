@@ -16,3 +16,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $o/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:fast_s16 -s 3 -c 1 -o $o/${tag}_prof_fast -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $o/${tag}_ncu_full.log 2>&1
 tail -2 $o/${tag}_ncu_full.log | cut -c1-160
+# block-length x batch sweep (BASELINE configs[3]) and the caller-side kernels
+python tools/sweep_throughput.py --out $o/${tag}_sweep_k_batch.jsonl > $o/${tag}_sweep.log 2>&1; tail -1 $o/${tag}_sweep.log | cut -c1-200
+python tools/time_modem.py --json $o/${tag}_modem_timing.json > /dev/null 2>&1
+python tools/time_ratematch.py --json $o/${tag}_ratematch_timing.json > /dev/null 2>&1
+python tools/time_transport.py --json $o/${tag}_transport_timing.json > /dev/null 2>&1
+python tools/profile_callers.py > $o/${tag}_plain_callers.log 2>&1 &&
+ncu --set full --clock-control none -k regex:"demap|rate_|crc24|modulate|awgn" -c 14 -o $o/${tag}_prof_callers -f python tools/profile_callers.py > $o/${tag}_ncu_callers.log 2>&1
+tail -1 $o/${tag}_ncu_callers.log | cut -c1-160

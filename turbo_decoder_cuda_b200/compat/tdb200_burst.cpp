@@ -6,6 +6,11 @@
 // everything device-resident, the decode timed with CUDA events.
 //
 //   tdb200_burst [--total N] [--gpus G] [--ebn0 dB] [--chunk C] [--early-term 0|1] [--K K]
+//                [--modulation 1|2|3|4|6] [--E bits-per-codeblock-after-rate-matching] [--rv 0..3]
+//
+// With --modulation > 1 or --E the loop is main.cpp's with the two commented-out stages restored:
+// encode -> tdb200_rate_match_batch -> tdb200_modulate_flat -> tdb200_awgn_batch x2 -> tdb200_demap_flat ->
+// tdb200_decode_rm_batch (timed: demap + de-rate-match + decode).
 //
 // Prints one JSON line.  Built by turbo_decoder_cuda_b200/build.py next to the libraries.
 #include <cuda_runtime.h>
@@ -42,7 +47,9 @@ struct Result {
         if (s_ != TDB200_OK) { r.error = std::string(#x) + ": " + tdb200_last_error(); return; } \
     } while (0)
 
-void worker(int dev, int K, long long lo, long long hi, int chunk, double sigma, int early_term, Result &r)
+struct Chain { int modulation = 1, E = 0, rv = 0; };
+
+void worker(int dev, int K, long long lo, long long hi, int chunk, double sigma, int early_term, Chain ch, Result &r)
 {
     CK(cudaSetDevice(dev));
     tdb200_config cfg;
@@ -59,6 +66,19 @@ void worker(int dev, int K, long long lo, long long hi, int chunk, double sigma,
     CK(cudaMalloc(&d_out, (size_t)chunk * K));
     CK(cudaMalloc(&d_llr, (size_t)chunk * NL * sizeof(float)));
     CK(cudaMalloc(&d_iters, (size_t)chunk * sizeof(int32_t)));
+    // the optional rate-matching / mapping stages work on rows of E bits (E = 3K+12 without rate matching)
+    const bool chain = ch.modulation > 1 || ch.E > 0;
+    const size_t E = ch.E > 0 ? (size_t)ch.E : NL, NS = E / ch.modulation;
+    uint8_t *d_tx = nullptr;
+    float *d_si = nullptr, *d_sq = nullptr, *d_ri = nullptr, *d_rq = nullptr, *d_ellr = nullptr;
+    if (chain) {
+        CK(cudaMalloc(&d_tx, (size_t)chunk * E));
+        CK(cudaMalloc(&d_si, (size_t)chunk * NS * sizeof(float)));
+        CK(cudaMalloc(&d_sq, (size_t)chunk * NS * sizeof(float)));
+        CK(cudaMalloc(&d_ri, (size_t)chunk * NS * sizeof(float)));
+        CK(cudaMalloc(&d_rq, (size_t)chunk * NS * sizeof(float)));
+        CK(cudaMalloc(&d_ellr, (size_t)chunk * E * sizeof(float)));
+    }
     cudaStream_t st;
     CK(cudaStreamCreate(&st));
     cudaEvent_t e0, e1;
@@ -75,13 +95,25 @@ void worker(int dev, int K, long long lo, long long hi, int chunk, double sigma,
         }
         CK(cudaMemcpyAsync(d_bits, h_bits.data(), (size_t)n * K, cudaMemcpyHostToDevice, st));
         TK(tdb200_encode_batch(dec, d_bits, d_coded, TDB200_MEM_DEVICE, n, st));
-        TK(tdb200_channel_batch(dec, d_coded, d_llr, TDB200_LLR_F32, TDB200_MEM_DEVICE, n, sigma, (uint64_t)(c0 + 1), st));
         tdb200_outputs out;
         std::memset(&out, 0, sizeof(out));
         out.bits = d_out; out.iters_used = d_iters;
-        CK(cudaEventRecord(e0, st));
-        TK(tdb200_decode_batch(dec, d_llr, TDB200_LLR_F32, TDB200_MEM_DEVICE, n, &out, st));
-        CK(cudaEventRecord(e1, st));
+        if (!chain) {
+            TK(tdb200_channel_batch(dec, d_coded, d_llr, TDB200_LLR_F32, TDB200_MEM_DEVICE, n, sigma, (uint64_t)(c0 + 1), st));
+            CK(cudaEventRecord(e0, st));
+            TK(tdb200_decode_batch(dec, d_llr, TDB200_LLR_F32, TDB200_MEM_DEVICE, n, &out, st));
+            CK(cudaEventRecord(e1, st));
+        } else {
+            TK(tdb200_rate_match_batch(dec, d_coded, d_tx, TDB200_MEM_DEVICE, n, (int)E, ch.rv, 0, st));
+            TK(tdb200_modulate_flat(dec, d_tx, d_si, d_sq, TDB200_LLR_F32, TDB200_MEM_DEVICE, (size_t)n * E, ch.modulation, st));
+            TK(tdb200_awgn_batch(dec, d_si, d_ri, TDB200_LLR_F32, TDB200_MEM_DEVICE, (size_t)n * NS, sigma, (uint64_t)(2 * c0 + 1), st));
+            TK(tdb200_awgn_batch(dec, d_sq, d_rq, TDB200_LLR_F32, TDB200_MEM_DEVICE, (size_t)n * NS, sigma, (uint64_t)(2 * c0 + 2), st));
+            CK(cudaEventRecord(e0, st));
+            TK(tdb200_demap_flat(dec, d_ri, d_rq, TDB200_LLR_F32, d_ellr, TDB200_LLR_F32, TDB200_MEM_DEVICE, (size_t)n * E, ch.modulation,
+                                 1.0 / (2.0 * sigma * sigma), st));
+            TK(tdb200_decode_rm_batch(dec, d_ellr, TDB200_LLR_F32, TDB200_MEM_DEVICE, n, (int)E, ch.rv, 0, &out, st));
+            CK(cudaEventRecord(e1, st));
+        }
         CK(cudaMemcpyAsync(h_out.data(), d_out, (size_t)n * K, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_iters.data(), d_iters, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -98,6 +130,7 @@ void worker(int dev, int K, long long lo, long long hi, int chunk, double sigma,
         r.n += n;
     }
     cudaFree(d_bits); cudaFree(d_coded); cudaFree(d_out); cudaFree(d_llr); cudaFree(d_iters);
+    cudaFree(d_tx); cudaFree(d_si); cudaFree(d_sq); cudaFree(d_ri); cudaFree(d_rq); cudaFree(d_ellr);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     tdb200_destroy(dec);
 }
@@ -109,6 +142,7 @@ int main(int argc, char **argv)
     long long total = 65536;
     int gpus = 0, K = 6144, chunk = 8192, early_term = 0;
     double ebn0 = 1.0;
+    Chain ch;
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string a = argv[i];
         if (a == "--total") total = std::atoll(argv[i + 1]);
@@ -117,6 +151,9 @@ int main(int argc, char **argv)
         else if (a == "--chunk") chunk = std::atoi(argv[i + 1]);
         else if (a == "--ebn0") ebn0 = std::atof(argv[i + 1]);
         else if (a == "--early-term") early_term = std::atoi(argv[i + 1]);
+        else if (a == "--modulation") ch.modulation = std::atoi(argv[i + 1]);
+        else if (a == "--E") ch.E = std::atoi(argv[i + 1]);
+        else if (a == "--rv") ch.rv = std::atoi(argv[i + 1]);
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     int ndev = 0;
@@ -125,14 +162,20 @@ int main(int argc, char **argv)
         return 1;
     }
     if (gpus <= 0 || gpus > ndev) gpus = ndev;
-    // sigma for BPSK at the code rate K/(3K+12), ITTC/main.cpp:47,174
-    const double rate = K / (3.0 * K + 12.0), sigma = std::pow(10.0, -ebn0 / 20.0) * std::sqrt(0.5 / rate);
+    if (ch.modulation != 1 && ch.modulation != 2 && ch.modulation != 3 && ch.modulation != 4 && ch.modulation != 6) {
+        std::fprintf(stderr, "tdb200_burst: --modulation must be 1, 2, 3, 4 or 6\n");
+        return 2;
+    }
+    if ((ch.E > 0 ? ch.E : 3 * K + 12) % ch.modulation) { std::fprintf(stderr, "tdb200_burst: E must be a multiple of the modulation order\n"); return 2; }
+    // sigma at the code rate K/E and MODULATION bits per symbol, ITTC/main.cpp:47,174
+    const double rate = K / (ch.E > 0 ? (double)ch.E : 3.0 * K + 12.0);
+    const double sigma = std::pow(10.0, -ebn0 / 20.0) * std::sqrt(0.5 / (rate * ch.modulation));
     std::vector<Result> res(gpus);
     std::vector<std::thread> th;
     for (int g = 0; g < gpus; g++) {
         const long long base = total / gpus, rem = total % gpus;
         const long long lo = g * base + std::min<long long>(g, rem), hi = lo + base + (g < rem ? 1 : 0);
-        th.emplace_back(worker, g, K, lo, hi, chunk, sigma, early_term, std::ref(res[g]));
+        th.emplace_back(worker, g, K, lo, hi, chunk, sigma, early_term, ch, std::ref(res[g]));
     }
     for (auto &t : th) t.join();
     double ms_max = 0;
@@ -143,8 +186,8 @@ int main(int argc, char **argv)
         be += r.bit_err; fe += r.frame_err; it += r.iters; n += r.n;
     }
     std::printf("{\"tool\": \"tdb200_burst (C++ over the C ABI, one host thread per GPU)\", \"n_gpus\": %d, \"K\": %d, "
-                "\"codeblocks\": %lld, \"ebn0_db\": %.2f, \"early_term\": %d, \"decode_ms_max_over_gpus\": %.3f, "
+                "\"modulation\": %d, \"E\": %d, \"rv\": %d, \"codeblocks\": %lld, \"ebn0_db\": %.2f, \"early_term\": %d, \"decode_ms_max_over_gpus\": %.3f, "
                 "\"gbit_s\": %.3f, \"bit_errors\": %lld, \"frame_errors\": %lld, \"mean_iters\": %.3f}\n",
-                gpus, K, n, ebn0, early_term, ms_max, (double)n * K / (ms_max * 1e-3) / 1e9, be, fe, n ? (double)it / n : 0.0);
+                gpus, K, ch.modulation, ch.E > 0 ? ch.E : 3 * K + 12, ch.rv, n, ebn0, early_term, ms_max, (double)n * K / (ms_max * 1e-3) / 1e9, be, fe, n ? (double)it / n : 0.0);
     return 0;
 }
