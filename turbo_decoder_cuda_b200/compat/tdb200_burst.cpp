@@ -87,6 +87,22 @@ void worker(int dev, int K, long long lo, long long hi, int chunk, double sigma,
     std::vector<uint8_t> h_bits((size_t)chunk * K), h_out((size_t)chunk * K);
     std::vector<int32_t> h_iters(chunk);
     std::mt19937_64 rng(0x9E3779B97F4A7C15ull ^ (unsigned long long)lo);
+    {   // one untimed call on zeroed inputs: table uploads and scratch allocations happen here, not under the events
+        const int n = (int)std::min<long long>(chunk, hi - lo);
+        tdb200_outputs out;
+        std::memset(&out, 0, sizeof(out));
+        out.bits = d_out; out.iters_used = d_iters;
+        if (!chain) {
+            CK(cudaMemsetAsync(d_llr, 0, (size_t)n * NL * sizeof(float), st));
+            TK(tdb200_decode_batch(dec, d_llr, TDB200_LLR_F32, TDB200_MEM_DEVICE, n, &out, st));
+        } else {
+            CK(cudaMemsetAsync(d_ri, 0, (size_t)n * NS * sizeof(float), st));
+            CK(cudaMemsetAsync(d_rq, 0, (size_t)n * NS * sizeof(float), st));
+            TK(tdb200_demap_flat(dec, d_ri, d_rq, TDB200_LLR_F32, d_ellr, TDB200_LLR_F32, TDB200_MEM_DEVICE, (size_t)n * E, ch.modulation, 1.0, st));
+            TK(tdb200_decode_rm_batch(dec, d_ellr, TDB200_LLR_F32, TDB200_MEM_DEVICE, n, (int)E, ch.rv, 0, &out, st));
+        }
+        CK(cudaStreamSynchronize(st));
+    }
     for (long long c0 = lo; c0 < hi; c0 += chunk) {
         const int n = (int)std::min<long long>(chunk, hi - c0);
         for (size_t i = 0; i < (size_t)n * K; i += 8) {  // 8 random bits per draw
