@@ -101,6 +101,13 @@ def test_cpp_multi_gpu_caller():
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["codeblocks"] == 3001 and r["bit_errors"] == 0 and r["frame_errors"] == 0
     assert 2.0 <= r["mean_iters"] < 8.0 and r["gbit_s"] > 1.0
+    # main.cpp's loop with the rate-matching and mapping stages restored (16QAM, rate 1/2), all through the C ABI
+    out = subprocess.run([exe, "--total", "1500", "--chunk", "1024", "--ebn0", "5.0", "--modulation", "4", "--E", "12288", "--early-term", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["codeblocks"] == 1500 and r["modulation"] == 4 and r["E"] == 12288 and r["bit_errors"] == 0
+    assert subprocess.run([exe, "--modulation", "5"], capture_output=True).returncode == 2
 
 
 def test_device_path_is_cuda_graph_capturable():
