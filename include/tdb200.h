@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TDB200_VERSION 4
+#define TDB200_VERSION 5
 
 typedef enum tdb200_status {
     TDB200_OK = 0,
@@ -85,7 +85,13 @@ typedef struct tdb200_config {
     int warmup;     /* guard steps recomputed from the neighbouring sub-block before each
                        sub-block boundary; 0 = next-iteration initialisation only */
     int early_term; /* 1 = stop a codeblock when an iteration leaves every hard decision unchanged AND
-                       every a-posteriori magnitude is at least et_threshold (min 2 iterations) */
+                       every a-posteriori magnitude is at least et_threshold (min 2 iterations);
+                       2 / 3 (TDB200_ALGO_MAXLOG_S16 only) = stop when the K hard decisions divide by the
+                       CRC24B / CRC24A generator (TS 36.212 5.1.1: a code block of a segmented transport
+                       block ends in a CRC24B, an unsegmented one in the transport block's CRC24A) --
+                       the stop rule the reference leaves as a placeholder (previous/Decoder.cc:1026,
+                       1098-1099).  Checked on the natural-order decisions of SISO-1 from the second
+                       iteration on; a block without a valid CRC simply runs all n_iter iterations */
     int et_threshold; /* magnitude test of the stopping rule, fixed-point units, a power of two
                          (1 = decisions only).  0 = default: 2^(frac_bits+3), i.e. |LLR| >= 8 */
     int ext_scale_q2; /* extrinsic scaling in quarters for the max-log modes: 3 = 0.75, 4 = 1.0;

@@ -91,6 +91,8 @@ typedef struct tdo_fx_params {
     int ext_scale_q2; /* extrinsic scale in quarters: 3 = 0.75, 4 = 1.0 */
     int early_term;   /* 1: stop when an iteration changes no hard decision and every |a-posteriori| >= et_threshold */
     int et_threshold; /* fixed-point units; values < 1 are treated as 1 */
+    int crc_poly;     /* early_term == 2: stop when the natural-order decisions of SISO-1 (second iteration
+                         on) divide by x^24 + crc_poly; the delivered bits are then those decisions */
 } tdo_fx_params;
 
 /* Returns the number of iterations run.  bits_out[K] final decisions; le_out

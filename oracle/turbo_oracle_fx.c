@@ -118,6 +118,8 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
     int *prev_bits = (int *)malloc(sizeof(int) * K);
     int *cur_bits = (int *)malloc(sizeof(int) * K);
     int *Xold = (int *)malloc(sizeof(int) * K);
+    unsigned char *nat_bits = (unsigned char *)malloc(K);
+    int crc_stop = 0;
 
     for (int i = 0; i < K; i++) {
         ys[i] = quant(llr_in[3 * i], F, p->llr_clip);
@@ -197,6 +199,7 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                     memcpy(b, o, sizeof(b));
                     X[n] = add(ys[n], es);
                     if (k == G) memcpy(newB[t], b, sizeof(b));
+                    if (s == 0) nat_bits[i] = (unsigned char)(lam < 0 ? 0 : 1);
                     if (s == 1) {
                         cur_bits[n] = lam < 0 ? 0 : 1;
                         if (lam < et_T && lam > -et_T) weak = 1;
@@ -210,13 +213,23 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                 memcpy(niiA[s * P + t + 1], newA[t], sizeof(int) * NS);
                 memcpy(niiB[s * P + t], newB[t + 1], sizeof(int) * NS);
             }
+            /* CRC stopping rule: after SISO-1 of the second and later iterations */
+            if (s == 0 && p->early_term == 2 && it >= 1 && tdo_crc24(nat_bits, K, (unsigned)p->crc_poly) == 0) {
+                for (int i = 0; i < K; i++) prev_bits[i] = nat_bits[i];
+                crc_stop = 1;
+                break;
+            }
+        }
+        if (crc_stop) {
+            it++;
+            break;
         }
         int same = 1;
         for (int i = 0; i < K; i++) {
             if (cur_bits[i] != prev_bits[i]) same = 0;
             prev_bits[i] = cur_bits[i];
         }
-        if (p->early_term && same && !weak && it >= 1) {
+        if (p->early_term == 1 && same && !weak && it >= 1) {
             it++;
             break;
         }
@@ -224,6 +237,6 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
     memcpy(bits_out, prev_bits, sizeof(int) * K);
     if (overflow) *overflow = g_ovf;
     free(ys); free(yp1); free(yp2); free(X); free(alpha);
-    free(niiA); free(niiB); free(newA); free(newB); free(prev_bits); free(cur_bits); free(Xold);
+    free(niiA); free(niiB); free(newA); free(newB); free(prev_bits); free(cur_bits); free(Xold); free(nat_bits);
     return it;
 }

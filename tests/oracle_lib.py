@@ -43,7 +43,7 @@ def build_oracle(force=False):
 class FxParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "K", "n_iter", "sub_len", "warmup", "frac_bits", "llr_clip", "ext_clip",
-        "ext_scale_q2", "early_term", "et_threshold")]
+        "ext_scale_q2", "early_term", "et_threshold", "crc_poly")]
 
 
 class F32Params(C.Structure):

@@ -140,6 +140,8 @@ struct tdb200_decoder {
         int *d_perm = nullptr, *d_inv = nullptr;
     };
     std::vector<RmTable> rm_tables;  // one per (rv, N_cb) used so far
+    uint32_t *d_crc_tab = nullptr, *d_crc_shift = nullptr;  // CRC stopping rule (early_term 2 / 3)
+    uint32_t crc_poly = 0;
     int launches_last = 0;
 };
 
@@ -209,6 +211,7 @@ void tdb200_destroy(tdb200_decoder *d)
     cudaFree(d->d_pi); cudaFree(d->d_pi_inv); cudaFree(d->ws64_block); cudaFree(d->d_tab2);
     cudaFree(d->siso_in); cudaFree(d->siso_out); cudaFree(d->dem);
     for (auto &t : d->rm_tables) { cudaFree(t.d_perm); cudaFree(t.d_inv); }
+    cudaFree(d->d_crc_tab); cudaFree(d->d_crc_shift);
     for (auto &sl : d->slot) {
         cudaFree(sl.d_in); cudaFree(sl.d_dem); cudaFree(sl.d_bits); cudaFree(sl.d_bits_iters); cudaFree(sl.d_iters_used);
         cudaFree(sl.d_llr1); cudaFree(sl.d_llr2); cudaFree(sl.d_ext2);
@@ -292,6 +295,9 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
                c.algo == TDB200_ALGO_LINLOGMAP_F32) {
         const bool s16 = (c.algo == TDB200_ALGO_MAXLOG_S16);
         if (c.max_batch <= 0) c.max_batch = 16384;
+        if (c.early_term < 0 || c.early_term > 3) return fail(TDB200_ERR_INVALID_ARG, "early_term=%d (0..3)", c.early_term);
+        if (c.early_term >= 2 && !s16) return fail(TDB200_ERR_UNSUPPORTED, "the CRC stopping rule exists in TDB200_ALGO_MAXLOG_S16 only");
+        if (c.early_term >= 2 && K <= 24) return fail(TDB200_ERR_INVALID_ARG, "K=%d leaves no room for a 24-bit CRC", K);
         if (c.frac_bits == 0) c.frac_bits = 3;
         if (c.frac_bits < 1 || c.frac_bits > 4) return fail(TDB200_ERR_INVALID_ARG, "frac_bits=%d out of range [1,4]", c.frac_bits);
         if (c.ext_scale_q2 == 0) c.ext_scale_q2 = (c.algo == TDB200_ALGO_LOGMAP_F32 || c.algo == TDB200_ALGO_LINLOGMAP_F32) ? 4 : 3;
@@ -336,7 +342,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
             g.pair_bytes = fast_s16_pair_bytes(g);
             // pairs per CTA: fill two warps when a codeblock needs less than one (measured: larger CTAs
             // only add barrier coupling -- registers cap an SM at eight warps either way)
-            int np = (fast_s16_specialised(g) || g.P >= 32) ? 1 : std::max(1, std::min(64 / g.P, 64));
+            int np = (fast_s16_specialised(g) || g.P >= 32 || c.early_term >= 2) ? 1 : std::max(1, std::min(64 / g.P, 64));  // the CRC fold is per CTA
             while (np > 1) {
                 g.NP = np; g.threads = ((np * g.P + 31) / 32) * 32;
                 if ((size_t)fast_s16_smem_bytes(g) <= prop.sharedMemPerBlockOptin) break;
@@ -355,6 +361,25 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         for (int i = 0; i < K; i++) {
             const int t = i / L, j = i % L, n = d->h_pi[i];
             tab[j * g.PP + t] = (uint16_t)((n % L) * g.PP + n / L);
+        }
+        if (c.early_term >= 2) {
+            // byte-wise table of the generator and the weight x^((P-1-t)L) mod g of sub-block t's remainder
+            const uint32_t poly = d->crc_poly = (c.early_term == 2) ? 0x800063u : 0x864CFBu;
+            std::vector<uint32_t> tb(256), sh(g.P);
+            for (uint32_t v = 0; v < 256; v++) {
+                uint32_t r = v << 16;
+                for (int b = 0; b < 8; b++) r = ((r << 1) & 0xffffffu) ^ ((r & 0x800000u) ? poly : 0u);
+                tb[v] = r;
+            }
+            uint32_t a = 1;
+            for (int t = g.P - 1; t >= 0; t--) {
+                sh[t] = a;
+                for (int b = 0; b < L; b++) a = ((a << 1) & 0xffffffu) ^ ((a & 0x800000u) ? poly : 0u);
+            }
+            TDB_CUDA(cudaMalloc(&d->d_crc_tab, sizeof(uint32_t) * 256));
+            TDB_CUDA(cudaMalloc(&d->d_crc_shift, sizeof(uint32_t) * g.P));
+            TDB_CUDA(cudaMemcpy(d->d_crc_tab, tb.data(), sizeof(uint32_t) * 256, cudaMemcpyHostToDevice));
+            TDB_CUDA(cudaMemcpy(d->d_crc_shift, sh.data(), sizeof(uint32_t) * g.P, cudaMemcpyHostToDevice));
         }
         TDB_CUDA(cudaMalloc(&d->d_tab2, sizeof(uint16_t) * tab.size()));
         TDB_CUDA(cudaMemcpy(d->d_tab2, tab.data(), sizeof(uint16_t) * tab.size(), cudaMemcpyHostToDevice));
@@ -443,7 +468,8 @@ static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int 
         a.frac_bits = c.frac_bits;
         a.llr_clip = std::min((1 << (c.frac_bits + 4)) - 1, 127);  // systematic values are kept as bytes in shared memory
         a.ext_lim = c.ext_clip + 1;
-        a.q2 = c.ext_scale_q2; a.early_term = c.early_term; a.et_threshold = c.et_threshold;
+        a.q2 = c.ext_scale_q2; a.early_term = std::min(c.early_term, 2); a.et_threshold = c.et_threshold;
+        a.crc_poly = d->crc_poly; a.crc_tab = d->d_crc_tab; a.crc_shift = d->d_crc_shift;
         a.tab2 = d->d_tab2;
         a.opaque[0] = 0xffffffffu; a.opaque[1] = 4u; a.opaque[2] = 65536u; a.opaque[3] = 0xC0000000u;
         a.prefetch_stride = d->geom.resident_ctas;

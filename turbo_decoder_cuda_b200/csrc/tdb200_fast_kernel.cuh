@@ -553,6 +553,51 @@ __device__ __forceinline__ Smem pair_smem(unsigned char *raw, const FastGeom &g,
     return sm;
 }
 
+// a * b mod g over GF(2), 24-bit operands (g = x^24 + poly)
+__device__ __forceinline__ unsigned crc_mulmod24(unsigned a, unsigned b, unsigned poly)
+{
+    unsigned r = 0;
+#pragma unroll 1
+    for (int i = 0; i < 24; i++) {
+        r ^= (b & 1u) ? a : 0u;
+        b >>= 1;
+        a = ((a << 1) & 0xffffffu) ^ ((a & 0x800000u) ? poly : 0u);
+    }
+    return r;
+}
+
+// CRC stopping rule: remainders of codeblocks A and B over the natural-order decisions SISO-1 left in
+// sm.dec.  Every thread divides the 8*NW decisions of its own sub-block byte by byte (table look-up),
+// weights the remainder with x^(bits that follow) mod g, and the CTA XORs the 24-bit results together:
+// a CRC is linear over GF(2).  Returns {remainder A, remainder B}, identical in all threads.
+__device__ __forceinline__ uint2 crc_of_decisions(const FastArgs &A, const Smem &sm, unsigned *flags, int P, int NW, int t, bool active)
+{
+    unsigned ca = 0, cb = 0;
+    if (active) {
+        for (int w = 0; w < NW; w++) {
+            const w32 word = sm.dec[(w >> 1) * P + t] >> (8 * (w & 1));  // sign bits: set = decision 0
+            const unsigned da = (~word) & 0xffu, db = (~(word >> 16)) & 0xffu;
+            ca = ((ca << 8) & 0xffffffu) ^ __ldg(A.crc_tab + (((ca >> 16) ^ da) & 0xffu));
+            cb = ((cb << 8) & 0xffffffu) ^ __ldg(A.crc_tab + (((cb >> 16) ^ db) & 0xffu));
+        }
+        const unsigned m = __ldg(A.crc_shift + t);
+        ca = crc_mulmod24(ca, m, A.crc_poly);
+        cb = crc_mulmod24(cb, m, A.crc_poly);
+    }
+    ca = __reduce_xor_sync(0xffffffffu, ca);
+    cb = __reduce_xor_sync(0xffffffffu, cb);
+    if (threadIdx.x < 2) flags[threadIdx.x] = 0u;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        atomicXor(&flags[0], ca);
+        atomicXor(&flags[1], cb);
+    }
+    __syncthreads();
+    const uint2 r = make_uint2(flags[0], flags[1]);
+    __syncthreads();  // the words are reused by the next check
+    return r;
+}
+
 template <int LLR_T, int KP, int KNW, int KG>
 __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 128 : (KP == -2 ? 192 : 256)), KP ? 2 : 1) fast_s16_kernel(FastArgs A)
 {
@@ -672,17 +717,29 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
     __syncthreads();
 
     const bool want_soft = (A.llr2 != nullptr);
+    const bool crc_et = (A.early_term == 2);  // one pair per CTA (the host plans it that way)
+    bool natural = false;                     // the delivered decisions are SISO-1's (natural order)
     int used = A.n_iter, usedA = 0, usedB = 0;
     for (int it = 0; it < A.n_iter; it++) {
         const bool last = (it == A.n_iter - 1);
         w32 weak = 0;
-        siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
-        if (A.early_term || last) {
+        if (crc_et && it >= 1) {
+            // SISO-1 with decisions; stop when the natural-order decisions of both codeblocks divide by the
+            // generator -- half an iteration after the SISO-2 pass that made them right
+            siso_pass<false, true, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
+            const uint2 rem = crc_of_decisions(A, sm, flags, P, NW, t, active);
+            if (!rem.x && !usedA) usedA = it + 1;
+            if (!rem.y && !usedB) usedB = it + 1;
+            if (usedA && usedB) { used = it + 1; natural = true; break; }
+        } else {
+            siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
+        }
+        if (A.early_term == 1 || last) {
             // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
             // (by then dead) parity-1 array
             const w32 chg = siso_pass<true, true, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed,
                                                                (want_soft && last) ? sm.par1 : nullptr, weak);
-            if (A.early_term) {
+            if (A.early_term == 1) {
                 // stop: no decision of this iteration differs from the previous one and no
                 // a-posteriori value is weaker than the threshold -- per codeblock; a CTA leaves when
                 // all its codeblocks have stopped
@@ -724,9 +781,12 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                 for (int kk = 0; kk < 16; kk++) {
                     const int j = 16 * w2 + (kk & 8) + 7 - (kk & 7);  // step k of a window sits in bit 7-k of its byte
                     if (j < L) {
-                        const int e = sm.tab[j * PP + t];
-                        const int jj = e / PP, tt = e - jj * PP;
-                        const int n = tt * L + jj;
+                        int n = t * L + j;  // SISO-1 decisions are in natural order already
+                        if (!natural) {
+                            const int e = sm.tab[j * PP + t];
+                            const int jj = e / PP, tt = e - jj * PP;
+                            n = tt * L + jj;
+                        }
                         byA[n] = (uint8_t)(((word >> kk) & 1u) ^ 1u);
                         byB[n] = (uint8_t)(((word >> (16 + kk)) & 1u) ^ 1u);
                     }

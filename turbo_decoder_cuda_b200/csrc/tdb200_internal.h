@@ -100,7 +100,10 @@ struct FastArgs {
     FastGeom g;
     int n_iter;
     int frac_bits, llr_clip, ext_lim /* Ce+1, multiple of 4 */, q2;
-    int early_term, et_threshold;
+    int early_term, et_threshold;  // early_term: 0 off, 1 decisions + magnitude, 2 CRC of the SISO-1 decisions
+    uint32_t crc_poly;             // low 24 bits of the generator (early_term == 2)
+    const uint32_t *crc_tab;       // [256] device: byte-wise table of that generator
+    const uint32_t *crc_shift;     // [P] device: x^((P-1-t)L) mod g, the weight of sub-block t's remainder
     uint32_t opaque[4];  // {0xffffffff, 4, 65536, 0xC0000000}: see PassCfg in tdb200_fast_kernel.cuh
     const uint16_t *tab2;  // [L*PP] device: smem word of element pi(tL+j), stored at index j*PP+t
     int prefetch_stride;   // CTAs resident on the device at once (0 = no L2 prefetch of the next pair)

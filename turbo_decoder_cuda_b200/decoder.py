@@ -158,6 +158,8 @@ class TurboDecoder:
         _check(L.tdb200_default_config(C.byref(cfg), K))
         cfg.f1, cfg.f2, cfg.n_iter = f1, f2, n_iter
         cfg.algo = ALGO_NAMES[algo] if isinstance(algo, str) else int(algo)
+        # early_term: False/0 off, True/1 decisions + magnitude, "crc24b"/2 and "crc24a"/3 the CRC stopping rule
+        early_term = {"crc24b": 2, "crc24a": 3}.get(early_term, early_term)
         cfg.sub_block, cfg.warmup, cfg.early_term = sub_block, warmup, int(early_term)
         cfg.ext_scale_q2, cfg.frac_bits, cfg.device, cfg.max_batch = ext_scale_q2, frac_bits, device, max_batch
         cfg.ext_clip, cfg.et_threshold = ext_clip, et_threshold
