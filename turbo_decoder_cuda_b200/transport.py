@@ -17,6 +17,7 @@ from .decoder import CRC24A, CRC24B, TurboDecoder, segmentation
 
 class TransportBlockCodec:
     def __init__(self, A, device=0, n_iter=8, algo="maxlog_s16", early_term=True, max_batch=0):
+        """early_term: True = the CRC stopping rule (s16 decoder), "hda" = decisions + magnitude, False = none."""
         self.A = int(A)
         self.B = self.A + 24                                    # with the transport-block CRC24A
         s = self.seg = segmentation(self.B)
@@ -24,8 +25,12 @@ class TransportBlockCodec:
         # blocks r = 0 .. C_minus-1 have K_minus bits, the rest K_plus (5.1.2)
         self.groups = ([(s["K_minus"], s["C_minus"])] if s["C_minus"] else []) + [(s["K_plus"], s["C_plus"])]
         kw = dict(n_iter=n_iter, algo=algo, device=device, max_batch=max_batch)
-        if algo != "logmap_f64":
-            kw["early_term"] = early_term
+        if algo == "maxlog_s16" and early_term is True:
+            # every code block ends in a CRC: its own CRC24B, or the transport block's CRC24A when there is one block
+            # (leading filler zeros do not change a CRC): stop each block as soon as its decisions divide
+            kw["early_term"] = "crc24b" if s["C"] > 1 else "crc24a"
+        elif algo != "logmap_f64":
+            kw["early_term"] = True if early_term == "hda" else early_term
         self.dec = {K: TurboDecoder(K, **kw) for K, _ in self.groups}
         self._any = next(iter(self.dec.values()))
 
@@ -41,13 +46,13 @@ class TransportBlockCodec:
             blk = torch.zeros((n_tb, K), dtype=torch.uint8, device=payload.device)
             blk[:, s["F"]:] = tb
             return [(K, blk)]
-        out, pos = [], -s["F"]                                  # the fillers sit in front of the first block
+        # fillers + transport block, cut into the payload parts of the blocks (K - 24 bits each): pure reshapes
+        stream = torch.cat([torch.zeros((n_tb, s["F"]), dtype=torch.uint8, device=payload.device), tb], dim=1)
+        out, pos = [], 0
         for K, cnt in self.groups:
             blk = torch.zeros((n_tb, cnt, K), dtype=torch.uint8, device=payload.device)
-            for r in range(cnt):
-                lo, hi = pos, pos + K - 24
-                blk[:, r, max(0, -lo):K - 24] = tb[:, max(lo, 0):hi]
-                pos = hi
+            blk[:, :, :K - 24] = stream[:, pos:pos + cnt * (K - 24)].reshape(n_tb, cnt, K - 24)
+            pos += cnt * (K - 24)
             blk = blk.reshape(n_tb * cnt, K)
             self.dec[K].crc24_attach(blk, CRC24B)
             out.append((K, blk))
@@ -66,15 +71,11 @@ class TransportBlockCodec:
             tb = bits[0][1][:, s["F"]:].contiguous()
             cb_ok = torch.ones((n_tb, 1), dtype=torch.uint8, device=dev)
         else:
-            tb = torch.empty((n_tb, self.B), dtype=torch.uint8, device=dev)
-            oks, pos = [], -s["F"]
+            oks, parts = [], []
             for (K, cnt), (_, b) in zip(self.groups, bits):
                 oks.append(self.dec[K].crc24_check(b, CRC24B).reshape(n_tb, cnt))
-                b = b.reshape(n_tb, cnt, K)
-                for r in range(cnt):
-                    lo, hi = pos, pos + K - 24
-                    tb[:, max(lo, 0):hi] = b[:, r, max(0, -lo):K - 24]
-                    pos = hi
+                parts.append(b.reshape(n_tb, cnt, K)[:, :, :K - 24].reshape(n_tb, cnt * (K - 24)))
+            tb = torch.cat(parts, dim=1)[:, s["F"]:].contiguous()
             cb_ok = torch.cat(oks, dim=1)
         tb_ok = self._any.crc24_check(tb, CRC24A)
         return tb[:, :self.A].contiguous(), tb_ok, cb_ok
