@@ -33,6 +33,10 @@ KERNEL_TUS = [
     ("tdb200_fast_inst_f64.cu", ["-Xptxas", "-v"]),
     ("tdb200_fast_inst_s8.cu", ["-Xptxas", "-v"]),
     ("tdb200_fast_inst_f16.cu", ["-Xptxas", "-v"]),
+    ("tdb200_fast_inst_crc_f32.cu", []),
+    ("tdb200_fast_inst_crc_f64.cu", []),
+    ("tdb200_fast_inst_crc_s8.cu", []),
+    ("tdb200_fast_inst_crc_f16.cu", []),
     ("tdb200_f32.cu", ["-fmad=false", "-Xptxas", "-v"]),
     ("tdb200_encode.cu", []),
     ("tdb200_modem.cu", ["-fmad=false"]),

@@ -13,11 +13,24 @@ fast_kernel_fn fast_pick_f64(const FastGeom &g);
 fast_kernel_fn fast_pick_f32(const FastGeom &g);
 fast_kernel_fn fast_pick_s8(const FastGeom &g);
 fast_kernel_fn fast_pick_f16(const FastGeom &g);
+// the same with the CRC stopping rule compiled in (tdb200_fast_inst_crc_*.cu)
+fast_kernel_fn fast_pick_crc_f64(const FastGeom &g);
+fast_kernel_fn fast_pick_crc_f32(const FastGeom &g);
+fast_kernel_fn fast_pick_crc_s8(const FastGeom &g);
+fast_kernel_fn fast_pick_crc_f16(const FastGeom &g);
 
 namespace {
 
-fast_kernel_fn pick_kernel(const FastGeom &g, int llr_type)
+fast_kernel_fn pick_kernel(const FastGeom &g, int llr_type, bool crc = false)
 {
+    if (crc) {
+        switch (llr_type) {
+            case TDB200_LLR_F32: return fast_pick_crc_f32(g);
+            case TDB200_LLR_F64: return fast_pick_crc_f64(g);
+            case TDB200_LLR_F16: return fast_pick_crc_f16(g);
+            default: return fast_pick_crc_s8(g);
+        }
+    }
     switch (llr_type) {
         case TDB200_LLR_F32: return fast_pick_f32(g);
         case TDB200_LLR_F64: return fast_pick_f64(g);
@@ -54,6 +67,7 @@ cudaError_t fast_s16_configure(FastGeom &g, int sm_count)
     if (e0 != cudaSuccess) return e0;
     for (int t = TDB200_LLR_F64; t <= TDB200_LLR_F16; t++) {
         cudaError_t e = cudaFuncSetAttribute(pick_kernel(g, t), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pick_kernel(g, t, true), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
         if (e != cudaSuccess) return e;
     }
     int per_sm = 0;
@@ -74,7 +88,7 @@ cudaError_t launch_fast_s16(const FastArgs &a0, cudaStream_t st, int *n_launches
     a.pairs_per_cta = np;
     const int threads = ((np * a.g.P + 31) / 32) * 32;
     const int smem = a.g.pair_bytes * np + shared_bytes(a.g, threads, np);
-    pick_kernel(a.g, a.llr_type)<<<(pairs + np - 1) / np, threads, smem, st>>>(a);
+    pick_kernel(a.g, a.llr_type, a.early_term == 2)<<<(pairs + np - 1) / np, threads, smem, st>>>(a);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

@@ -4,5 +4,5 @@
 
 namespace tdb200 {
 typedef void (*fast_kernel_fn)(FastArgs);
-fast_kernel_fn fast_pick_f32(const FastGeom &g) { return pick_kernel_t<TDB200_LLR_F32>(g); }
+fast_kernel_fn fast_pick_f32(const FastGeom &g) { return pick_kernel_t<TDB200_LLR_F32, false>(g); }
 }  // namespace tdb200

@@ -4,5 +4,5 @@
 
 namespace tdb200 {
 typedef void (*fast_kernel_fn)(FastArgs);
-fast_kernel_fn fast_pick_f64(const FastGeom &g) { return pick_kernel_t<TDB200_LLR_F64>(g); }
+fast_kernel_fn fast_pick_f64(const FastGeom &g) { return pick_kernel_t<TDB200_LLR_F64, false>(g); }
 }  // namespace tdb200

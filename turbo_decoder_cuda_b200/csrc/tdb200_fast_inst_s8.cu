@@ -4,5 +4,5 @@
 
 namespace tdb200 {
 typedef void (*fast_kernel_fn)(FastArgs);
-fast_kernel_fn fast_pick_s8(const FastGeom &g) { return pick_kernel_t<TDB200_LLR_S8>(g); }
+fast_kernel_fn fast_pick_s8(const FastGeom &g) { return pick_kernel_t<TDB200_LLR_S8, false>(g); }
 }  // namespace tdb200

@@ -598,7 +598,7 @@ __device__ __forceinline__ uint2 crc_of_decisions(const FastArgs &A, const Smem 
     return r;
 }
 
-template <int LLR_T, int KP, int KNW, int KG>
+template <int LLR_T, int KP, int KNW, int KG, bool CRC>
 __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 128 : (KP == -2 ? 192 : 256)), KP ? 2 : 1) fast_s16_kernel(FastArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -717,23 +717,26 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
     __syncthreads();
 
     const bool want_soft = (A.llr2 != nullptr);
-    const bool crc_et = (A.early_term == 2);  // one pair per CTA (the host plans it that way)
+    // CRC: the stopping rule by CRC has its own instantiations (the default kernels do not carry the path); one pair per CTA
     bool natural = false;                     // the delivered decisions are SISO-1's (natural order)
     int used = A.n_iter, usedA = 0, usedB = 0;
     for (int it = 0; it < A.n_iter; it++) {
         const bool last = (it == A.n_iter - 1);
         w32 weak = 0;
-        if (crc_et && it >= 1) {
-            // SISO-1 with decisions; stop when the natural-order decisions of both codeblocks divide by the
-            // generator -- half an iteration after the SISO-2 pass that made them right
-            siso_pass<false, true, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
-            const uint2 rem = crc_of_decisions(A, sm, flags, P, NW, t, active);
-            if (!rem.x && !usedA) usedA = it + 1;
-            if (!rem.y && !usedB) usedB = it + 1;
-            if (usedA && usedB) { used = it + 1; natural = true; break; }
-        } else {
-            siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
+        bool siso1_done = false;
+        if constexpr (CRC) {
+            if (it >= 1) {
+                // SISO-1 with decisions; stop when the natural-order decisions of both codeblocks divide by the
+                // generator -- half an iteration after the SISO-2 pass that made them right
+                siso_pass<false, true, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
+                const uint2 rem = crc_of_decisions(A, sm, flags, P, NW, t, active);
+                if (!rem.x && !usedA) usedA = it + 1;
+                if (!rem.y && !usedB) usedB = it + 1;
+                if (usedA && usedB) { used = it + 1; natural = true; break; }
+                siso1_done = true;
+            }
         }
+        if (!siso1_done) siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
         if (A.early_term == 1 || last) {
             // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
             // (by then dead) parity-1 array
@@ -841,35 +844,35 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
 
 typedef void (*kernel_fn)(FastArgs);
 
-template <int LLR_T, int KP>
+template <int LLR_T, int KP, bool CRC>
 kernel_fn pick_nw(int NW)
 {
-    if (NW == 6) return fast_s16_kernel<LLR_T, KP, 6, 16>;
-    if (NW == 5) return fast_s16_kernel<LLR_T, KP, 5, 16>;
-    return fast_s16_kernel<LLR_T, KP, 4, 16>;
+    if (NW == 6) return fast_s16_kernel<LLR_T, KP, 6, 16, CRC>;
+    if (NW == 5) return fast_s16_kernel<LLR_T, KP, 5, 16, CRC>;
+    return fast_s16_kernel<LLR_T, KP, 4, 16, CRC>;
 }
 
-template <int LLR_T>
+template <int LLR_T, bool CRC>
 kernel_fn pick_rt(int NW)
 {
     switch (NW) {
-        case 4: return fast_s16_kernel<LLR_T, -1, 4, 16>;
-        case 5: return fast_s16_kernel<LLR_T, -1, 5, 16>;
-        case 6: return fast_s16_kernel<LLR_T, -1, 6, 16>;
-        case 7: return fast_s16_kernel<LLR_T, -1, 7, 16>;
-        default: return fast_s16_kernel<LLR_T, -1, 8, 16>;
+        case 4: return fast_s16_kernel<LLR_T, -1, 4, 16, CRC>;
+        case 5: return fast_s16_kernel<LLR_T, -1, 5, 16, CRC>;
+        case 6: return fast_s16_kernel<LLR_T, -1, 6, 16, CRC>;
+        case 7: return fast_s16_kernel<LLR_T, -1, 7, 16, CRC>;
+        default: return fast_s16_kernel<LLR_T, -1, 8, 16, CRC>;
     }
 }
 
-template <int LLR_T>
+template <int LLR_T, bool CRC>
 kernel_fn pick_kernel_t(const FastGeom &g)
 {
-    if (fast_spec_pn(g)) return g.P == 128 ? pick_nw<LLR_T, 128>(g.NW) : (g.P == 64 ? pick_nw<LLR_T, 64>(g.NW) : pick_nw<LLR_T, 32>(g.NW));
-    if (fast_spec128g8(g)) return fast_s16_kernel<LLR_T, 128, 6, 8>;
-    if (fast_spec192(g)) return fast_s16_kernel<LLR_T, 192, 4, 16>;
-    if (fast_spec_rt(g)) return pick_rt<LLR_T>(g.NW);
-    if (fast_spec_rt192(g)) return g.NW == 4 ? fast_s16_kernel<LLR_T, -2, 4, 16> : fast_s16_kernel<LLR_T, -2, 5, 16>;
-    return fast_s16_kernel<LLR_T, 0, 0, 0>;
+    if (fast_spec_pn(g)) return g.P == 128 ? pick_nw<LLR_T, 128, CRC>(g.NW) : (g.P == 64 ? pick_nw<LLR_T, 64, CRC>(g.NW) : pick_nw<LLR_T, 32, CRC>(g.NW));
+    if (fast_spec128g8(g)) return fast_s16_kernel<LLR_T, 128, 6, 8, CRC>;
+    if (fast_spec192(g)) return fast_s16_kernel<LLR_T, 192, 4, 16, CRC>;
+    if (fast_spec_rt(g)) return pick_rt<LLR_T, CRC>(g.NW);
+    if (fast_spec_rt192(g)) return g.NW == 4 ? fast_s16_kernel<LLR_T, -2, 4, 16, CRC> : fast_s16_kernel<LLR_T, -2, 5, 16, CRC>;
+    return fast_s16_kernel<LLR_T, 0, 0, 0, CRC>;
 }
 
 }  // namespace
