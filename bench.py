@@ -236,6 +236,31 @@ def run_ours(args):
                    "ber": float((et_bits != bits).sum().item()) / (batch * K),
                    "rule": "no hard decision changes and every |a-posteriori| >= 8.0, at most 8 iterations"}
         dec_et.close()
+        # the CRC stopping rule needs blocks that end in a CRC24B: the same payloads with their last 24 bits
+        # replaced, encoded and sent through the same channel (kernels of the library, outside any timed region)
+        if args.sub_block == 0 and args.guard == 0:
+            dec_crc = TurboDecoder(K, n_iter=N_ITER, algo=args.algo, device=local, max_batch=batch, early_term="crc24b")
+            crc_bits = bits.clone()
+            dec_crc.crc24_attach(crc_bits, tdb.CRC24B)
+            crc_llr = dec_crc.channel(dec_crc.encode(crc_bits), synth.sigma_from_ebn0(args.ebn0, K), seed=1234 + rank)
+
+            def step_crc():
+                dec_crc.decode_raw(crc_llr.data_ptr(), tdb.LLR_F32, tdb.MEM_DEVICE, batch, bits=et_bits.data_ptr(),
+                                   iters_used=et_iters.data_ptr(), stream=sp)
+            for _ in range(3):
+                step_crc()
+            torch.cuda.synchronize()
+            g0.record(stream)
+            for _ in range(args.steps):
+                step_crc()
+            g1.record(stream)
+            torch.cuda.synchronize()
+            et_info["crc24b_rule"] = {"gbit_s_this_rank": batch * K * args.steps / (g0.elapsed_time(g1) * 1e-3) / 1e9,
+                                      "mean_iterations": float(et_iters.float().mean().item()),
+                                      "ber": float((et_bits != crc_bits).sum().item()) / (batch * K),
+                                      "rule": "hard decisions of SISO-1 divide by the CRC24B generator (the last iteration counted is half-run)"}
+            dec_crc.close()
+            del crc_llr
 
     # ---- end to end through host buffers (pinned): H2D + decode + D2H inside the timed region
     h_llr = torch.empty(llr.shape, dtype=llr.dtype, pin_memory=True)
