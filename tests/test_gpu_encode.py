@@ -108,6 +108,16 @@ def test_cpp_multi_gpu_caller():
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["codeblocks"] == 1500 and r["modulation"] == 4 and r["E"] == 12288 and r["bit_errors"] == 0
     assert subprocess.run([exe, "--modulation", "5"], capture_output=True).returncode == 2
+    # the CRC stopping rule from C++: blocks get a CRC24B attached on the device, fewer iterations than rule 1
+    its = {}
+    for rule in ("1", "2"):
+        out = subprocess.run([exe, "--total", "2048", "--chunk", "1024", "--ebn0", "1.5", "--early-term", rule],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+        assert r["bit_errors"] == 0
+        its[rule] = r["mean_iters"]
+    assert its["2"] < its["1"]
 
 
 def test_device_path_is_cuda_graph_capturable():

@@ -5,7 +5,7 @@
 // random bits -> tdb200_encode_batch -> tdb200_channel_batch -> tdb200_decode_batch -> error count,
 // everything device-resident, the decode timed with CUDA events.
 //
-//   tdb200_burst [--total N] [--gpus G] [--ebn0 dB] [--chunk C] [--early-term 0|1] [--K K]
+//   tdb200_burst [--total N] [--gpus G] [--ebn0 dB] [--chunk C] [--early-term 0|1|2 (CRC24B)|3 (CRC24A)] [--K K]
 //                [--modulation 1|2|3|4|6] [--E bits-per-codeblock-after-rate-matching] [--rv 0..3]
 //
 // With --modulation > 1 or --E the loop is main.cpp's with the two commented-out stages restored:
@@ -110,6 +110,10 @@ void worker(int dev, int K, long long lo, long long hi, int chunk, double sigma,
             for (int j = 0; j < 8 && i + j < (size_t)n * K; j++) h_bits[i + j] = (uint8_t)((w >> (8 * j)) & 1u);
         }
         CK(cudaMemcpyAsync(d_bits, h_bits.data(), (size_t)n * K, cudaMemcpyHostToDevice, st));
+        if (early_term >= 2) {  // the CRC stopping rule needs blocks that end in a CRC: replace the last 24 bits
+            TK(tdb200_crc24_attach_batch(dec, d_bits, 0, early_term == 2 ? TDB200_CRC24B : TDB200_CRC24A, TDB200_MEM_DEVICE, n, st));
+            CK(cudaMemcpyAsync(h_bits.data(), d_bits, (size_t)n * K, cudaMemcpyDeviceToHost, st));
+        }
         TK(tdb200_encode_batch(dec, d_bits, d_coded, TDB200_MEM_DEVICE, n, st));
         tdb200_outputs out;
         std::memset(&out, 0, sizeof(out));
