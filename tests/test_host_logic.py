@@ -234,3 +234,25 @@ def test_segmentation_known_cases_and_abi(oracle, lib):
         assert got["C_plus"] * got["K_plus"] + got["C_minus"] * got["K_minus"] == Bp + got["F"]
         assert got["K_plus"] in sizes and (got["C_minus"] == 0 or got["K_minus"] in sizes) and 0 <= got["F"] < 64 * got["C"]
     assert lib.tdb200_segmentation(0, C.byref(Seg())) != 0
+
+
+def test_header_is_plain_c99(lib, tmp_path):
+    """include/tdb200.h is the C ABI: it must compile as strict C99 (no C++-isms, no torch / CUDA types) and a C program
+    linked against the library can call the host-only entry points without a GPU."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "tdb200.h"\n'
+                   'int main(void) { tdb200_seg_info s; tdb200_config c; int f1, f2;\n'
+                   '  if (tdb200_segmentation(75400, &s) != TDB200_OK || s.C != 13 || s.K_plus != 5824) return 1;\n'
+                   '  if (tdb200_default_config(&c, 6144) != TDB200_OK || c.n_iter != 8) return 2;\n'
+                   '  if (tdb200_lte_qpp_params(6144, &f1, &f2) != TDB200_OK || f1 != 263 || f2 != 480) return 3;\n'
+                   '  return tdb200_lte_qpp_params(6145, &f1, &f2) == TDB200_OK ? 4 : 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "turbo_decoder_cuda_b200", "lib")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-ltdb200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
