@@ -154,3 +154,6 @@ def test_crc_stopping_rule_bit_exact(oracle, K, which, ebn0):
     assert got_it[keep].mean() <= it_hda[keep].mean(), "the CRC rule never needs more iterations than decisions + magnitude"
     # host-memory path and an odd batch of one
     assert np.array_equal(dec.decode(h_llr[:1])["bits"], got_bits[:1])
+    from turbo_decoder_cuda_b200.decoder import TdbError
+    with pytest.raises(TdbError):
+        dec.decode(llr, want=("bits", "ext_siso2"))   # a block may stop after SISO-1: no SISO-2 extrinsic to report

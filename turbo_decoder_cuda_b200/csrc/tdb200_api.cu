@@ -581,6 +581,8 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
     const size_t fsz = f64 ? sizeof(double) : sizeof(float);  // native float type of the LLR outputs
     if (!f64 && (out->bits_iters || out->llr_siso1))
         return fail(TDB200_ERR_UNSUPPORTED, "bits_iters / llr_siso1 are produced by TDB200_ALGO_LOGMAP_F64 only");
+    if (!f64 && c.early_term >= 2 && out->ext_siso2)
+        return fail(TDB200_ERR_UNSUPPORTED, "ext_siso2 is not available with the CRC stopping rule (a block may stop after SISO-1)");
     if (!f64 && c.early_term && out->llr_siso2)
         return fail(TDB200_ERR_UNSUPPORTED, "llr_siso2 is not available with early termination (the stopping iteration is not known in advance)");
 
