@@ -189,6 +189,38 @@ def test_every_lte_block_size(oracle):
         dec.close()
 
 
+@pytest.mark.parametrize("K,early", [(1312, False), (1312, True), (656, False), (656, True), (2624, False), (3136, True)])
+def test_packed_pairs_large_batch(oracle, K, early):
+    """Sub-block counts just above a warp multiple (P = 41; P = 56 where shared memory is the limit) share a CTA between two or three
+    codeblock pairs once the batch is large enough to fill the device; the result stays bit-exact
+    (decisions, and per-pair stopping with early termination), also for the odd last codeblock."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    n_cb, n_iter = 1801, 5
+    pi = oracle.qpp(K)
+    bits, llr = oracle.make_batch(K, n_cb, 1.6, seed=K + 5)
+    llr32 = llr.astype(np.float32)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16", early_term=early, max_batch=2048)
+    plan = dec.plan()
+    assert plan["cb_per_cta"] >= 4, plan
+    out = dec.decode(llr32, want=("bits", "iters_used"))
+    prm = _fx_params(K, n_iter, plan["sub_block"], plan["warmup"])
+    if early:
+        prm.early_term = 1
+        prm.et_threshold = 1 << (prm.frac_bits + 3)
+    for c in (0, 1, 4, 5, 900, 901, 1798, 1799, 1800):
+        it = oracle.fx_decode(llr32[c], pi, prm)[2]
+        mate = c ^ 1 if (c ^ 1) < n_cb else c
+        ran = max(it, oracle.fx_decode(llr32[mate], pi, prm)[2])
+        assert out["iters_used"][c] == it, "cb %d" % c
+        b = oracle.fx_decode(llr32[c], pi, _fx_params(K, ran, plan["sub_block"], plan["warmup"]))[0]
+        assert np.array_equal(out["bits"][c], b.astype(np.uint8)), "cb %d" % c
+    # everything else: at 1.6 dB nearly every block of these sizes decodes to the transmitted bits
+    wrong = (out["bits"] != bits.astype(np.uint8)).any(axis=1)
+    assert wrong.mean() < 0.05
+    dec.close()
+
+
 def test_int8_input_large_batch_and_alignment(oracle):
     """8-bit channel values with more codeblocks than resident CTAs (the next-row L2 prefetch runs;
     byte rows are only 4-byte aligned) and a row-offset view of the buffer; a misaligned device

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -340,9 +341,28 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         g.NP = 1; g.pair_bytes = 0;
         if (s16) {
             g.pair_bytes = fast_s16_pair_bytes(g);
-            // pairs per CTA: fill two warps when a codeblock needs less than one (measured: larger CTAs
-            // only add barrier coupling -- registers cap an SM at eight warps either way)
-            int np = (fast_s16_specialised(g) || g.P >= 32 || c.early_term >= 2) ? 1 : std::max(1, std::min(64 / g.P, 64));  // the CRC fold is per CTA
+            // Pairs per CTA.  Fewer than 32 sub-blocks: fill two warps (measured: larger CTAs only add barrier
+            // coupling -- registers cap an SM at eight or nine warps either way).  33..42 sub-blocks leave most of
+            // the CTA's second warp idle: three pairs share a full 128-thread CTA instead (measured on B200,
+            // tools/tune_pairs.py, profiles/r01_pairs_tuning.json: +40 % at L <= 32, +4 % at L = 64; two pairs in a
+            // 96-thread CTA gain nothing -- three-warp CTAs load the four sub-partitions unevenly).  49..64
+            // sub-blocks: two pairs per CTA only where shared memory admits three single-pair CTAs per SM but two
+            // doubles (K = 3136: +13 %).
+            int np = 1;
+            if (c.early_term < 2) {  // the CRC fold is per CTA
+                const bool packable = !fast_s16_specialised(g) || fast_spec_rt(g);
+                auto ctas_by_smem = [&](int n) {
+                    g.NP = n; g.threads = ((n * g.P + 31) / 32) * 32;
+                    return (int)(prop.sharedMemPerMultiprocessor / ((size_t)fast_s16_smem_bytes(g) + 1024));
+                };
+                if (g.P < 32) np = std::max(1, 64 / g.P);
+                else if (packable && g.P > 32 && 3 * g.P <= 128) np = 3;
+                else if (packable && 2 * g.P <= 128 && 2 * g.P > 96 && ctas_by_smem(1) == 3 && ctas_by_smem(2) >= 2) np = 2;
+                if (const char *e = getenv("TDB200_PAIRS_PER_CTA")) {  // tuning knob (tools/tune_pairs.py)
+                    const int want = atoi(e);
+                    if (want >= 1 && (want == 1 || (packable && want * g.P <= 128))) np = want;
+                }
+            }
             while (np > 1) {
                 g.NP = np; g.threads = ((np * g.P + 31) / 32) * 32;
                 if ((size_t)fast_s16_smem_bytes(g) <= prop.sharedMemPerBlockOptin) break;

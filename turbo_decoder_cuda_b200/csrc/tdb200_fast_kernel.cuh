@@ -608,13 +608,17 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
     const int L = 8 * NW, K = P * L;
     const int W = L * PP;            // words per array
     const int Wp = (W + 7) & ~7;     // every region starts 16-byte aligned
-    const int NP = KP ? 1 : A.pairs_per_cta;  // codeblock pairs this CTA decodes side by side (small K)
+    // codeblock pairs this CTA decodes side by side: short blocks, and sub-block counts that would leave
+    // most of a CTA's last warp idle (P = 41: three pairs fill 123 of 128 lanes instead of 41 of 64)
+    constexpr bool kSingle = KP > 0 || KP == -2;  // kernels that never pack (P > 128 has no room for a second pair)
+    const int NP = kSingle ? 1 : A.pairs_per_cta;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int n_pairs = (A.n_cb + 1) / 2;
     // thread -> (pair slot q, sub-block t)
-    const int q = KP ? 0 : tid / P, t = KP ? tid : tid - q * P;
+    const int q = kSingle ? 0 : tid / P, t = kSingle ? tid : tid - q * P;
     const int pair = blockIdx.x * NP + q;
-    const bool active = KP > 0 ? true : (KP < 0 ? tid < P : (q < NP && pair < n_pairs));
+    const bool active = KP > 0 ? true : (kSingle ? tid < P : (q < NP && pair < n_pairs));
+    const bool one_pair = kSingle || NP == 1;  // CTA-uniform
     const Smem sm = pair_smem(smem_raw, g, P, NW, Wp, NP, active ? q : 0);
     unsigned *flags = reinterpret_cast<unsigned *>(sm.edge + 16 * (nthr >> 5));
     const int cbA = 2 * (active ? pair : 0);
@@ -664,12 +668,13 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
     // ---- pull the rows of the codeblock pair that will run on this SM slot next into L2 (bulk
     //      prefetch, a few KB per instruction; rows are 16-byte multiples)
     if (KP && A.prefetch_stride > 0) {
-        const long long nxt = (long long)2 * (blockIdx.x + A.prefetch_stride);
+        const long long nxt = (long long)2 * NP * (blockIdx.x + A.prefetch_stride);
         if (nxt < A.n_cb) {
+            const long long nrows = (A.n_cb - nxt < 2 * NP) ? (A.n_cb - nxt) : 2 * NP;
             const size_t esz = LLR_T == TDB200_LLR_F64 ? 8 : (LLR_T == TDB200_LLR_F32 ? 4 : (LLR_T == TDB200_LLR_F16 ? 2 : 1));
             // 16-byte granules: with one-byte channel values a row pair starts on an 8-byte boundary
             const size_t b0 = reinterpret_cast<size_t>(A.llr) + (size_t)nxt * row * esz;
-            const size_t lo = b0 & ~(size_t)15, hi = (b0 + (nxt + 1 < A.n_cb ? 2 : 1) * row * esz) & ~(size_t)15;
+            const size_t lo = b0 & ~(size_t)15, hi = (b0 + (size_t)nrows * row * esz) & ~(size_t)15;
             const char *p = reinterpret_cast<const char *>(lo);
             const size_t nbytes = hi - lo;
             const size_t chunk = 4096;
@@ -747,7 +752,7 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                 // a-posteriori value is weaker than the threshold -- per codeblock; a CTA leaves when
                 // all its codeblocks have stopped
                 int chA, chB;
-                if (KP) {
+                if (one_pair) {
                     chA = __syncthreads_or((int)((chg | weak) & 0xffffu));
                     chB = __syncthreads_or((int)((chg | weak) >> 16));
                 } else {
@@ -762,8 +767,8 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                     if (!chA && !usedA) usedA = it + 1;
                     if (!chB && !usedB) usedB = it + 1;
                 }
-                const bool done = (usedA && usedB) || (!KP && !active);  // with one pair per CTA the flags are CTA-uniform
-                if (KP ? done : (__syncthreads_and((int)done) != 0)) { used = it + 1; break; }
+                const bool done = (usedA && usedB) || (!one_pair && !active);  // with one pair per CTA the flags are CTA-uniform
+                if (one_pair ? done : (__syncthreads_and((int)done) != 0)) { used = it + 1; break; }
             }
         } else {
             siso_pass<true, false, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed, nullptr, weak);

@@ -89,7 +89,7 @@ struct FastGeom {
     int n_ckpt;      // alpha checkpoints kept in shared memory per thread: max(NW-2, 0)
     int smem_bytes;
     int resident_ctas;  // CTAs of this geometry the whole device holds at once
-    int NP;             // codeblock pairs one CTA can decode side by side (1 for K >= 4096)
+    int NP;             // codeblock pairs one CTA decodes side by side (planner rule in tdb200_create; 1 for compile-time geometry)
     int pair_bytes;     // shared memory of one pair's region
 };
 
