@@ -189,18 +189,20 @@ def test_every_lte_block_size(oracle):
         dec.close()
 
 
-@pytest.mark.parametrize("K,early", [(1312, False), (1312, True), (656, False), (656, True), (2624, False), (3136, True)])
-def test_packed_pairs_large_batch(oracle, K, early):
+@pytest.mark.parametrize("K,early,n_cb", [(1312, False, 1801), (1312, True, 1801), (656, False, 1801), (656, True, 1801),
+                                          (2624, False, 1801), (3136, True, 1801), (512, False, 2401), (512, True, 2401),
+                                          (960, True, 1801)])
+def test_packed_pairs_large_batch(oracle, K, early, n_cb):
     """Sub-block counts just above a warp multiple (P = 41; P = 56 where shared memory is the limit) share a CTA between two or three
     codeblock pairs once the batch is large enough to fill the device; the result stays bit-exact
     (decisions, and per-pair stopping with early termination), also for the odd last codeblock."""
     _torch_cuda()
     from turbo_decoder_cuda_b200 import TurboDecoder
-    n_cb, n_iter = 1801, 5
+    n_iter = 5
     pi = oracle.qpp(K)
     bits, llr = oracle.make_batch(K, n_cb, 1.6, seed=K + 5)
     llr32 = llr.astype(np.float32)
-    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16", early_term=early, max_batch=2048)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="maxlog_s16", early_term=early, max_batch=4096)
     plan = dec.plan()
     assert plan["cb_per_cta"] >= 4, plan
     out = dec.decode(llr32, want=("bits", "iters_used"))
@@ -208,7 +210,7 @@ def test_packed_pairs_large_batch(oracle, K, early):
     if early:
         prm.early_term = 1
         prm.et_threshold = 1 << (prm.frac_bits + 3)
-    for c in (0, 1, 4, 5, 900, 901, 1798, 1799, 1800):
+    for c in (0, 1, 4, 5, 900, 901, n_cb - 3, n_cb - 2, n_cb - 1):
         it = oracle.fx_decode(llr32[c], pi, prm)[2]
         mate = c ^ 1 if (c ^ 1) < n_cb else c
         ran = max(it, oracle.fx_decode(llr32[mate], pi, prm)[2])

@@ -141,8 +141,9 @@ int f32_smem_bytes(const FastGeom &g);
 inline bool fast_spec_pn(const FastGeom &g) { return (g.P == 32 || g.P == 64 || g.P == 128) && g.NW >= 4 && g.NW <= 6 && g.G == 16 && g.PP == (g.P | 1); }
 inline bool fast_spec128g8(const FastGeom &g) { return g.P == 128 && g.NW == 6 && g.G == 8 && g.PP == 129; }
 inline bool fast_spec192(const FastGeom &g) { return g.P == 192 && g.NW == 4 && g.G == 16 && g.PP == 193; }
-// every other plan with 33..128 sub-blocks of 32..64 steps and guard 16: P at run time, NW and G compile-time
-inline bool fast_spec_rt(const FastGeom &g) { return !fast_spec_pn(g) && g.P > 32 && g.P <= 128 && g.NW >= 4 && g.NW <= 8 && g.G == 16 && g.PP == (g.P | 1); }
+// every other plan with 2..128 sub-blocks of 32..64 steps and guard 16: P at run time, NW and G compile-time
+// (CTAs of up to 128 threads; below 43 sub-blocks several codeblock pairs share one)
+inline bool fast_spec_rt(const FastGeom &g) { return !fast_spec_pn(g) && g.P >= 2 && g.P <= 128 && g.NW >= 4 && g.NW <= 8 && g.G == 16 && g.PP == (g.P | 1); }
 // 129..192 sub-blocks of 32 or 40 steps: six warps per CTA at 168 registers, two CTAs per SM
 inline bool fast_spec_rt192(const FastGeom &g) { return !fast_spec192(g) && g.P > 128 && g.P <= 192 && (g.NW == 4 || g.NW == 5) && g.G == 16 && g.PP == (g.P | 1); }
 
