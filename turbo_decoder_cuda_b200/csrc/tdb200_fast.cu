@@ -47,15 +47,21 @@ bool fast_s16_specialised(const FastGeom &g) { return fast_spec_pn(g) || fast_sp
 int fast_s16_pair_bytes(const FastGeom &g)
 {
     const int W = g.L * g.PP, Wp = (W + 7) & ~7;
-    const int b = 3 * 4 * Wp + 2 * Wp + 4 * g.n_ckpt * 7 * g.P + 4 * ((g.NW + 1) / 2) * g.P;
-    return (b + 15) & ~15;
+    int b = 3 * 4 * Wp + 2 * Wp + 4 * g.n_ckpt * 7 * g.P + 4 * ((g.NW + 1) / 2) * g.P;
+    b = (b + 3) & ~3;
+    // Pairs that share a CTA sit side by side; thread (pair q, sub-block t) reads word q * stride + j * PP + t.
+    // With stride = P (mod 32 words) that is bank tid + const: conflict-free across the pairs of a warp (a stride
+    // that is a multiple of 16 words put K = 64 on 4 banks).
+    if (g.P <= 64)
+        while (((b / 4) & 31) != (g.P & 31)) b += 4;
+    return b;
 }
 static int shared_bytes(const FastGeom &g, int threads, int np)
 {
     const int W = g.L * g.PP, Wp = (W + 7) & ~7;
     return 2 * Wp + 4 * 16 * (threads / 32) + 4 * ((np + 3) & ~3);
 }
-int fast_s16_smem_bytes(const FastGeom &g) { return g.pair_bytes * g.NP + shared_bytes(g, g.threads, g.NP); }
+int fast_s16_smem_bytes(const FastGeom &g) { return ((g.pair_bytes * g.NP + 15) & ~15) + shared_bytes(g, g.threads, g.NP); }
 
 cudaError_t fast_s16_configure(FastGeom &g, int sm_count)
 {
@@ -87,7 +93,7 @@ cudaError_t launch_fast_s16(const FastArgs &a0, cudaStream_t st, int *n_launches
     while (np > 1 && (pairs + np - 1) / np < 2 * a.sm_count) np = (np + 1) / 2;
     a.pairs_per_cta = np;
     const int threads = ((np * a.g.P + 31) / 32) * 32;
-    const int smem = a.g.pair_bytes * np + shared_bytes(a.g, threads, np);
+    const int smem = ((a.g.pair_bytes * np + 15) & ~15) + shared_bytes(a.g, threads, np);
     pick_kernel(a.g, a.llr_type, a.early_term == 2)<<<(pairs + np - 1) / np, threads, smem, st>>>(a);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();

@@ -547,7 +547,7 @@ __device__ __forceinline__ Smem pair_smem(unsigned char *raw, const FastGeom &g,
     sm.sysB = sm.sysA + Wp;
     sm.ckpt = reinterpret_cast<w32 *>(sm.sysB + Wp);
     sm.dec = sm.ckpt + (size_t)g.n_ckpt * 7 * P;
-    unsigned char *sh = raw + (size_t)NP * g.pair_bytes;
+    unsigned char *sh = raw + (((size_t)NP * g.pair_bytes + 15) & ~(size_t)15);  // pair regions are word-aligned only (bank-staggered)
     sm.tab = reinterpret_cast<uint16_t *>(sh);
     sm.edge = reinterpret_cast<w32 *>(sm.tab + Wp);
     return sm;
@@ -631,29 +631,31 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
     // ---- load + quantise + de-multiplex (once per decode); element n = tt*L + j -> word j*PP + tt.
     //      NG groups of loads (NG x 2 codeblocks x 48 bytes) are in flight per thread before the
     //      first is consumed: the phase is pure load latency, so depth is what shortens it.
-    for (int p = 0; p < NP; p++) {
-        const int pr = blockIdx.x * NP + p;
-        if (pr >= n_pairs) break;
-        const Smem smp = pair_smem(smem_raw, g, P, NW, Wp, NP, p);
-        const int a_cb = 2 * pr, b_cb = (a_cb + 1 < A.n_cb) ? a_cb + 1 : a_cb;
+    //      With several pairs per CTA the groups of all pairs form one index space, so that short blocks
+    //      (K/4 groups per pair < CTA size) still keep every thread loading.
+    {
+        const int np_here = kSingle ? 1 : min(NP, n_pairs - (int)blockIdx.x * NP);
         constexpr int NG = (LLR_T == TDB200_LLR_F64) ? 2 : 4;
         const w32 clipv = dup2(clip), nclipv = dup2(-clip);
-        const int nq = K / 4;
-        for (int q0 = tid; q0 < nq; q0 += NG * nthr) {
+        const int nq = K / 4, total = np_here * nq;
+        for (int i0 = tid; i0 < total; i0 += NG * nthr) {
             Raw12<LLR_T> ra[NG], rb[NG];
 #pragma unroll
             for (int j = 0; j < NG; j++) {
-                const int qq = min(q0 + j * nthr, nq - 1);  // the clamp re-reads the last group instead of branching
+                const int ii = min(i0 + j * nthr, total - 1);  // the clamp re-reads the last group instead of branching
+                const int p = one_pair ? 0 : ii / nq, qq = ii - p * nq;
+                const int a_cb = 2 * ((int)blockIdx.x * NP + p), b_cb = (a_cb + 1 < A.n_cb) ? a_cb + 1 : a_cb;
                 load12<LLR_T>(A.llr, row, a_cb, qq, ra[j]);
                 load12<LLR_T>(A.llr, row, b_cb, qq, rb[j]);
             }
 #pragma unroll
             for (int j = 0; j < NG; j++) {
-                const int qq = q0 + j * nthr;
-                if (qq < nq) {
+                const int ii = i0 + j * nthr;
+                if (ii < total) {
+                    const int p = one_pair ? 0 : ii / nq, qq = ii - p * nq;
                     w32 v[12];
                     pack12<LLR_T>(ra[j], rb[j], scale, clipv, nclipv, v);
-                    put4(smp, qq, L, PP, v);
+                    put4(pair_smem(smem_raw, g, P, NW, Wp, NP, p), qq, L, PP, v);
                 }
             }
         }
@@ -802,16 +804,16 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
             }
         }
         __syncthreads();
-        for (int p = 0; p < NP; p++) {
-            const int pr = blockIdx.x * NP + p;
-            if (pr >= n_pairs) break;
-            const Smem smp = pair_smem(smem_raw, g, P, NW, Wp, NP, p);
-            const uint32_t *wa = reinterpret_cast<const uint32_t *>(smp.par2), *wb = wa + K / 4;
-            const bool pB = 2 * pr + 1 < A.n_cb;
-            uint32_t *oa = reinterpret_cast<uint32_t *>(A.bits + (size_t)(2 * pr) * K), *ob = oa + K / 4;
-            for (int i = tid; i < K / 4; i += nthr) {
+        {   // the pairs of a CTA are consecutive rows of the output: one index space over all of them
+            const int np_here = kSingle ? 1 : min(NP, n_pairs - (int)blockIdx.x * NP);
+            const int nw = K / 4, total = np_here * nw;
+            for (int ii = tid; ii < total; ii += nthr) {
+                const int p = one_pair ? 0 : ii / nw, i = ii - p * nw;
+                const int pr = blockIdx.x * NP + p;
+                const uint32_t *wa = reinterpret_cast<const uint32_t *>(pair_smem(smem_raw, g, P, NW, Wp, NP, p).par2), *wb = wa + nw;
+                uint32_t *oa = reinterpret_cast<uint32_t *>(A.bits + (size_t)(2 * pr) * K), *ob = oa + nw;
                 oa[i] = wa[i];
-                if (pB) ob[i] = wb[i];
+                if (2 * pr + 1 < A.n_cb) ob[i] = wb[i];
             }
         }
     }
