@@ -24,3 +24,4 @@ python tools/time_transport.py --json $o/${tag}_transport_timing.json > /dev/nul
 python tools/profile_callers.py > $o/${tag}_plain_callers.log 2>&1 &&
 ncu --set full --clock-control none -k regex:"demap|rate_|crc24|modulate|awgn" -c 14 -o $o/${tag}_prof_callers -f python tools/profile_callers.py > $o/${tag}_ncu_callers.log 2>&1
 tail -1 $o/${tag}_ncu_callers.log | cut -c1-160
+python tools/sweep_all_sizes.py --json $o/${tag}_all_sizes_auto_plan.json > $o/${tag}_all_sizes.log 2>&1; tail -1 $o/${tag}_all_sizes.log | cut -c1-200
