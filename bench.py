@@ -142,7 +142,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "ber": errs / float(n_sample * K * args.steps),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, batch, plan):
@@ -371,12 +371,31 @@ def run_ours(args):
                 "value": n_sample * K / secs / 1e9, "unit": "Gbit/s", "cores": cores, "kind": kind,
                 "sample": "first %d codeblocks of the batch, fp64 LUT Log-MAP, 8 iterations, one codeword per thread, %.1f s" % (n_sample, secs),
                 "ber": float((out != bits[:n_sample].cpu().numpy()).sum()) / (n_sample * K)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner, when the
+    # environment sets NCCL_DEBUG) is sent to stderr instead
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
