@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TDB200_VERSION 5
+#define TDB200_VERSION 6
 
 typedef enum tdb200_status {
     TDB200_OK = 0,
@@ -58,7 +58,15 @@ typedef enum tdb200_algo {
     /* fp32 Log-MAP with the linear correction max(0, 0.24904 (2.5068 - |x-y|)) instead of the exact one:
      * no special-function unit on the critical path, about 2.5x the speed of TDB200_ALGO_LOGMAP_F32 at
      * the same FER.  Bit-exact against its plain-C model. */
-    TDB200_ALGO_LINLOGMAP_F32 = 4
+    TDB200_ALGO_LINLOGMAP_F32 = 4,
+    /* Log-MAP in the packed 16-bit arithmetic of TDB200_ALGO_MAXLOG_S16 (two codeblocks per 32-bit lane, same
+     * sub-block schedule, one CTA per codeblock pair for all iterations): every max of the alpha, beta and
+     * a-posteriori computations is max*(x,y) = max + c(|x-y|) with the linear correction
+     * c = max(0, 0.625 - |x-y|/4), the reference's E_algorithm() table (log_map.cpp:779-801, :14-18) fitted by a
+     * line, evaluated on quarter-differences shared by the two max* of a trellis butterfly.  Extrinsic scale 1.0
+     * as in the reference, 4 fractional bits, guard 32 by default.  The throughput mode that sits on the
+     * reference's BER/FER curve; bit-exact against its integer model (oracle/turbo_oracle_fx.c, logmap = 1). */
+    TDB200_ALGO_LOGMAP_S16 = 5
 } tdb200_algo;
 
 /* Element type of the channel-LLR input. */
@@ -96,11 +104,11 @@ typedef struct tdb200_config {
                          (1 = decisions only).  0 = default: 2^(frac_bits+3), i.e. |LLR| >= 8 */
     int ext_scale_q2; /* extrinsic scaling in quarters for the max-log modes: 3 = 0.75, 4 = 1.0;
                          0 = default (3 for max-log, 4 for Log-MAP) */
-    int frac_bits;  /* fixed-point fractional bits of TDB200_ALGO_MAXLOG_S16 and of
-                       TDB200_LLR_S8 input; 0 = default (3) */
+    int frac_bits;  /* fixed-point fractional bits of TDB200_ALGO_MAXLOG_S16 / _LOGMAP_S16 and of
+                       TDB200_LLR_S8 input; 0 = default (3 for max-log, 4 for Log-MAP) */
     int ext_clip;   /* TDB200_ALGO_MAXLOG_S16: extrinsic values are clamped to [-(ext_clip+1), ext_clip]
                        (fixed-point units); ext_clip+1 must be a multiple of 4.
-                       0 = default: 2^(frac_bits+6) - 1, i.e. |Le| < 64 */
+                       0 = default: 2^(frac_bits+6) - 1, i.e. |Le| < 64 (511 for TDB200_ALGO_LOGMAP_S16) */
     int device;     /* CUDA device ordinal */
     int max_batch;  /* codeblocks the workspace is sized for per launch; larger batches are
                        processed in chunks.  0 = default for the algo */

@@ -93,6 +93,12 @@ typedef struct tdo_fx_params {
     int et_threshold; /* fixed-point units; values < 1 are treated as 1 */
     int crc_poly;     /* early_term == 2: stop when the natural-order decisions of SISO-1 (second iteration
                          on) divide by x^24 + crc_poly; the delivered bits are then those decisions */
+    int logmap;       /* 1: TDB200_ALGO_LOGMAP_S16 -- max* with the linear correction (see turbo_oracle_fx.c) */
+    int lm_t4;        /* correction at d = 0 in fixed-point units; 0 = 5 << (frac_bits - 3) */
+    int lm_upper;     /* exploration: upper levels of the a-posteriori trees 0 linear / 1 trapezoid / 2 uncorrected */
+    int lm_tt, lm_tc; /* exploration: trapezoid parameters */
+    int lm_warm_maxlog; /* exploration: warm-up recursions without the correction */
+    int lm_upper_off; /* exploration */
 } tdo_fx_params;
 
 /* Returns the number of iterations run.  bits_out[K] final decisions; le_out

@@ -93,6 +93,110 @@ static int extrinsic(const int *a, const int *b, int v)
     return chk(m1 - m0);
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * Log-MAP in the same packed-16-bit arithmetic (TDB200_ALGO_LOGMAP_S16): max*(x,y) = max(x,y) +
+ * c(|x-y|), the Jacobian logarithm the reference evaluates through E_algorithm()'s 16-step table
+ * (ITTC/log_map.cpp:779-801, table :14-18), here as the linear fit c = max(0, T4 - |d|/4) in units of
+ * 2^-frac_bits (T4 = 5 at 3 fractional bits: 0.625 - d/4; the least-squares line is 0.249(2.507 - d)).
+ * The difference d never exists at full resolution: the two max* of a trellis butterfly share the
+ * state-metric difference D = p - q, and d/4 is formed from floor((D-1)/4) and floor(g/4) (g = the
+ * butterfly's branch-metric difference), which is what makes the correction cost one shift per
+ * butterfly instead of one per max* on the device (there is no packed 16-bit shift instruction).
+ * ------------------------------------------------------------------------------------------ */
+static __thread int g_T4;      /* correction at d = 0, in fixed-point units */
+static __thread int g_upper;   /* how the upper levels of the a-posteriori max* trees are corrected: 0 linear, 1 trapezoid, 2 not at all */
+static __thread int g_uoff;    /* rounding offset of the generic max* */
+static __thread int g_TT, g_TC;   /* trapezoid: c = min(TC, max(0, TT - |d|)) */
+
+static inline int asr2(int x) { return x >> 2; } /* arithmetic shift: floor(x / 4) */
+static inline int relu(int x) { return x > 0 ? x : 0; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+
+/* corrections of the two max* of a butterfly: ca for max*(p + g, q), cb for max*(q + g, p); g4 = floor(g / 4) */
+static inline void bfly_corr(int p, int q, int g4, int *ca, int *cb)
+{
+    const int h = asr2(chk(p - q - 1)), nh = -h - 1;
+    *ca = relu(imin(h + g4 + 1 + g_T4, nh - g4 + g_T4));
+    *cb = relu(imin(nh + g4 + 1 + g_T4, h - g4 + g_T4));
+}
+
+static void alpha_step_lm(const int *a, int u, int v, int *o)
+{
+    const int w = add(u, v), w4 = asr2(w), gm4 = asr2(chk(u - v - 1));
+    int ca, cb;
+    bfly_corr(a[1], a[0], w4, &ca, &cb);
+    o[0] = add(imax(add(a[1], w), a[0]), ca);
+    o[4] = add(imax(add(a[0], w), a[1]), cb);
+    bfly_corr(a[3], a[2], gm4, &ca, &cb);
+    o[5] = add(imax(add(a[3], u), add(a[2], v)), ca);
+    o[1] = add(imax(add(a[2], u), add(a[3], v)), cb);
+    bfly_corr(a[5], a[4], gm4, &ca, &cb);
+    o[2] = add(imax(add(a[5], u), add(a[4], v)), ca);
+    o[6] = add(imax(add(a[4], u), add(a[5], v)), cb);
+    bfly_corr(a[7], a[6], w4, &ca, &cb);
+    o[7] = add(imax(add(a[7], w), a[6]), ca);
+    o[3] = add(imax(add(a[6], w), a[7]), cb);
+}
+
+static void beta_step_lm(const int *b, int u, int v, int *o)
+{
+    const int w = add(u, v), w4 = asr2(w), gm4 = asr2(chk(u - v - 1));
+    int ca, cb;
+    bfly_corr(b[4], b[0], w4, &ca, &cb);
+    o[0] = add(imax(add(b[4], w), b[0]), ca);
+    o[1] = add(imax(add(b[0], w), b[4]), cb);
+    bfly_corr(b[1], b[5], gm4, &ca, &cb);
+    o[2] = add(imax(add(b[1], u), add(b[5], v)), ca);
+    o[3] = add(imax(add(b[5], u), add(b[1], v)), cb);
+    bfly_corr(b[6], b[2], gm4, &ca, &cb);
+    o[4] = add(imax(add(b[6], u), add(b[2], v)), ca);
+    o[5] = add(imax(add(b[2], u), add(b[6], v)), cb);
+    bfly_corr(b[3], b[7], w4, &ca, &cb);
+    o[6] = add(imax(add(b[3], w), b[7]), ca);
+    o[7] = add(imax(add(b[7], w), b[3]), cb);
+}
+
+/* max* of two values that share nothing with anything else (the upper levels of the a-posteriori trees) */
+static inline int maxstar_generic(int x, int y)
+{
+    const int mx = imax(x, y), mn = imin(x, y);
+    const int e1 = chk(mn - mx - 1); /* -|d| - 1 */
+    int c;
+    if (g_upper == 2) c = 0;
+    else if (g_upper == 1) c = imin(g_TC, relu(e1 + 1 + g_TT));
+    else c = relu(asr2(e1) + g_uoff + g_T4);
+    return add(mx, c);
+}
+
+/* first level of the a-posteriori trees: the four terms alpha_i + beta_m, alpha_j + beta_n (input 0) and
+ * alpha_i + beta_n, alpha_j + beta_m (input 1) of a state pair (i, j) x (m, n); p = (aj, ai), q = (bn, bm)
+ * oriented like the butterflies of the recursions, so hA and hB are the shifts those already formed */
+static inline void lam_pair(int ai, int aj, int bm, int bn, int *same, int *cross)
+{
+    /* same: max*(aj + bn, ai + bm), d = (aj - ai) + (bn - bm);  cross: max*(aj + bm, ai + bn), d = (aj - ai) - (bn - bm) */
+    const int hA = asr2(chk(aj - ai - 1)), nhA = -hA - 1;
+    const int hB = asr2(chk(bn - bm - 1)), nhB = -hB - 1;
+    const int c1 = relu(imin(hA + hB + 1 + g_T4, nhA + nhB + 1 + g_T4));
+    const int c2 = relu(imin(hA + nhB + 1 + g_T4, nhA + hB + 1 + g_T4));
+    *same = add(imax(add(aj, bn), add(ai, bm)), c1);
+    *cross = add(imax(add(aj, bm), add(ai, bn)), c2);
+}
+
+static int extrinsic_lm(const int *a, const int *b, int v)
+{
+    int s01, x01, s67, x67, s23, x23, s45, x45;
+    lam_pair(a[0], a[1], b[0], b[4], &s01, &x01); /* input 0: a0+b0, a1+b4;  input 1: a1+b0, a0+b4 */
+    lam_pair(a[6], a[7], b[7], b[3], &s67, &x67); /* input 0: a6+b7, a7+b3;  input 1: a7+b7, a6+b3 */
+    lam_pair(a[2], a[3], b[5], b[1], &s23, &x23); /* input 0 (+v): a2+b5, a3+b1;  input 1: a3+b5, a2+b1 */
+    lam_pair(a[4], a[5], b[2], b[6], &s45, &x45); /* input 0 (+v): a4+b2, a5+b6;  input 1: a5+b2, a4+b6 */
+    const int m0a = maxstar_generic(s01, s67), m0b = maxstar_generic(s23, s45);
+    const int m1a = maxstar_generic(x01, x67), m1b = maxstar_generic(x23, x45);
+    const int m0 = maxstar_generic(m0a, add(m0b, v));
+    const int m1 = maxstar_generic(add(m1a, v), m1b);
+    return chk(m1 - m0);
+}
+
 static void normalise(int *m)
 {
     int z = m[0];
@@ -107,6 +211,13 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
     if (L < 8 || L % 8 || K % L || G < 0 || G % 8 || G > L) return -1;
     const int P = K / L;
     g_ovf = 0;
+    const int lm = p->logmap, lmw = lm && !p->lm_warm_maxlog;
+    g_T4 = p->lm_t4 > 0 ? p->lm_t4 : 5 << (F > 3 ? F - 3 : 0);
+    g_upper = p->lm_upper;
+    g_TT = p->lm_tt; g_TC = p->lm_tc;
+    g_uoff = p->lm_upper_off;
+#define ASTEP(lmf, a_, u_, v_, o_) ((lmf) ? alpha_step_lm(a_, u_, v_, o_) : alpha_step(a_, u_, v_, o_))
+#define BSTEP(lmf, b_, u_, v_, o_) ((lmf) ? beta_step_lm(b_, u_, v_, o_) : beta_step(b_, u_, v_, o_))
 
     int *ys = (int *)malloc(sizeof(int) * K), *yp1 = (int *)malloc(sizeof(int) * K);
     int *yp2 = (int *)malloc(sizeof(int) * K), *X = (int *)malloc(sizeof(int) * K);
@@ -138,7 +249,7 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
         for (int m = 2; m >= 0; m--) {
             int u = quant(llr_in[3 * K + 6 * s + 2 * m], F, p->llr_clip);
             int v = quant(llr_in[3 * K + 6 * s + 2 * m + 1], F, p->llr_clip);
-            beta_step(b, u, v, o);
+            BSTEP(lm, b, u, v, o);
             memcpy(b, o, sizeof(b));
         }
         normalise(b);
@@ -164,7 +275,7 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                     for (int k = -G; k < 0; k++) {
                         int i = t * L + k, n = s ? pi[i] : i;
                         if ((k + G) % 8 == 0) normalise(a);
-                        alpha_step(a, Xold[n], yp[i], o);
+                        ASTEP(lmw, a, Xold[n], yp[i], o);
                         memcpy(a, o, sizeof(o));
                     }
                 /* ---- beta warm-up over the first G steps of sub-block t+1 */
@@ -173,7 +284,7 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                     for (int k = G - 1; k >= 0; k--) {
                         int i = (t + 1) * L + k, n = s ? pi[i] : i;
                         if (k % 8 == 7) normalise(b);
-                        beta_step(b, Xold[n], yp[i], o);
+                        BSTEP(lmw, b, Xold[n], yp[i], o);
                         memcpy(b, o, sizeof(b));
                     }
                 /* ---- forward: alpha at every step of the sub-block, normalised at window starts */
@@ -181,7 +292,7 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                     int i = t * L + k, n = s ? pi[i] : i;
                     if (k % 8 == 0) normalise(a + k * NS);
                     if (k == L - G) memcpy(newA[t], a + k * NS, sizeof(int) * NS);
-                    alpha_step(a + k * NS, X[n], yp[i], a + (k + 1) * NS);
+                    ASTEP(lm, a + k * NS, X[n], yp[i], a + (k + 1) * NS);
                 }
                 if (G == 0) memcpy(newA[t], a + L * NS, sizeof(int) * NS);
                 normalise(newA[t]);
@@ -191,11 +302,11 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                     int i = t * L + k, n = s ? pi[i] : i;
                     if (k % 8 == 7) normalise(b);
                     int u = X[n], v = yp[i];
-                    int e = extrinsic(a + k * NS, b, v);
+                    int e = lm ? extrinsic_lm(a + k * NS, b, v) : extrinsic(a + k * NS, b, v);
                     int lam = add(u, e);
                     int ec = e > p->ext_clip ? p->ext_clip : (e < -p->ext_clip - 1 ? -p->ext_clip - 1 : e); /* [-2^n, 2^n-1] */
                     int es = (p->ext_scale_q2 == 3) ? ((3 * ec) >> 2) : ec;
-                    beta_step(b, u, v, o);
+                    BSTEP(lm, b, u, v, o);
                     memcpy(b, o, sizeof(b));
                     X[n] = add(ys[n], es);
                     if (k == G) memcpy(newB[t], b, sizeof(b));

@@ -43,7 +43,8 @@ def build_oracle(force=False):
 class FxParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "K", "n_iter", "sub_len", "warmup", "frac_bits", "llr_clip", "ext_clip",
-        "ext_scale_q2", "early_term", "et_threshold", "crc_poly")]
+        "ext_scale_q2", "early_term", "et_threshold", "crc_poly",
+        "logmap", "lm_t4", "lm_upper", "lm_tt", "lm_tc", "lm_warm_maxlog", "lm_upper_off")]
 
 
 class F32Params(C.Structure):

@@ -1,0 +1,153 @@
+"""GPU parity of TDB200_ALGO_LOGMAP_S16 -- Log-MAP (max* with the linear correction) in the packed 16-bit
+arithmetic of the throughput kernel -- through the C ABI.
+
+Integer work -> the bar is BIT-EXACT: hard decisions, extrinsics and iteration counts must equal the int32
+specification oracle/turbo_oracle_fx.c (logmap = 1) on the same seeded inputs, for compile-time and run-time
+geometries, both fixed-point formats, every input type, ragged batches and saturated inputs.  How this mode
+relates to the reference's fp64 Log-MAP (ITTC/log_map.cpp:898-1047 with E_algorithm :779-801) is statistical
+and is tested in test_gpu_ber.py (same frames through both decoders).
+"""
+import numpy as np
+import pytest
+
+from oracle_lib import FxParams
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def lm_params(K, n_iter, L, G, F=4, ext_clip=511, early_term=0, et_threshold=0):
+    return FxParams(K=K, n_iter=n_iter, sub_len=L, warmup=G, frac_bits=F, llr_clip=127, ext_clip=ext_clip,
+                    ext_scale_q2=4, early_term=early_term, et_threshold=et_threshold, logmap=1, lm_upper_off=1)
+
+
+def _check(oracle, dec, llr_in, llr_f32, pi, prm, n_cb, K, iters=None):
+    out = dec.decode(llr_in, want=("bits", "ext_siso2", "llr_siso2", "iters_used"))
+    out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+    scale = float(1 << prm.frac_bits)
+    for c in range(n_cb):
+        bits, le, it, ovf = oracle.fx_decode(llr_f32[c], pi, prm, want_le=True)
+        assert ovf == 0, "int16 range exceeded in the specification model"
+        assert np.array_equal(out["bits"][c], bits.astype(np.uint8)), "hard decisions differ (cb %d)" % c
+        got = np.rint(out["ext_siso2"][c][:K] * scale).astype(np.int32)
+        assert np.array_equal(got, le[pi]), "extrinsics differ (cb %d)" % c
+        lam = out["llr_siso2"][c][:K]
+        assert np.array_equal((lam >= 0).astype(np.uint8), bits[pi].astype(np.uint8))
+        assert out["iters_used"][c] == (prm.n_iter if iters is None else iters[c])
+
+
+@pytest.mark.parametrize("K,L,G,n_cb,n_iter,ebn0", [
+    (6144, 0, 0, 5, 8, 0.4),     # auto plan (L=48, G=32): compile-time geometry, odd batch, waterfall
+    (6144, 48, 16, 2, 4, 0.4),   # the faster guard
+    (6144, 96, 32, 2, 3, 0.4),   # run-time geometry
+    (5120, 40, 32, 3, 3, 0.8),
+    (4096, 32, 16, 3, 3, 0.8),
+    (6144, 24, 24, 2, 2, 0.8),   # guard == sub-block length
+    (40, 40, 0, 7, 6, 2.0),      # single sub-block: the unsegmented recursion
+    (40, 8, 8, 4, 4, 2.0),
+    (512, 16, 16, 4, 5, 1.5),
+    (1008, 0, 0, 3, 4, 1.0),     # P = 21: not a warp multiple, several pairs per CTA
+    (2048, 64, 16, 2, 4, 1.0),
+])
+def test_bit_exact_vs_fixed_point_model(oracle, K, L, G, n_cb, n_iter, ebn0):
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, n_cb, ebn0, seed=177 + K + L)
+    llr32 = llr.astype(np.float32)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="logmap_s16", sub_block=L, warmup=G)
+    plan = dec.plan()
+    if L == 0 and K == 6144:
+        assert (plan["sub_block"], plan["warmup"]) == (48, 32)
+    prm = lm_params(K, n_iter, plan["sub_block"], plan["warmup"])
+    _check(oracle, dec, torch.from_numpy(llr32).cuda(), llr32, pi, prm, n_cb, K)   # device path
+    _check(oracle, dec, llr32, llr32, pi, prm, n_cb, K)                             # host path
+
+
+@pytest.mark.parametrize("F,ec", [(3, 511), (4, 255), (3, 1023)])
+def test_fixed_point_formats(oracle, F, ec):
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_cb, n_iter = 1024, 4, 5
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, n_cb, 1.0, seed=31)
+    llr32 = llr.astype(np.float32)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="logmap_s16", frac_bits=F, ext_clip=ec)
+    plan = dec.plan()
+    _check(oracle, dec, llr32, llr32, pi, lm_params(K, n_iter, plan["sub_block"], plan["warmup"], F, ec), n_cb, K)
+
+
+def test_input_types(oracle):
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_cb, n_iter = 768, 3, 4
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, n_cb, 1.2, seed=8)
+    llr32 = llr.astype(np.float32)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="logmap_s16")
+    plan = dec.plan()
+    prm = lm_params(K, n_iter, plan["sub_block"], plan["warmup"])
+    _check(oracle, dec, llr, llr32, pi, prm, n_cb, K)
+    q = np.clip(np.rint(llr32 * 16.0), -127, 127).astype(np.int8)     # 4 fractional bits
+    _check(oracle, dec, q, (q.astype(np.float32) / 16.0), pi, prm, n_cb, K)
+    h = llr32.astype(np.float16)
+    _check(oracle, dec, h, h.astype(np.float32), pi, prm, n_cb, K)
+    _check(oracle, dec, torch.from_numpy(h).cuda(), h.astype(np.float32), pi, prm, n_cb, K)
+
+
+def test_extreme_llrs_do_not_overflow(oracle):
+    """Saturated, erased (0 / NaN) and non-codeword inputs stay inside int16 and stay bit-exact."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_iter = 6144, 8
+    pi = oracle.qpp(K)
+    rng = np.random.default_rng(5)
+    bits, llr = oracle.make_batch(K, 4, 3.0, seed=9)
+    llr32 = llr.astype(np.float32)
+    llr32[0] *= 1e4
+    llr32[1, ::7] = 0.0
+    llr32[1, 5::11] = np.nan
+    llr32[2] = (rng.integers(0, 2, llr32.shape[1]) * 2 - 1) * 1e3
+    llr32[3] = 0.0
+    dec = TurboDecoder(K, n_iter=n_iter, algo="logmap_s16")
+    plan = dec.plan()
+    prm = lm_params(K, n_iter, plan["sub_block"], plan["warmup"])
+    out = dec.decode(llr32, want=("bits", "ext_siso2"))
+    for c in range(4):
+        b, le, it, ovf = oracle.fx_decode(np.nan_to_num(llr32[c], nan=0.0), pi, prm, want_le=True)
+        assert ovf == 0
+        assert np.array_equal(out["bits"][c], b.astype(np.uint8))
+        assert np.array_equal(np.rint(out["ext_siso2"][c][:K] * 16).astype(np.int32), le[pi])
+    assert np.array_equal(out["bits"][0], bits[0].astype(np.uint8))
+
+
+@pytest.mark.parametrize("K,ebn0", [(6144, 1.0), (6144, 0.45), (1024, 2.0)])
+def test_early_termination(oracle, K, ebn0):
+    """Per-codeblock stopping rule (decisions unchanged and every |a-posteriori| >= threshold): iteration counts as the
+    model's; a pair leaves together, so the delivered bits are those after max(iterations of the pair)."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    n_cb, n_iter = 6, 8
+    pi = oracle.qpp(K)
+    bits, llr = oracle.make_batch(K, n_cb, ebn0, seed=4242 + K)
+    llr32 = llr.astype(np.float32)
+    dec = TurboDecoder(K, n_iter=n_iter, algo="logmap_s16", early_term=1, max_batch=n_cb)
+    plan = dec.plan()
+    T = 1 << (4 + 3)
+    out = dec.decode(llr32, want=("bits", "iters_used"))
+    used = []
+    for c in range(n_cb):
+        _, _, it, _ = oracle.fx_decode(llr32[c], pi, lm_params(K, n_iter, plan["sub_block"], plan["warmup"], early_term=1, et_threshold=T))
+        used.append(it)
+    assert list(out["iters_used"]) == used
+    for c in range(n_cb):
+        mate = c ^ 1 if (c ^ 1) < n_cb else c
+        ran = max(used[c], used[mate])
+        b = oracle.fx_decode(llr32[c], pi, lm_params(K, ran, plan["sub_block"], plan["warmup"]))[0]
+        assert np.array_equal(out["bits"][c], b.astype(np.uint8))

@@ -37,6 +37,10 @@ KERNEL_TUS = [
     ("tdb200_fast_inst_crc_f64.cu", []),
     ("tdb200_fast_inst_crc_s8.cu", []),
     ("tdb200_fast_inst_crc_f16.cu", []),
+    ("tdb200_fast_inst_lm_f32.cu", ["-Xptxas", "-v"]),
+    ("tdb200_fast_inst_lm_f64.cu", []),
+    ("tdb200_fast_inst_lm_s8.cu", []),
+    ("tdb200_fast_inst_lm_f16.cu", []),
     ("tdb200_f32.cu", ["-fmad=false", "-Xptxas", "-v"]),
     ("tdb200_encode.cu", []),
     ("tdb200_modem.cu", ["-fmad=false"]),

@@ -56,7 +56,8 @@ void ensure_decoder(int K)
 {
     const int n_iter = env_int("TDB200_COMPAT_ITERS", 15);
     const char *a = std::getenv("TDB200_COMPAT_ALGO");
-    const int algo = (a && std::strcmp(a, "maxlog_s16") == 0) ? TDB200_ALGO_MAXLOG_S16 : TDB200_ALGO_LOGMAP_F64;
+    const int algo = (a && std::strcmp(a, "maxlog_s16") == 0) ? TDB200_ALGO_MAXLOG_S16
+                     : ((a && std::strcmp(a, "logmap_s16") == 0) ? TDB200_ALGO_LOGMAP_S16 : TDB200_ALGO_LOGMAP_F64);
     const int qf1 = (&f1 && &source_length && source_length == K) ? f1 : 0;
     const int qf2 = (&f2 && &source_length && source_length == K) ? f2 : 0;
     if (g.dec && g.K == K && g.f1 == qf1 && g.f2 == qf2 && g.n_iter == n_iter && g.algo == algo) return;

@@ -293,26 +293,28 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         w.beta = p; p += 8 * (T + 1) * nb;
         w.max_batch = c.max_batch;
     } else if (c.algo == TDB200_ALGO_MAXLOG_S16 || c.algo == TDB200_ALGO_LOGMAP_F32 || c.algo == TDB200_ALGO_MAXLOG_F32 ||
-               c.algo == TDB200_ALGO_LINLOGMAP_F32) {
-        const bool s16 = (c.algo == TDB200_ALGO_MAXLOG_S16);
+               c.algo == TDB200_ALGO_LINLOGMAP_F32 || c.algo == TDB200_ALGO_LOGMAP_S16) {
+        const bool lm16 = (c.algo == TDB200_ALGO_LOGMAP_S16);
+        const bool s16 = (c.algo == TDB200_ALGO_MAXLOG_S16) || lm16;
         if (c.max_batch <= 0) c.max_batch = 16384;
         if (c.early_term < 0 || c.early_term > 3) return fail(TDB200_ERR_INVALID_ARG, "early_term=%d (0..3)", c.early_term);
-        if (c.early_term >= 2 && !s16) return fail(TDB200_ERR_UNSUPPORTED, "the CRC stopping rule exists in TDB200_ALGO_MAXLOG_S16 only");
+        if (c.early_term >= 2 && (!s16 || lm16)) return fail(TDB200_ERR_UNSUPPORTED, "the CRC stopping rule exists in TDB200_ALGO_MAXLOG_S16 only");
         if (c.early_term >= 2 && K <= 24) return fail(TDB200_ERR_INVALID_ARG, "K=%d leaves no room for a 24-bit CRC", K);
-        if (c.frac_bits == 0) c.frac_bits = 3;
+        if (c.frac_bits == 0) c.frac_bits = lm16 ? 4 : 3;
+        if (lm16 && c.frac_bits < 3) return fail(TDB200_ERR_INVALID_ARG, "frac_bits=%d: TDB200_ALGO_LOGMAP_S16 needs 3 or 4 (the correction is 5 << (frac_bits - 3) at most)", c.frac_bits);
         if (c.frac_bits < 1 || c.frac_bits > 4) return fail(TDB200_ERR_INVALID_ARG, "frac_bits=%d out of range [1,4]", c.frac_bits);
-        if (c.ext_scale_q2 == 0) c.ext_scale_q2 = (c.algo == TDB200_ALGO_LOGMAP_F32 || c.algo == TDB200_ALGO_LINLOGMAP_F32) ? 4 : 3;
+        if (c.ext_scale_q2 == 0) c.ext_scale_q2 = (c.algo == TDB200_ALGO_LOGMAP_F32 || c.algo == TDB200_ALGO_LINLOGMAP_F32 || lm16) ? 4 : 3;
         if (c.ext_scale_q2 != 3 && c.ext_scale_q2 != 4) return fail(TDB200_ERR_INVALID_ARG, "ext_scale_q2=%d (3 or 4)", c.ext_scale_q2);
         if (c.et_threshold == 0) c.et_threshold = 1 << (c.frac_bits + 3);
         if (c.et_threshold < 1 || c.et_threshold > 4096 || (c.et_threshold & (c.et_threshold - 1)))
             return fail(TDB200_ERR_INVALID_ARG, "et_threshold=%d must be a power of two in [1,4096]", c.et_threshold);
-        if (c.ext_clip == 0) c.ext_clip = (1 << (c.frac_bits + 6)) - 1;  // |Le| < 64.0: keeps every metric sum inside int16
+        if (c.ext_clip == 0) c.ext_clip = lm16 ? 511 : (1 << (c.frac_bits + 6)) - 1;  // |Le| < 64.0 (32.0 at 4 fractional bits): keeps every metric sum inside int16
         if (c.ext_clip < 63 || c.ext_clip > 2047 || ((c.ext_clip + 1) & 3))
             return fail(TDB200_ERR_INVALID_ARG, "ext_clip=%d: need 63 <= ext_clip <= 2047 and ext_clip+1 a multiple of 4", c.ext_clip);
         // ---- sub-block geometry: K = P * L, L = 8 * NW, P <= 256 threads
         FastGeom &g = d->geom;
         int L = c.sub_block;
-        if (s16 && L == 0 && c.warmup == 0) {
+        if (s16 && !lm16 && L == 0 && c.warmup == 0) {
             // measured on a B200 for every LTE block size (tools/tune_subblock.py): which admissible L is fastest
             // depends on how the sub-block count fills warps and how many CTAs fit an SM, not on L alone
             for (int i = 0; i < 188; i++)
@@ -332,7 +334,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
             return fail(TDB200_ERR_INVALID_ARG, "sub_block=%d must be a multiple of 8 dividing K=%d with K/sub_block <= 256", L, K);
         int G = c.warmup;
         if (G < 0 || G % 8) return fail(TDB200_ERR_INVALID_ARG, "warmup=%d must be a non-negative multiple of 8", G);
-        if (c.warmup == 0 && c.sub_block == 0) G = 16;  // auto plan: guard of 16 (BER vs (L,G))
+        if (c.warmup == 0 && c.sub_block == 0) G = lm16 ? 32 : 16;  // auto plan: guard of 16 (BER vs (L,G)); Log-MAP: 32, which is what keeps it on the unsegmented curve
         if (G > L) G = L;
         g.K = K; g.L = L; g.P = K / L; g.NW = L / 8; g.G = (g.P == 1) ? 0 : G;
         g.PP = g.P | 1;  // odd row pitch: de-multiplex stores spread over the banks, walks stay conflict-free
@@ -350,7 +352,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
             // doubles (K = 3136: +13 %).
             int np = 1;
             if (c.early_term < 2) {  // the CRC fold is per CTA
-                const bool packable = !fast_s16_specialised(g) || fast_spec_rt(g);
+                const bool packable = lm16 ? !fast_s16_specialised(g, true) : (!fast_s16_specialised(g) || fast_spec_rt(g));
                 auto ctas_by_smem = [&](int n) {
                     g.NP = n; g.threads = ((n * g.P + 31) / 32) * 32;
                     return (int)(prop.sharedMemPerMultiprocessor / ((size_t)fast_s16_smem_bytes(g) + 1024));
@@ -374,7 +376,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         if ((size_t)g.smem_bytes > prop.sharedMemPerBlockOptin)
             return fail(TDB200_ERR_UNSUPPORTED, "plan needs %d B of shared memory per CTA, device allows %zu", g.smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
         c.sub_block = L; c.warmup = g.G;
-        if (s16) TDB_CUDA(fast_s16_configure(g, d->sm_count));
+        if (s16) TDB_CUDA(fast_s16_configure(g, d->sm_count, lm16));
         else TDB_CUDA(f32_configure(g));
         // word address of element pi(tL+j), stored at j*PP+t
         std::vector<uint16_t> tab((size_t)L * g.PP, 0);
@@ -436,7 +438,7 @@ int tdb200_get_plan(const tdb200_decoder *d, tdb200_plan_info *info)
         info->sub_block = d->cfg.K; info->n_sub_blocks = 1; info->cb_per_cta = 8; info->threads_per_cta = 64;
     } else {
         info->sub_block = d->geom.L; info->n_sub_blocks = d->geom.P; info->warmup = d->geom.G;
-        info->cb_per_cta = (d->cfg.algo == TDB200_ALGO_MAXLOG_S16) ? 2 * d->geom.NP : 1;
+        info->cb_per_cta = (d->cfg.algo == TDB200_ALGO_MAXLOG_S16 || d->cfg.algo == TDB200_ALGO_LOGMAP_S16) ? 2 * d->geom.NP : 1;
         info->threads_per_cta = d->geom.threads; info->smem_bytes = d->geom.smem_bytes;
     }
     return TDB200_OK;
@@ -470,7 +472,7 @@ static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int 
         a.bits = v_bits; a.bits_iters = v_bits_iters;
         a.llr1 = static_cast<double *>(v_llr1); a.llr2 = static_cast<double *>(v_llr2); a.ext2 = static_cast<double *>(v_ext2);
         TDB_CUDA(launch_ref64_decode(a, st, &d->launches_last));
-    } else if (c.algo != TDB200_ALGO_MAXLOG_S16) {
+    } else if (c.algo != TDB200_ALGO_MAXLOG_S16 && c.algo != TDB200_ALGO_LOGMAP_S16) {
         F32Args a{};
         a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.g = d->geom; a.n_iter = c.n_iter;
         a.logmap = (c.algo == TDB200_ALGO_LOGMAP_F32) ? 1 : (c.algo == TDB200_ALGO_LINLOGMAP_F32 ? 2 : 0);
@@ -490,6 +492,8 @@ static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int 
         a.ext_lim = c.ext_clip + 1;
         a.q2 = c.ext_scale_q2; a.early_term = std::min(c.early_term, 2); a.et_threshold = c.et_threshold;
         a.crc_poly = d->crc_poly; a.crc_tab = d->d_crc_tab; a.crc_shift = d->d_crc_shift;
+        a.logmap = (c.algo == TDB200_ALGO_LOGMAP_S16) ? 1 : 0;
+        a.lm_t4 = 5 << (c.frac_bits - 3 > 0 ? c.frac_bits - 3 : 0);
         a.tab2 = d->d_tab2;
         a.opaque[0] = 0xffffffffu; a.opaque[1] = 4u; a.opaque[2] = 65536u; a.opaque[3] = 0xC0000000u;
         a.prefetch_stride = d->geom.resident_ctas;
@@ -518,7 +522,7 @@ struct Source {
 // the channel-value format the decoder consumes without conversion loss
 static int native_llr_type(const tdb200_config &c)
 {
-    return c.algo == TDB200_ALGO_LOGMAP_F64 ? TDB200_LLR_F64 : (c.algo == TDB200_ALGO_MAXLOG_S16 ? TDB200_LLR_S8 : TDB200_LLR_F32);
+    return c.algo == TDB200_ALGO_LOGMAP_F64 ? TDB200_LLR_F64 : ((c.algo == TDB200_ALGO_MAXLOG_S16 || c.algo == TDB200_ALGO_LOGMAP_S16) ? TDB200_LLR_S8 : TDB200_LLR_F32);
 }
 
 static int launch_demap_chunk(tdb200_decoder *d, const Source &src, const void *si, const void *sq, void *llr, int n, cudaStream_t st)
@@ -589,7 +593,7 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
             return fail(TDB200_ERR_INVALID_ARG, "device LLR buffer must be %d-byte aligned", (int)need);
     }
     // what the decode kernel reads: the caller's LLRs, or the staged output of the demapper / de-rate-matcher
-    const int llr_type = sym ? native_llr_type(c) : ((rm && c.algo == TDB200_ALGO_MAXLOG_S16) ? TDB200_LLR_S8 : src.llr_type);
+    const int llr_type = sym ? native_llr_type(c) : ((rm && (c.algo == TDB200_ALGO_MAXLOG_S16 || c.algo == TDB200_ALGO_LOGMAP_S16)) ? TDB200_LLR_S8 : src.llr_type);
     const void *llr = src.llr;
     const size_t esz = llr_elem_size(llr_type);
     const size_t ssz = sym ? llr_elem_size(src.sym_type) : 0;

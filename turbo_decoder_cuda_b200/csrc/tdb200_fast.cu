@@ -19,10 +19,24 @@ fast_kernel_fn fast_pick_crc_f32(const FastGeom &g);
 fast_kernel_fn fast_pick_crc_s8(const FastGeom &g);
 fast_kernel_fn fast_pick_crc_f16(const FastGeom &g);
 
+// the Log-MAP variants (tdb200_fast_inst_lm_*.cu)
+fast_kernel_fn fast_pick_lm_f64(const FastGeom &g);
+fast_kernel_fn fast_pick_lm_f32(const FastGeom &g);
+fast_kernel_fn fast_pick_lm_s8(const FastGeom &g);
+fast_kernel_fn fast_pick_lm_f16(const FastGeom &g);
+
 namespace {
 
-fast_kernel_fn pick_kernel(const FastGeom &g, int llr_type, bool crc = false)
+fast_kernel_fn pick_kernel(const FastGeom &g, int llr_type, bool crc = false, bool logmap = false)
 {
+    if (logmap) {
+        switch (llr_type) {
+            case TDB200_LLR_F32: return fast_pick_lm_f32(g);
+            case TDB200_LLR_F64: return fast_pick_lm_f64(g);
+            case TDB200_LLR_F16: return fast_pick_lm_f16(g);
+            default: return fast_pick_lm_s8(g);
+        }
+    }
     if (crc) {
         switch (llr_type) {
             case TDB200_LLR_F32: return fast_pick_crc_f32(g);
@@ -41,7 +55,11 @@ fast_kernel_fn pick_kernel(const FastGeom &g, int llr_type, bool crc = false)
 
 }  // namespace
 
-bool fast_s16_specialised(const FastGeom &g) { return fast_spec_pn(g) || fast_spec128g8(g) || fast_spec192(g) || fast_spec_rt(g) || fast_spec_rt192(g); }
+bool fast_s16_specialised(const FastGeom &g, bool logmap)
+{
+    if (logmap) return fast_spec_lm(g);
+    return fast_spec_pn(g) || fast_spec128g8(g) || fast_spec192(g) || fast_spec_rt(g) || fast_spec_rt192(g);
+}
 
 // bytes of one codeblock-pair region / of the part shared by the pairs of a CTA of `threads` threads
 int fast_s16_pair_bytes(const FastGeom &g)
@@ -63,7 +81,7 @@ static int shared_bytes(const FastGeom &g, int threads, int np)
 }
 int fast_s16_smem_bytes(const FastGeom &g) { return ((g.pair_bytes * g.NP + 15) & ~15) + shared_bytes(g, g.threads, g.NP); }
 
-cudaError_t fast_s16_configure(FastGeom &g, int sm_count)
+cudaError_t fast_s16_configure(FastGeom &g, int sm_count, bool logmap)
 {
     // The attribute belongs to the kernel, not to a decoder handle: several handles with
     // different geometries share one instantiation, so always opt in to the device maximum.
@@ -72,12 +90,12 @@ cudaError_t fast_s16_configure(FastGeom &g, int sm_count)
     if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e0 != cudaSuccess) return e0;
     for (int t = TDB200_LLR_F64; t <= TDB200_LLR_F16; t++) {
-        cudaError_t e = cudaFuncSetAttribute(pick_kernel(g, t), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(pick_kernel(g, t, true), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        cudaError_t e = cudaFuncSetAttribute(pick_kernel(g, t, false, logmap), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        if (e == cudaSuccess && !logmap) e = cudaFuncSetAttribute(pick_kernel(g, t, true), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
         if (e != cudaSuccess) return e;
     }
     int per_sm = 0;
-    e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(g, TDB200_LLR_F32), g.threads, g.smem_bytes);
+    e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(g, TDB200_LLR_F32, false, logmap), g.threads, g.smem_bytes);
     if (e0 != cudaSuccess) return e0;
     g.resident_ctas = per_sm * sm_count;
     return cudaSuccess;
@@ -94,7 +112,7 @@ cudaError_t launch_fast_s16(const FastArgs &a0, cudaStream_t st, int *n_launches
     a.pairs_per_cta = np;
     const int threads = ((np * a.g.P + 31) / 32) * 32;
     const int smem = ((a.g.pair_bytes * np + 15) & ~15) + shared_bytes(a.g, threads, np);
-    pick_kernel(a.g, a.llr_type, a.early_term == 2)<<<(pairs + np - 1) / np, threads, smem, st>>>(a);
+    pick_kernel(a.g, a.llr_type, a.early_term == 2, a.logmap != 0)<<<(pairs + np - 1) / np, threads, smem, st>>>(a);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

@@ -1,0 +1,8 @@
+// tdb200_fast_inst_lm_s8.cu -- the packed-int16 Log-MAP decoder kernels (TDB200_ALGO_LOGMAP_S16) for
+// TDB200_LLR_S8 channel LLRs (device code in tdb200_fast_kernel.cuh).
+#include "tdb200_fast_kernel.cuh"
+
+namespace tdb200 {
+typedef void (*fast_kernel_fn)(FastArgs);
+fast_kernel_fn fast_pick_lm_s8(const FastGeom &g) { return pick_kernel_lm_t<TDB200_LLR_S8>(g); }
+}  // namespace tdb200

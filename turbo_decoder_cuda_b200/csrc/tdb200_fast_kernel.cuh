@@ -96,6 +96,169 @@ __device__ __forceinline__ void beta_step(w32 (&b)[8], w32 u, w32 v)
     b[0] = o0; b[1] = o1; b[2] = o2; b[3] = o3; b[4] = o4; b[5] = o5; b[6] = o6; b[7] = o7;
 }
 
+// Constants the compiler must not see through: ptxas strength-reduces x*-1-1, x*2, x*65536 and
+// mulhi(x, 3<<30) into ALU-pipe instructions (IADD3 / LEA / PRMT / SHF), and the ALU pipe is the one
+// the add-compare-select instructions saturate.  Passed as kernel arguments they stay IMADs on the
+// fma-heavy pipe, which has slack.
+struct PassCfg {
+    int q2;
+    w32 lim1;    // dup2(ext_lim + 1): the +1 completes m1 + ~m0 = m1 - m0 - 1
+    w32 limmax;  // dup2(2*ext_lim - 1)
+    w32 unbias;  // dup2(-(3*ext_lim/4) - 128) or dup2(-ext_lim - 128): extrinsic bias and systematic-byte bias
+    w32 neg1;    // 0xffffffff
+    w32 four;    // 4
+    w32 k64k;    // 65536
+    w32 k3q;     // 0xC0000000: mulhi(y, k3q) = (3*y) >> 2
+    w32 etT, et2T, etmask;  // dup2(T), dup2(2T), dup2(2T-1): magnitude test of the stopping rule
+    // TDB200_ALGO_LOGMAP_S16 (see "max* with the correction" below)
+    w32 lk;   // dup2(1 + T4 - 0x4000): completes every sum of two biased quarter-differences
+    w32 lku;  // dup2(1 + T4): the a-posteriori trees' upper levels
+    w32 lm, lx2, lx1, lkc;  // 0x3fff3fff, 0x20002000, 0x1fff1fff, 0xC000C000
+};
+
+// ---- max* with the correction: TDB200_ALGO_LOGMAP_S16 (integer specification: oracle/turbo_oracle_fx.c, logmap = 1)
+//
+// max*(x,y) = max(x,y) + c(|x-y|) is the Jacobian logarithm the reference evaluates through E_algorithm()'s
+// 16-step table (ITTC/log_map.cpp:779-801, table :14-18; 30 of them per trellis step, :975-1039).  Here c is the
+// linear fit max(0, T4 - |d|/4) in units of 2^-frac_bits (T4 = 10 at 4 fractional bits: 0.625 - d/4).
+// sm_100 has no packed 16-bit shift, subtract or absolute difference, so d/4 is never formed per max*:
+//   * the two max* of a trellis butterfly, max*(p+g, q) and max*(q+g, p), have d = (p-q)+g and d = g-(p-q).
+//     One 32-bit SHF + two LOP3 per butterfly give h' = floor((p-q-1)/4) + 0x2000 and nh' = -floor(..)-1 + 0x2000 in
+//     both lanes (the 14-bit field is re-biased, which undoes the cross-lane bits of the 32-bit shift), and the same
+//     pair once per step for each of the two branch-metric differences g (u+v and u-v);
+//   * T4 - |d/4| = min(T4 + d/4, T4 - d/4) is then ONE VIADDMNMX.RELU per max*: relu(min(h' + GP, nh' + GM));
+//   * the first level of the a-posteriori trees pairs (alpha_i, alpha_j) x (beta_m, beta_n) along the same
+//     butterflies, so it reuses the h' of the alpha and beta recursions; only the six upper-level max* per step pay
+//     a shift each (via max - min, whose sign is known).
+struct GK {
+    w32 P, M;  // floor(g/4) + 1 + T4 - 0x2000,  T4 - floor(g/4) - 0x2000
+};
+__device__ __forceinline__ w32 vnot(w32 x) { return ~x; }
+__device__ __forceinline__ void quarter(w32 d1, const PassCfg &c, w32 &h, w32 &nh)
+{
+    const w32 f = (d1 >> 2) & c.lm;
+    h = f ^ c.lx2;
+    nh = f ^ c.lx1;
+}
+__device__ __forceinline__ GK gk_of(w32 g, const PassCfg &c)
+{
+    w32 a, b;
+    quarter(g, c, a, b);
+    GK r;
+    r.P = vadd(a, c.lk);
+    r.M = vadd(b, c.lk);
+    return r;
+}
+// corrections of max*(p + g, q) and max*(q + g, p), given the quarter-difference of (p, q)
+__device__ __forceinline__ void bfly_corr(w32 h, w32 nh, const GK &g, w32 &ca, w32 &cb)
+{
+    ca = __viaddmin_s16x2_relu(h, g.P, vadd(nh, g.M));
+    cb = __viaddmin_s16x2_relu(nh, g.P, vadd(h, g.M));
+}
+// quarter-differences of the four butterflies of an alpha vector: (a1,a0) (a3,a2) (a5,a4) (a7,a6)
+__device__ __forceinline__ void alpha_quarters(const w32 (&a)[8], const PassCfg &c, w32 (&h)[4], w32 (&nh)[4])
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) quarter(vadd(a[2 * i + 1], vnot(a[2 * i])), c, h[i], nh[i]);
+}
+// ... of a beta vector: (b4,b0) (b1,b5) (b6,b2) (b3,b7)
+__device__ __forceinline__ void beta_quarters(const w32 (&b)[8], const PassCfg &c, w32 (&h)[4], w32 (&nh)[4])
+{
+    quarter(vadd(b[4], vnot(b[0])), c, h[0], nh[0]);
+    quarter(vadd(b[1], vnot(b[5])), c, h[1], nh[1]);
+    quarter(vadd(b[6], vnot(b[2])), c, h[2], nh[2]);
+    quarter(vadd(b[3], vnot(b[7])), c, h[3], nh[3]);
+}
+__device__ __forceinline__ void alpha_step_lm_to(const w32 (&a)[8], const w32 (&h)[4], const w32 (&nh)[4], w32 u, w32 v, const PassCfg &c,
+                                                 w32 (&o)[8])
+{
+    const w32 w = vadd(u, v);
+    const GK gw = gk_of(w, c), gg = gk_of(vadd(u, vnot(v)), c);
+    w32 c0, c4, c5, c1, c2, c6, c7, c3;
+    bfly_corr(h[0], nh[0], gw, c0, c4);
+    bfly_corr(h[1], nh[1], gg, c5, c1);
+    bfly_corr(h[2], nh[2], gg, c2, c6);
+    bfly_corr(h[3], nh[3], gw, c7, c3);
+    const w32 t5 = vadd(a[2], v), t1 = vadd(a[3], v), t2 = vadd(a[4], v), t6 = vadd(a[5], v);
+    const w32 o0 = vadd(vaddmax(a[1], w, a[0]), c0), o4 = vadd(vaddmax(a[0], w, a[1]), c4);
+    const w32 o5 = vadd(vaddmax(a[3], u, t5), c5), o1 = vadd(vaddmax(a[2], u, t1), c1);
+    const w32 o2 = vadd(vaddmax(a[5], u, t2), c2), o6 = vadd(vaddmax(a[4], u, t6), c6);
+    const w32 o7 = vadd(vaddmax(a[7], w, a[6]), c7), o3 = vadd(vaddmax(a[6], w, a[7]), c3);
+    o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3; o[4] = o4; o[5] = o5; o[6] = o6; o[7] = o7;
+}
+__device__ __forceinline__ void beta_step_lm(w32 (&b)[8], const w32 (&h)[4], const w32 (&nh)[4], w32 u, w32 v, const PassCfg &c)
+{
+    const w32 w = vadd(u, v);
+    const GK gw = gk_of(w, c), gg = gk_of(vadd(u, vnot(v)), c);
+    w32 c0, c1, c2, c3, c4, c5, c6, c7;
+    bfly_corr(h[0], nh[0], gw, c0, c1);
+    bfly_corr(h[1], nh[1], gg, c2, c3);
+    bfly_corr(h[2], nh[2], gg, c4, c5);
+    bfly_corr(h[3], nh[3], gw, c6, c7);
+    const w32 t2 = vadd(b[5], v), t3 = vadd(b[1], v), t4 = vadd(b[2], v), t5 = vadd(b[6], v);
+    const w32 o0 = vadd(vaddmax(b[4], w, b[0]), c0), o1 = vadd(vaddmax(b[0], w, b[4]), c1);
+    const w32 o2 = vadd(vaddmax(b[1], u, t2), c2), o3 = vadd(vaddmax(b[5], u, t3), c3);
+    const w32 o4 = vadd(vaddmax(b[6], u, t4), c4), o5 = vadd(vaddmax(b[2], u, t5), c5);
+    const w32 o6 = vadd(vaddmax(b[3], w, b[7]), c6), o7 = vadd(vaddmax(b[7], w, b[3]), c7);
+    b[0] = o0; b[1] = o1; b[2] = o2; b[3] = o3; b[4] = o4; b[5] = o5; b[6] = o6; b[7] = o7;
+}
+// one recursion step, quarter-differences formed on the spot (warm-up, forward sweep, tail)
+template <bool LM>
+__device__ __forceinline__ void alpha_step_x(w32 (&a)[8], w32 u, w32 v, const PassCfg &c)
+{
+    if (LM) {
+        w32 h[4], nh[4];
+        alpha_quarters(a, c, h, nh);
+        alpha_step_lm_to(a, h, nh, u, v, c, a);
+    } else {
+        alpha_step(a, u, v);
+    }
+}
+template <bool LM>
+__device__ __forceinline__ void beta_step_x(w32 (&b)[8], w32 u, w32 v, const PassCfg &c)
+{
+    if (LM) {
+        w32 h[4], nh[4];
+        beta_quarters(b, c, h, nh);
+        beta_step_lm(b, h, nh, u, v, c);
+    } else {
+        beta_step(b, u, v);
+    }
+}
+// max* of two values that share nothing (upper levels of the a-posteriori trees): mn - mx - 1 is negative in both
+// lanes, so its arithmetic shift is the 32-bit shift with the two top bits of each lane set
+__device__ __forceinline__ w32 maxstar_g(w32 x, w32 y, const PassCfg &c)
+{
+    const w32 mx = __vmaxs2(x, y), mn = __vmins2(x, y);
+    const w32 e4 = (vadd(mn, vnot(mx)) >> 2) | c.lkc;
+    return vadd(mx, __viaddmax_s16x2_relu(e4, c.lku, 0u));
+}
+// first level: the input-0 terms alpha_i + beta_m, alpha_j + beta_n ("same") and the input-1 terms alpha_j + beta_m,
+// alpha_i + beta_n ("cross") of the state pair (i, j) x (m, n); hA / hB: quarter-differences of (aj, ai) / (bn, bm)
+__device__ __forceinline__ void lam_pair(w32 ai, w32 aj, w32 bm, w32 bn, w32 hA, w32 nhA, w32 hB, w32 nhB, const PassCfg &c, w32 &same, w32 &cross)
+{
+    const w32 HB = vadd(hB, c.lk), nHB = vadd(nhB, c.lk);
+    const w32 c1 = __viaddmin_s16x2_relu(hA, HB, vadd(nhA, nHB));
+    const w32 c2 = __viaddmin_s16x2_relu(hA, nHB, vadd(nhA, HB));
+    same = vadd(vaddmax(aj, bn, vadd(ai, bm)), c1);
+    cross = vadd(vaddmax(aj, bm, vadd(ai, bn)), c2);
+}
+// e - 1 like extrinsic_m1 below, every max a max* (:1024-1039)
+__device__ __forceinline__ w32 extrinsic_m1_lm(const w32 (&a)[8], const w32 (&hA)[4], const w32 (&b)[8], const w32 (&hB)[4], const w32 (&nhB)[4], w32 v,
+                                               const PassCfg &c)
+{
+    w32 s01, x01, s67, x67, s23, x23, s45, x45;
+    lam_pair(a[0], a[1], b[0], b[4], hA[0], hA[0] ^ c.lm, hB[0], nhB[0], c, s01, x01);
+    lam_pair(a[6], a[7], b[7], b[3], hA[3], hA[3] ^ c.lm, hB[3], nhB[3], c, s67, x67);
+    lam_pair(a[2], a[3], b[5], b[1], hA[1], hA[1] ^ c.lm, hB[1], nhB[1], c, s23, x23);
+    lam_pair(a[4], a[5], b[2], b[6], hA[2], hA[2] ^ c.lm, hB[2], nhB[2], c, s45, x45);
+    const w32 m0a = maxstar_g(s01, s67, c), m0b = maxstar_g(s23, s45, c);
+    const w32 m1a = maxstar_g(x01, x67, c), m1b = maxstar_g(x23, x45, c);
+    const w32 m0 = maxstar_g(m0a, vadd(m0b, v), c);
+    const w32 m1 = maxstar_g(vadd(m1a, v), m1b, c);
+    return vadd(m1, vnot(m0));
+}
+
 // ---- channel-LLR load + quantisation (q = clamp(rint(x * 2^F), +-clip), oracle: quant())
 __device__ __forceinline__ int quant(float x, float scale, int clip)
 {
@@ -213,22 +376,6 @@ struct Smem {
     w32 *ckpt, *dec, *edge;
 };
 
-// Constants the compiler must not see through: ptxas strength-reduces x*-1-1, x*2, x*65536 and
-// mulhi(x, 3<<30) into ALU-pipe instructions (IADD3 / LEA / PRMT / SHF), and the ALU pipe is the one
-// the add-compare-select instructions saturate.  Passed as kernel arguments they stay IMADs on the
-// fma-heavy pipe, which has slack.
-struct PassCfg {
-    int q2;
-    w32 lim1;    // dup2(ext_lim + 1): the +1 completes m1 + ~m0 = m1 - m0 - 1
-    w32 limmax;  // dup2(2*ext_lim - 1)
-    w32 unbias;  // dup2(-(3*ext_lim/4) - 128) or dup2(-ext_lim - 128): extrinsic bias and systematic-byte bias
-    w32 neg1;    // 0xffffffff
-    w32 four;    // 4
-    w32 k64k;    // 65536
-    w32 k3q;     // 0xC0000000: mulhi(y, k3q) = (3*y) >> 2
-    w32 etT, et2T, etmask;  // dup2(T), dup2(2T), dup2(2T-1): magnitude test of the stopping rule
-};
-
 __device__ __forceinline__ w32 vnot_fma(w32 x, w32 neg1) { return x * neg1 + neg1; }  // ~x
 
 #ifndef TDB_LAMBDA_V3
@@ -296,11 +443,12 @@ __device__ __forceinline__ w32 sys_biased(const PassCfg &c, const Smem &sm, cons
 // ahead, so the look-up is off the critical path).  Returns the decision bits of the window (WANT
 // only): sign of step k in bit 15-k (codeblock A) / 31-k (codeblock B); weak collects, per lane, a
 // non-zero value if some |a-posteriori| of the window is below the stopping threshold.
-template <bool IL, bool WANT>
+template <bool IL, bool WANT, bool LM>
 __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, const w32 *par, const int base, const int PP,
                                           const unsigned (&tabin)[8], const w32 (&a0)[8], w32 (&b)[8], w32 *stage, w32 &weak)
 {
     w32 aw[8][8], u[8], v[8];
+    w32 hA[LM ? 8 : 1][4];  // Log-MAP: quarter-differences of the window's alpha vectors, shared by the re-creation and the a-posteriori trees
     Elem el[8];
 #pragma unroll
     for (int s = 0; s < 8; s++) aw[0][s] = a0[s];
@@ -310,13 +458,26 @@ __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, cons
         el[k] = elem_of<IL>(c, tabin[k], idx);
         u[k] = x_at(sm, el[k]);
         v[k] = par[idx];
-        if (k < 7) alpha_step_to(aw[k], u[k], v[k], aw[k + 1]);
+        if (LM) {
+            w32 nh[4];
+            alpha_quarters(aw[k], c, hA[k], nh);
+            if (k < 7) alpha_step_lm_to(aw[k], hA[k], nh, u[k], v[k], c, aw[k + 1]);
+        } else {
+            if (k < 7) alpha_step_to(aw[k], u[k], v[k], aw[k + 1]);
+        }
     }
     norm8(b);
     w32 acc = 0;
 #pragma unroll
     for (int k = 7; k >= 0; k--) {
-        const w32 exm1 = extrinsic_m1(aw[k], b, v[k], c.neg1);
+        w32 hB[4], nhB[4];
+        w32 exm1;
+        if (LM) {
+            beta_quarters(b, c, hB, nhB);
+            exm1 = extrinsic_m1_lm(aw[k], hA[k], b, hB, nhB, v[k], c);
+        } else {
+            exm1 = extrinsic_m1(aw[k], b, v[k], c.neg1);
+        }
         // clamp to [-lim, lim-1], bias to [0, 2lim-1]
         const w32 y = __viaddmin_s16x2_relu(exm1, c.lim1, c.limmax);
         w32 es;
@@ -330,7 +491,8 @@ __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, cons
             weak |= __viaddmin_s16x2_relu(lam, c.etT, c.et2T) & c.etmask;
             if (stage) word_at(stage, el[k].xoff) = lam;
         }
-        beta_step(b, u[k], v[k]);
+        if (LM) beta_step_lm(b, hB, nhB, u[k], v[k], c);
+        else beta_step(b, u[k], v[k]);
     }
     return acc;
 }
@@ -342,7 +504,7 @@ __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, cons
 // pass go to sm.dec (one word per two windows) and the return value has bits 0-15 / 16-31 set
 // where a decision of codeblock A / B differs from what sm.dec held before; weak gets a non-zero
 // low / high half if some a-posteriori magnitude of codeblock A / B is below the stopping threshold.
-template <bool IL, bool WANT, int KP, int KNW, int KG>
+template <bool IL, bool WANT, int KP, int KNW, int KG, bool LM>
 __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, const Smem &sm, const w32 *par, w32 (&na)[8], w32 (&nb)[8],
                                          const int t, const bool active, const bool first_fixed, const bool last_fixed, w32 *stage,
                                          w32 &weak)
@@ -374,8 +536,8 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int ia = base_a + k * PP, ib = base_b + (7 - k) * PP;
-                alpha_step(a, x_at(sm, elem_at<IL>(c, sm, ia)), par[ia]);
-                beta_step(b, x_at(sm, elem_at<IL>(c, sm, ib)), par[ib]);
+                alpha_step_x<LM>(a, x_at(sm, elem_at<IL>(c, sm, ia)), par[ia], c);
+                beta_step_x<LM>(b, x_at(sm, elem_at<IL>(c, sm, ib)), par[ib], c);
             }
         }
 #pragma unroll
@@ -407,7 +569,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
             }
             const int base = 8 * w * PP + t;
 #pragma unroll
-            for (int k = 0; k < 8; k++) alpha_step(a, x_at(sm, el[k]), par[base + k * PP]);
+            for (int k = 0; k < 8; k++) alpha_step_x<LM>(a, x_at(sm, el[k]), par[base + k * PP], c);
         }
         if (NW > 1) norm8(a);
     }
@@ -431,7 +593,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int idx = base + k * PP;
-                alpha_step(tmp, x_at(sm, elem_at<IL>(c, sm, idx)), par[idx]);
+                alpha_step_x<LM>(tmp, x_at(sm, elem_at<IL>(c, sm, idx)), par[idx], c);
             }
 #pragma unroll
             for (int s = 0; s < 8; s++) sa[s] = tmp[s];
@@ -460,7 +622,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
                 off[k] = offn[k];
                 if (IL) offn[k] = sm.tab[(8 * max(w - 1, 0) + k) * PP + t];
             }
-            const w32 acc = bwd_window<IL, WANT>(c, sm, par, 8 * w * PP + t, PP, off, aw0, b, stage, weak);
+            const w32 acc = bwd_window<IL, WANT, LM>(c, sm, par, 8 * w * PP + t, PP, off, aw0, b, stage, weak);
             if (w == w_sb) {
 #pragma unroll
                 for (int s = 0; s < 8; s++) sb[s] = b[s];
@@ -598,7 +760,7 @@ __device__ __forceinline__ uint2 crc_of_decisions(const FastArgs &A, const Smem 
     return r;
 }
 
-template <int LLR_T, int KP, int KNW, int KG, bool CRC>
+template <int LLR_T, int KP, int KNW, int KG, bool CRC, bool LM = false>
 __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 128 : (KP == -2 ? 192 : 256)), KP ? 2 : 1) fast_s16_kernel(FastArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -694,6 +856,8 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
     c.unbias = dup2((A.q2 == 3 ? -(3 * A.ext_lim / 4) : -A.ext_lim) - 128);
     c.neg1 = A.opaque[0]; c.four = A.opaque[1]; c.k64k = A.opaque[2]; c.k3q = A.opaque[3];
     c.etT = dup2(A.et_threshold); c.et2T = dup2(2 * A.et_threshold); c.etmask = dup2(2 * A.et_threshold - 1);
+    c.lk = dup2(1 + A.lm_t4 - 0x4000); c.lku = dup2(1 + A.lm_t4);
+    c.lm = 0x3fff3fffu; c.lx2 = 0x20002000u; c.lx1 = 0x1fff1fffu; c.lkc = 0xC000C000u;
     const bool first_fixed = (t == 0), last_fixed = (t == P - 1);
 
     // ---- boundary vectors.  [s][0..7]: s = SISO
@@ -714,7 +878,7 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                 const size_t o = (size_t)3 * K + 6 * s + 2 * m;
                 const w32 u = pack2(load1<LLR_T>(A.llr, cbA * row + o, scale, clip), load1<LLR_T>(A.llr, cbB * row + o, scale, clip));
                 const w32 v = pack2(load1<LLR_T>(A.llr, cbA * row + o + 1, scale, clip), load1<LLR_T>(A.llr, cbB * row + o + 1, scale, clip));
-                beta_step(bt, u, v);
+                beta_step_x<LM>(bt, u, v, c);
             }
             norm8(bt);
 #pragma unroll
@@ -735,7 +899,7 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
             if (it >= 1) {
                 // SISO-1 with decisions; stop when the natural-order decisions of both codeblocks divide by the
                 // generator -- half an iteration after the SISO-2 pass that made them right
-                siso_pass<false, true, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
+                siso_pass<false, true, KP, KNW, KG, LM>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
                 const uint2 rem = crc_of_decisions(A, sm, flags, P, NW, t, active);
                 if (!rem.x && !usedA) usedA = it + 1;
                 if (!rem.y && !usedB) usedB = it + 1;
@@ -743,11 +907,11 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                 siso1_done = true;
             }
         }
-        if (!siso1_done) siso_pass<false, false, KP, KNW, KG>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
+        if (!siso1_done) siso_pass<false, false, KP, KNW, KG, LM>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
         if (A.early_term == 1 || last) {
             // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
             // (by then dead) parity-1 array
-            const w32 chg = siso_pass<true, true, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed,
+            const w32 chg = siso_pass<true, true, KP, KNW, KG, LM>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed,
                                                                (want_soft && last) ? sm.par1 : nullptr, weak);
             if (A.early_term == 1) {
                 // stop: no decision of this iteration differs from the previous one and no
@@ -773,7 +937,7 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                 if (one_pair ? done : (__syncthreads_and((int)done) != 0)) { used = it + 1; break; }
             }
         } else {
-            siso_pass<true, false, KP, KNW, KG>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed, nullptr, weak);
+            siso_pass<true, false, KP, KNW, KG, LM>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed, nullptr, weak);
         }
     }
     if (!usedA) usedA = used;
@@ -880,6 +1044,18 @@ kernel_fn pick_kernel_t(const FastGeom &g)
     if (fast_spec_rt(g)) return pick_rt<LLR_T, CRC>(g.NW);
     if (fast_spec_rt192(g)) return g.NW == 4 ? fast_s16_kernel<LLR_T, -2, 4, 16, CRC> : fast_s16_kernel<LLR_T, -2, 5, 16, CRC>;
     return fast_s16_kernel<LLR_T, 0, 0, 0, CRC>;
+}
+
+// TDB200_ALGO_LOGMAP_S16: compile-time geometry for 128 sub-blocks of 32 / 40 / 48 steps with guard 16 or 32
+// (K = 4096, 5120, 6144); every other plan runs the instantiation with run-time geometry
+template <int LLR_T>
+kernel_fn pick_kernel_lm_t(const FastGeom &g)
+{
+    if (fast_spec_lm(g)) {
+        if (g.G == 32) return g.NW == 6 ? fast_s16_kernel<LLR_T, 128, 6, 32, false, true> : (g.NW == 5 ? fast_s16_kernel<LLR_T, 128, 5, 32, false, true> : fast_s16_kernel<LLR_T, 128, 4, 32, false, true>);
+        return g.NW == 6 ? fast_s16_kernel<LLR_T, 128, 6, 16, false, true> : (g.NW == 5 ? fast_s16_kernel<LLR_T, 128, 5, 16, false, true> : fast_s16_kernel<LLR_T, 128, 4, 16, false, true>);
+    }
+    return fast_s16_kernel<LLR_T, 0, 0, 0, false, true>;
 }
 
 }  // namespace

@@ -104,6 +104,8 @@ struct FastArgs {
     uint32_t crc_poly;             // low 24 bits of the generator (early_term == 2)
     const uint32_t *crc_tab;       // [256] device: byte-wise table of that generator
     const uint32_t *crc_shift;     // [P] device: x^((P-1-t)L) mod g, the weight of sub-block t's remainder
+    int logmap;          // 1: TDB200_ALGO_LOGMAP_S16 (max* with the linear correction), 0: max-log
+    int lm_t4;           // Log-MAP: correction at |d| = 0 in fixed-point units (5 << (frac_bits - 3))
     uint32_t opaque[4];  // {0xffffffff, 4, 65536, 0xC0000000}: see PassCfg in tdb200_fast_kernel.cuh
     const uint16_t *tab2;  // [L*PP] device: smem word of element pi(tL+j), stored at index j*PP+t
     int prefetch_stride;   // CTAs resident on the device at once (0 = no L2 prefetch of the next pair)
@@ -147,11 +149,14 @@ inline bool fast_spec_rt(const FastGeom &g) { return !fast_spec_pn(g) && g.P >= 
 // 129..192 sub-blocks of 32 or 40 steps: six warps per CTA at 168 registers, two CTAs per SM
 inline bool fast_spec_rt192(const FastGeom &g) { return !fast_spec192(g) && g.P > 128 && g.P <= 192 && (g.NW == 4 || g.NW == 5) && g.G == 16 && g.PP == (g.P | 1); }
 
-cudaError_t fast_s16_configure(FastGeom &g, int sm_count);  // opt in to the dynamic shared memory size
+// Log-MAP kernels with compile-time geometry: 128 sub-blocks of 32 / 40 / 48 steps, guard 16 or 32
+inline bool fast_spec_lm(const FastGeom &g) { return g.P == 128 && g.NW >= 4 && g.NW <= 6 && (g.G == 16 || g.G == 32) && g.PP == 129; }
+
+cudaError_t fast_s16_configure(FastGeom &g, int sm_count, bool logmap);  // opt in to the dynamic shared memory size
 cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches);
 int fast_s16_smem_bytes(const FastGeom &g);
 int fast_s16_pair_bytes(const FastGeom &g);
-bool fast_s16_specialised(const FastGeom &g);  // compile-time geometry: one pair per CTA
+bool fast_s16_specialised(const FastGeom &g, bool logmap = false);  // compile-time geometry: one pair per CTA
 
 // ------------------------------------------------------------------ caller side: encoder + channel
 struct EncodeArgs {

@@ -22,7 +22,8 @@ ALGO_MAXLOG_S16 = 1
 ALGO_LOGMAP_F32 = 2
 ALGO_MAXLOG_F32 = 3
 ALGO_LINLOGMAP_F32 = 4
-ALGO_NAMES = {"logmap_f64": 0, "maxlog_s16": 1, "logmap_f32": 2, "maxlog_f32": 3, "linlogmap_f32": 4}
+ALGO_LOGMAP_S16 = 5
+ALGO_NAMES = {"logmap_f64": 0, "maxlog_s16": 1, "logmap_f32": 2, "maxlog_f32": 3, "linlogmap_f32": 4, "logmap_s16": 5}
 
 LLR_F64, LLR_F32, LLR_S8, LLR_F16 = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
