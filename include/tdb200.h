@@ -121,7 +121,9 @@ typedef struct tdb200_outputs {
                              order, one byte per bit (LLR < 0 -> 0 else 1, log_map.cpp:862-879) */
     int32_t *bits_iters;  /* [n_cb][n_iter][K] decisions after EVERY iteration, as ints: one
                              codeblock's slab is exactly TurboDecoding's flow_decoded
-                             (log_map.cpp:1264).  Rows past an early stop repeat the last one. */
+                             (log_map.cpp:1264).  Rows past an early stop repeat the last one.
+                             TDB200_ALGO_LOGMAP_F64 and the packed 16-bit decoders (which then take a
+                             decision pass every iteration: a diagnostic output, not the throughput path) */
     int32_t *iters_used;  /* [n_cb] iterations actually run */
     /* a-posteriori / extrinsic LLRs of the LAST iteration, in the algo's native float type
      * (double for LOGMAP_F64, float otherwise; MAXLOG_S16 writes float = q / 2^frac_bits):     */

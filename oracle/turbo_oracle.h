@@ -99,6 +99,7 @@ typedef struct tdo_fx_params {
     int lm_tt, lm_tc; /* exploration: trapezoid parameters */
     int lm_warm_maxlog; /* exploration: warm-up recursions without the correction */
     int lm_upper_off; /* exploration */
+    int lm_t4_lam;    /* exploration: T4 of the first a-posteriori level (0 = lm_t4) */
 } tdo_fx_params;
 
 /* Returns the number of iterations run.  bits_out[K] final decisions; le_out

@@ -106,6 +106,7 @@ static int extrinsic(const int *a, const int *b, int v)
  * ------------------------------------------------------------------------------------------ */
 static __thread int g_T4;      /* correction at d = 0, in fixed-point units */
 static __thread int g_upper;   /* how the upper levels of the a-posteriori max* trees are corrected: 0 linear, 1 trapezoid, 2 not at all */
+static __thread int g_T4L;     /* ... of the first level of the a-posteriori trees */
 static __thread int g_uoff;    /* rounding offset of the generic max* */
 static __thread int g_TT, g_TC;   /* trapezoid: c = min(TC, max(0, TT - |d|)) */
 
@@ -177,8 +178,8 @@ static inline void lam_pair(int ai, int aj, int bm, int bn, int *same, int *cros
     /* same: max*(aj + bn, ai + bm), d = (aj - ai) + (bn - bm);  cross: max*(aj + bm, ai + bn), d = (aj - ai) - (bn - bm) */
     const int hA = asr2(chk(aj - ai - 1)), nhA = -hA - 1;
     const int hB = asr2(chk(bn - bm - 1)), nhB = -hB - 1;
-    const int c1 = relu(imin(hA + hB + 1 + g_T4, nhA + nhB + 1 + g_T4));
-    const int c2 = relu(imin(hA + nhB + 1 + g_T4, nhA + hB + 1 + g_T4));
+    const int c1 = relu(imin(hA + hB + 1 + g_T4L, nhA + nhB + 1 + g_T4L));
+    const int c2 = relu(imin(hA + nhB + 1 + g_T4L, nhA + hB + 1 + g_T4L));
     *same = add(imax(add(aj, bn), add(ai, bm)), c1);
     *cross = add(imax(add(aj, bm), add(ai, bn)), c2);
 }
@@ -216,6 +217,7 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
     g_upper = p->lm_upper;
     g_TT = p->lm_tt; g_TC = p->lm_tc;
     g_uoff = p->lm_upper_off;
+    g_T4L = p->lm_t4_lam > 0 ? p->lm_t4_lam : g_T4;
 #define ASTEP(lmf, a_, u_, v_, o_) ((lmf) ? alpha_step_lm(a_, u_, v_, o_) : alpha_step(a_, u_, v_, o_))
 #define BSTEP(lmf, b_, u_, v_, o_) ((lmf) ? beta_step_lm(b_, u_, v_, o_) : beta_step(b_, u_, v_, o_))
 

@@ -151,3 +151,38 @@ def test_early_termination(oracle, K, ebn0):
         ran = max(used[c], used[mate])
         b = oracle.fx_decode(llr32[c], pi, lm_params(K, ran, plan["sub_block"], plan["warmup"]))[0]
         assert np.array_equal(out["bits"][c], b.astype(np.uint8))
+
+
+@pytest.mark.parametrize("algo,K,early", [("logmap_s16", 6144, 0), ("maxlog_s16", 6144, 0), ("logmap_s16", 1008, 0),
+                                          ("maxlog_s16", 512, 0), ("logmap_s16", 6144, 1), ("maxlog_s16", 6144, 1)])
+def test_per_iteration_decisions(oracle, algo, K, early):
+    """bits_iters of the throughput decoders: row k is what the same decoder delivers with n_iter = k + 1 -- the
+    reference's flow_decoded + K*iteration (ITTC/log_map.cpp:1261-1264), which main.cpp:224-237 counts errors on.
+    With early termination rows past the stop repeat the delivered decisions."""
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    n_cb, n_iter = 5, 6
+    ebn0 = 0.6 if K == 6144 else 1.5
+    _, llr = oracle.make_batch(K, n_cb, ebn0, seed=99 + K)
+    llr32 = llr.astype(np.float32)
+    x = torch.from_numpy(llr32).cuda()
+    dec = TurboDecoder(K, n_iter=n_iter, algo=algo, early_term=early)
+    out = dec.decode(x, want=("bits", "bits_iters", "iters_used"))
+    rows = out["bits_iters"].cpu().numpy()
+    bits = out["bits"].cpu().numpy()
+    used = out["iters_used"].cpu().numpy()
+    assert rows.shape == (n_cb, n_iter, K) and rows.dtype == np.int32
+    assert np.array_equal(rows[:, -1, :].astype(np.uint8), bits)
+    ran = [max(used[c], used[c ^ 1 if (c ^ 1) < n_cb else c]) for c in range(n_cb)]
+    for k in range(n_iter):
+        d = TurboDecoder(K, n_iter=k + 1, algo=algo)
+        b = d.decode(x, want=("bits",))["bits"].cpu().numpy()
+        for c in range(n_cb):
+            if k < ran[c]:
+                assert np.array_equal(rows[c, k].astype(np.uint8), b[c]), "iteration %d cb %d" % (k + 1, c)
+            else:
+                assert np.array_equal(rows[c, k].astype(np.uint8), bits[c])
+        d.close()
+    # host path delivers the same slab
+    out_h = dec.decode(llr32, want=("bits_iters",))
+    assert np.array_equal(out_h["bits_iters"], rows)

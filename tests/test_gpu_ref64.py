@@ -170,7 +170,7 @@ def test_error_paths_and_concurrent_handles(oracle):
     d1 = TurboDecoder(6144, n_iter=4, algo="maxlog_s16")
     d2 = TurboDecoder(512, n_iter=4, algo="maxlog_s16", sub_block=16, warmup=8)
     with pytest.raises(TdbError):
-        d1.decode(torch.zeros((2, 3 * 6144 + 12), device="cuda"), want=("bits_iters",))   # fp64-mode output
+        d1.decode(torch.zeros((2, 3 * 6144 + 12), device="cuda"), want=("llr_siso1",))   # fp64-mode output
     b1, l1 = oracle.make_batch(6144, 4, 1.5, seed=1)
     b2, l2 = oracle.make_batch(512, 6, 2.0, seed=2)
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()

@@ -46,14 +46,17 @@ def main():
     ap.add_argument("--out", default="gpurun_out/bler_refchannel.json")
     ap.add_argument("--frames", type=int, default=16384)
     ap.add_argument("--ebn0", type=float, nargs="+", default=[0.3, 0.4, 0.5])
+    ap.add_argument("--algo", default="logmap_f64", help="logmap_f64 | logmap_s16 | maxlog_s16 (decoders that deliver per-iteration decisions)")
+    ap.add_argument("--warmup", type=int, default=0)
+    ap.add_argument("--sub-block", type=int, default=0)
     args = ap.parse_args()
     if not RefLib.available():
         raise SystemExit("oracle/_ref/libittc_ref.so is missing (build it in the dev container: make -C oracle ref)")
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ittc_result_bler.json")))
     ref = gold["runs"][1]
     NIT = 8
-    dec = TurboDecoder(K, n_iter=NIT, algo="logmap_f64", max_batch=2048)
-    res = {"frames": args.frames, "points": []}
+    dec = TurboDecoder(K, n_iter=NIT, algo=args.algo, max_batch=2048, sub_block=args.sub_block, warmup=args.warmup)
+    res = {"frames": args.frames, "algo": args.algo, "plan": {k: dec.plan()[k] for k in ("sub_block", "warmup")}, "points": []}
     workers = max(1, len(os.sched_getaffinity(0)))
     with mp.Pool(workers) as pool:
         for eb in args.ebn0:
@@ -62,7 +65,8 @@ def main():
             jobs = [(eb, lo, min(lo + step, args.frames)) for lo in range(0, args.frames, step)]
             fe = np.zeros(NIT, np.int64)
             for bits, llr in pool.imap(_gen, jobs):
-                out = dec.decode(torch.from_numpy(llr).cuda(), want=("bits_iters",))["bits_iters"]
+                x = llr if args.algo == "logmap_f64" else llr.astype(np.float32)
+                out = dec.decode(torch.from_numpy(x).cuda(), want=("bits_iters",))["bits_iters"]
                 err = (out != torch.from_numpy(bits).cuda()[:, None, :].to(torch.int32)).any(dim=2)
                 fe += err.sum(dim=0).cpu().numpy()
             row = {"ebn0_db": eb, "bler": [], "reference": [], "z": []}
@@ -75,6 +79,12 @@ def main():
             res["points"].append(row)
             print("%.1f dB  ours %s\n        ref  %s\n        z    %s" % (eb, ["%.4f" % v for v in row["bler"]],
                   ["%.4f" % v for v in row["reference"]], ["%+.1f" % v for v in row["z"]]), flush=True)
+    zs = [abs(z) for r in res["points"] for z in r["z"]]
+    res["cells"] = len(zs)
+    res["cells_outside_95pct"] = sum(z > 1.96 for z in zs)
+    res["cells_outside_3sigma"] = sum(z > 3 for z in zs)
+    res["max_abs_z"] = max(zs) if zs else 0.0
+    print("cells %d, |z| > 1.96: %d, |z| > 3: %d, max |z| %.2f" % (len(zs), res["cells_outside_95pct"], res["cells_outside_3sigma"], res["max_abs_z"]))
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
 

@@ -93,18 +93,10 @@ void TurboDecoding(double *flow_for_decode, int *flow_decoded, int flow_length)
     ensure_decoder(K);
     tdb200_outputs out;
     std::memset(&out, 0, sizeof(out));
-    std::vector<uint8_t> last;
-    if (g.algo == TDB200_ALGO_LOGMAP_F64) {
-        out.bits_iters = flow_decoded;
-    } else {
-        last.resize(K);
-        out.bits = last.data();
-    }
+    // every decoder mode delivers the decisions after each iteration in the reference's flow_decoded layout (:1264)
+    out.bits_iters = flow_decoded;
     int s = tdb200_decode_batch(g.dec, flow_for_decode, TDB200_LLR_F64, TDB200_MEM_HOST, 1, &out, nullptr);
     if (s != TDB200_OK) die("tdb200_decode_batch", s);
-    if (g.algo != TDB200_ALGO_LOGMAP_F64)
-        for (int it = 0; it < g.n_iter; it++)
-            for (int i = 0; i < K; i++) flow_decoded[(size_t)it * K + i] = last[i];
     for (int i = 0; i < flow_length; i++) flow_for_decode[i] *= 0.5;  // the reference's side effect, :1202-1205
 }
 

@@ -498,7 +498,7 @@ static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int 
         a.opaque[0] = 0xffffffffu; a.opaque[1] = 4u; a.opaque[2] = 65536u; a.opaque[3] = 0xC0000000u;
         a.prefetch_stride = d->geom.resident_ctas;
         a.sm_count = d->sm_count;
-        a.bits = v_bits; a.iters_used = v_iters;
+        a.bits = v_bits; a.bits_iters = v_bits_iters; a.iters_used = v_iters;
         a.llr2 = static_cast<float *>(v_llr2); a.ext2 = static_cast<float *>(v_ext2);
         TDB_CUDA(launch_fast_s16(a, st, &d->launches_last));
     }
@@ -603,8 +603,11 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
 
     const bool f64 = (c.algo == TDB200_ALGO_LOGMAP_F64);
     const size_t fsz = f64 ? sizeof(double) : sizeof(float);  // native float type of the LLR outputs
-    if (!f64 && (out->bits_iters || out->llr_siso1))
-        return fail(TDB200_ERR_UNSUPPORTED, "bits_iters / llr_siso1 are produced by TDB200_ALGO_LOGMAP_F64 only");
+    const bool s16 = (c.algo == TDB200_ALGO_MAXLOG_S16 || c.algo == TDB200_ALGO_LOGMAP_S16);
+    if (!f64 && out->llr_siso1)
+        return fail(TDB200_ERR_UNSUPPORTED, "llr_siso1 is produced by TDB200_ALGO_LOGMAP_F64 only");
+    if (!f64 && !s16 && out->bits_iters)
+        return fail(TDB200_ERR_UNSUPPORTED, "bits_iters is produced by the fp64 and the packed 16-bit decoders only");
     if (!f64 && c.early_term >= 2 && out->ext_siso2)
         return fail(TDB200_ERR_UNSUPPORTED, "ext_siso2 is not available with the CRC stopping rule (a block may stop after SISO-1)");
     if (!f64 && c.early_term && out->llr_siso2)

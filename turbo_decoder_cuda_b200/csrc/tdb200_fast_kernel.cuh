@@ -133,12 +133,22 @@ struct PassCfg {
 struct GK {
     w32 P, M;  // floor(g/4) + 1 + T4 - 0x2000,  T4 - floor(g/4) - 0x2000
 };
-__device__ __forceinline__ w32 vnot(w32 x) { return ~x; }
+#ifndef TDB_LM_NOT_FMA
+#define TDB_LM_NOT_FMA 1
+#endif
+// ~x: as an IMAD with opaque constants (fma-heavy pipe) or as a LOP3 (ALU pipe) -- whichever pipe has slack
+__device__ __forceinline__ w32 vnot(w32 x, const PassCfg &c) { return TDB_LM_NOT_FMA ? x * c.neg1 + c.neg1 : ~x; }
+__device__ __forceinline__ w32 and_xor(w32 a, w32 b, w32 x)  // (a & b) ^ x in one LOP3 (the compiler shares the AND and spends three)
+{
+    w32 r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(r) : "r"(a), "r"(b), "r"(x));
+    return r;
+}
 __device__ __forceinline__ void quarter(w32 d1, const PassCfg &c, w32 &h, w32 &nh)
 {
-    const w32 f = (d1 >> 2) & c.lm;
-    h = f ^ c.lx2;
-    nh = f ^ c.lx1;
+    const w32 sh = d1 >> 2;
+    h = and_xor(sh, c.lm, c.lx2);
+    nh = and_xor(sh, c.lm, c.lx1);
 }
 __device__ __forceinline__ GK gk_of(w32 g, const PassCfg &c)
 {
@@ -159,21 +169,21 @@ __device__ __forceinline__ void bfly_corr(w32 h, w32 nh, const GK &g, w32 &ca, w
 __device__ __forceinline__ void alpha_quarters(const w32 (&a)[8], const PassCfg &c, w32 (&h)[4], w32 (&nh)[4])
 {
 #pragma unroll
-    for (int i = 0; i < 4; i++) quarter(vadd(a[2 * i + 1], vnot(a[2 * i])), c, h[i], nh[i]);
+    for (int i = 0; i < 4; i++) quarter(vadd(a[2 * i + 1], vnot(a[2 * i], c)), c, h[i], nh[i]);
 }
 // ... of a beta vector: (b4,b0) (b1,b5) (b6,b2) (b3,b7)
 __device__ __forceinline__ void beta_quarters(const w32 (&b)[8], const PassCfg &c, w32 (&h)[4], w32 (&nh)[4])
 {
-    quarter(vadd(b[4], vnot(b[0])), c, h[0], nh[0]);
-    quarter(vadd(b[1], vnot(b[5])), c, h[1], nh[1]);
-    quarter(vadd(b[6], vnot(b[2])), c, h[2], nh[2]);
-    quarter(vadd(b[3], vnot(b[7])), c, h[3], nh[3]);
+    quarter(vadd(b[4], vnot(b[0], c)), c, h[0], nh[0]);
+    quarter(vadd(b[1], vnot(b[5], c)), c, h[1], nh[1]);
+    quarter(vadd(b[6], vnot(b[2], c)), c, h[2], nh[2]);
+    quarter(vadd(b[3], vnot(b[7], c)), c, h[3], nh[3]);
 }
 __device__ __forceinline__ void alpha_step_lm_to(const w32 (&a)[8], const w32 (&h)[4], const w32 (&nh)[4], w32 u, w32 v, const PassCfg &c,
                                                  w32 (&o)[8])
 {
     const w32 w = vadd(u, v);
-    const GK gw = gk_of(w, c), gg = gk_of(vadd(u, vnot(v)), c);
+    const GK gw = gk_of(w, c), gg = gk_of(vadd(u, vnot(v, c)), c);
     w32 c0, c4, c5, c1, c2, c6, c7, c3;
     bfly_corr(h[0], nh[0], gw, c0, c4);
     bfly_corr(h[1], nh[1], gg, c5, c1);
@@ -189,7 +199,7 @@ __device__ __forceinline__ void alpha_step_lm_to(const w32 (&a)[8], const w32 (&
 __device__ __forceinline__ void beta_step_lm(w32 (&b)[8], const w32 (&h)[4], const w32 (&nh)[4], w32 u, w32 v, const PassCfg &c)
 {
     const w32 w = vadd(u, v);
-    const GK gw = gk_of(w, c), gg = gk_of(vadd(u, vnot(v)), c);
+    const GK gw = gk_of(w, c), gg = gk_of(vadd(u, vnot(v, c)), c);
     w32 c0, c1, c2, c3, c4, c5, c6, c7;
     bfly_corr(h[0], nh[0], gw, c0, c1);
     bfly_corr(h[1], nh[1], gg, c2, c3);
@@ -230,7 +240,7 @@ __device__ __forceinline__ void beta_step_x(w32 (&b)[8], w32 u, w32 v, const Pas
 __device__ __forceinline__ w32 maxstar_g(w32 x, w32 y, const PassCfg &c)
 {
     const w32 mx = __vmaxs2(x, y), mn = __vmins2(x, y);
-    const w32 e4 = (vadd(mn, vnot(mx)) >> 2) | c.lkc;
+    const w32 e4 = (vadd(mn, vnot(mx, c)) >> 2) | c.lkc;
     return vadd(mx, __viaddmax_s16x2_relu(e4, c.lku, 0u));
 }
 // first level: the input-0 terms alpha_i + beta_m, alpha_j + beta_n ("same") and the input-1 terms alpha_j + beta_m,
@@ -248,15 +258,15 @@ __device__ __forceinline__ w32 extrinsic_m1_lm(const w32 (&a)[8], const w32 (&hA
                                                const PassCfg &c)
 {
     w32 s01, x01, s67, x67, s23, x23, s45, x45;
-    lam_pair(a[0], a[1], b[0], b[4], hA[0], hA[0] ^ c.lm, hB[0], nhB[0], c, s01, x01);
-    lam_pair(a[6], a[7], b[7], b[3], hA[3], hA[3] ^ c.lm, hB[3], nhB[3], c, s67, x67);
-    lam_pair(a[2], a[3], b[5], b[1], hA[1], hA[1] ^ c.lm, hB[1], nhB[1], c, s23, x23);
-    lam_pair(a[4], a[5], b[2], b[6], hA[2], hA[2] ^ c.lm, hB[2], nhB[2], c, s45, x45);
+    lam_pair(a[0], a[1], b[0], b[4], hA[0], hA[0] * c.neg1 + c.lm, hB[0], nhB[0], c, s01, x01);
+    lam_pair(a[6], a[7], b[7], b[3], hA[3], hA[3] * c.neg1 + c.lm, hB[3], nhB[3], c, s67, x67);
+    lam_pair(a[2], a[3], b[5], b[1], hA[1], hA[1] * c.neg1 + c.lm, hB[1], nhB[1], c, s23, x23);
+    lam_pair(a[4], a[5], b[2], b[6], hA[2], hA[2] * c.neg1 + c.lm, hB[2], nhB[2], c, s45, x45);
     const w32 m0a = maxstar_g(s01, s67, c), m0b = maxstar_g(s23, s45, c);
     const w32 m1a = maxstar_g(x01, x67, c), m1b = maxstar_g(x23, x45, c);
     const w32 m0 = maxstar_g(m0a, vadd(m0b, v), c);
     const w32 m1 = maxstar_g(vadd(m1a, v), m1b, c);
-    return vadd(m1, vnot(m0));
+    return vadd(m1, vnot(m0, c));
 }
 
 // ---- channel-LLR load + quantisation (q = clamp(rint(x * 2^F), +-clip), oracle: quant())
@@ -412,18 +422,16 @@ __device__ __forceinline__ w32 extrinsic_m1(const w32 (&a)[8], const w32 (&b)[8]
 struct Elem {
     unsigned xoff, soff;  // byte offsets into X / the systematic byte planes
 };
-template <bool IL>
-__device__ __forceinline__ Elem elem_of(const PassCfg &c, unsigned tabval, int idx)
+__device__ __forceinline__ Elem elem_of(const bool IL, const PassCfg &c, unsigned tabval, int idx)
 {
     Elem e;
     e.soff = IL ? tabval : (unsigned)idx;
     e.xoff = IL ? tabval * c.four : 4u * (unsigned)idx;
     return e;
 }
-template <bool IL>
-__device__ __forceinline__ Elem elem_at(const PassCfg &c, const Smem &sm, int idx)
+__device__ __forceinline__ Elem elem_at(const bool IL, const PassCfg &c, const Smem &sm, int idx)
 {
-    return elem_of<IL>(c, IL ? (unsigned)sm.tab[idx] : 0u, idx);
+    return elem_of(IL, c, IL ? (unsigned)sm.tab[idx] : 0u, idx);
 }
 __device__ __forceinline__ w32 &word_at(w32 *base, unsigned xoff)
 {
@@ -443,8 +451,8 @@ __device__ __forceinline__ w32 sys_biased(const PassCfg &c, const Smem &sm, cons
 // ahead, so the look-up is off the critical path).  Returns the decision bits of the window (WANT
 // only): sign of step k in bit 15-k (codeblock A) / 31-k (codeblock B); weak collects, per lane, a
 // non-zero value if some |a-posteriori| of the window is below the stopping threshold.
-template <bool IL, bool WANT, bool LM>
-__device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, const w32 *par, const int base, const int PP,
+template <bool LM>
+__device__ __forceinline__ w32 bwd_window(const bool IL, const bool WANT, const PassCfg &c, const Smem &sm, const w32 *par, const int base, const int PP,
                                           const unsigned (&tabin)[8], const w32 (&a0)[8], w32 (&b)[8], w32 *stage, w32 &weak)
 {
     w32 aw[8][8], u[8], v[8];
@@ -455,7 +463,7 @@ __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, cons
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const int idx = base + k * PP;
-        el[k] = elem_of<IL>(c, tabin[k], idx);
+        el[k] = elem_of(IL, c, tabin[k], idx);
         u[k] = x_at(sm, el[k]);
         v[k] = par[idx];
         if (LM) {
@@ -504,11 +512,14 @@ __device__ __forceinline__ w32 bwd_window(const PassCfg &c, const Smem &sm, cons
 // pass go to sm.dec (one word per two windows) and the return value has bits 0-15 / 16-31 set
 // where a decision of codeblock A / B differs from what sm.dec held before; weak gets a non-zero
 // low / high half if some a-posteriori magnitude of codeblock A / B is below the stopping threshold.
-template <bool IL, bool WANT, int KP, int KNW, int KG, bool LM>
+template <int ILT, int WANTT, int KP, int KNW, int KG, bool LM>
 __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, const Smem &sm, const w32 *par, w32 (&na)[8], w32 (&nb)[8],
                                          const int t, const bool active, const bool first_fixed, const bool last_fixed, w32 *stage,
-                                         w32 &weak)
+                                         w32 &weak, const bool il_rt = false, const bool want_rt = false)
 {
+    // ILT / WANTT: 0 / 1 compile-time, -1 run-time (the Log-MAP kernels keep ONE copy of the pass: its body is three
+    // times the max-log one, and four inlined copies would be a quarter of a megabyte of code)
+    const bool IL = ILT < 0 ? il_rt : (ILT != 0), WANT = WANTT < 0 ? want_rt : (WANTT != 0);
     const int P = KP > 0 ? KP : g.P, PP = KP > 0 ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW, G = KP ? KG : g.G;  // KP < 0: run-time P
     const int L = 8 * NW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -536,8 +547,8 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int ia = base_a + k * PP, ib = base_b + (7 - k) * PP;
-                alpha_step_x<LM>(a, x_at(sm, elem_at<IL>(c, sm, ia)), par[ia], c);
-                beta_step_x<LM>(b, x_at(sm, elem_at<IL>(c, sm, ib)), par[ib], c);
+                alpha_step_x<LM>(a, x_at(sm, elem_at(IL, c, sm, ia)), par[ia], c);
+                beta_step_x<LM>(b, x_at(sm, elem_at(IL, c, sm, ib)), par[ib], c);
             }
         }
 #pragma unroll
@@ -559,7 +570,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
             Elem el[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                el[k] = elem_of<IL>(c, offn[k], (8 * w + k) * PP + t);
+                el[k] = elem_of(IL, c, offn[k], (8 * w + k) * PP + t);
                 if (IL) offn[k] = sm.tab[(8 * (w + 1) + k) * PP + t];
             }
             if (w > 0) {
@@ -593,7 +604,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int idx = base + k * PP;
-                alpha_step_x<LM>(tmp, x_at(sm, elem_at<IL>(c, sm, idx)), par[idx], c);
+                alpha_step_x<LM>(tmp, x_at(sm, elem_at(IL, c, sm, idx)), par[idx], c);
             }
 #pragma unroll
             for (int s = 0; s < 8; s++) sa[s] = tmp[s];
@@ -622,7 +633,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
                 off[k] = offn[k];
                 if (IL) offn[k] = sm.tab[(8 * max(w - 1, 0) + k) * PP + t];
             }
-            const w32 acc = bwd_window<IL, WANT, LM>(c, sm, par, 8 * w * PP + t, PP, off, aw0, b, stage, weak);
+            const w32 acc = bwd_window<LM>(IL, WANT, c, sm, par, 8 * w * PP + t, PP, off, aw0, b, stage, weak);
             if (w == w_sb) {
 #pragma unroll
                 for (int s = 0; s < 8; s++) sb[s] = b[s];
@@ -760,6 +771,33 @@ __device__ __forceinline__ uint2 crc_of_decisions(const FastArgs &A, const Smem 
     return r;
 }
 
+// Per-iteration hard decisions (flow_decoded + K*iteration, ITTC/log_map.cpp:1261-1264): the decision masks of the
+// pass that just ran, scattered to rows [row_lo, row_hi) of the codeblock's [n_iter][K] int slab.  A diagnostic output
+// (the reference's per-iteration error counting, main.cpp:224-237): plain 4-byte stores, not staged.
+__device__ __forceinline__ void emit_iter_bits(const FastArgs &A, const Smem &sm, int NW, int P, int PP, int L, int K, int t, bool natural,
+                                               int cbA, bool hasB, int row_lo, int row_hi)
+{
+    for (int w2 = 0; w2 < (NW + 1) / 2; w2++) {
+        const w32 word = sm.dec[w2 * P + t];
+#pragma unroll 1
+        for (int kk = 0; kk < 16; kk++) {
+            const int j = 16 * w2 + (kk & 8) + 7 - (kk & 7);
+            if (j >= L) continue;
+            int n = t * L + j;
+            if (!natural) {
+                const int e = sm.tab[j * PP + t];
+                const int jj = e / PP, tt = e - jj * PP;
+                n = tt * L + jj;
+            }
+            const int32_t ba = (int32_t)(((word >> kk) & 1u) ^ 1u), bb = (int32_t)(((word >> (16 + kk)) & 1u) ^ 1u);
+            for (int r = row_lo; r < row_hi; r++) {
+                A.bits_iters[((size_t)cbA * A.n_iter + r) * K + n] = ba;
+                if (hasB) A.bits_iters[((size_t)(cbA + 1) * A.n_iter + r) * K + n] = bb;
+            }
+        }
+    }
+}
+
 template <int LLR_T, int KP, int KNW, int KG, bool CRC, bool LM = false>
 __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 128 : (KP == -2 ? 192 : 256)), KP ? 2 : 1) fast_s16_kernel(FastArgs A)
 {
@@ -891,6 +929,47 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
     // CRC: the stopping rule by CRC has its own instantiations (the default kernels do not carry the path); one pair per CTA
     bool natural = false;                     // the delivered decisions are SISO-1's (natural order)
     int used = A.n_iter, usedA = 0, usedB = 0;
+    if constexpr (LM) {
+        // one copy of the pass serves both SISOs: the boundary vectors of the SISO that runs next sit in na[0] / nb[0]
+        // and trade places with the other pair after every pass
+#pragma unroll 1
+        for (int hp = 0; hp < 2 * A.n_iter; hp++) {
+            const bool il = (hp & 1) != 0;
+            const int it = hp >> 1;
+            const bool last = (it == A.n_iter - 1);
+            const bool want = il && (A.early_term == 1 || last || A.bits_iters != nullptr);
+            w32 weak = 0;
+            const w32 chg = siso_pass<-1, -1, KP, KNW, KG, true>(c, g, sm, il ? sm.par2 : sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed,
+                                                                 (want_soft && last && il) ? sm.par1 : nullptr, weak, il, want);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const w32 ta = na[0][j], tb2 = nb[0][j];
+                na[0][j] = na[1][j]; nb[0][j] = nb[1][j];
+                na[1][j] = ta; nb[1][j] = tb2;
+            }
+            if (il && A.bits_iters && active) emit_iter_bits(A, sm, NW, P, PP, L, K, t, false, cbA, hasB, it, it + 1);
+            if (il && A.early_term == 1) {
+                int chA, chB;
+                if (one_pair) {
+                    chA = __syncthreads_or((int)((chg | weak) & 0xffffu));
+                    chB = __syncthreads_or((int)((chg | weak) >> 16));
+                } else {
+                    if (tid < NP) flags[tid] = 0u;
+                    __syncthreads();
+                    if (active && (chg | weak)) atomicOr(&flags[q], chg | weak);
+                    __syncthreads();
+                    const unsigned f = active ? flags[q] : 0u;
+                    chA = (int)(f & 0xffffu); chB = (int)(f >> 16);
+                }
+                if (it >= 1) {
+                    if (!chA && !usedA) usedA = it + 1;
+                    if (!chB && !usedB) usedB = it + 1;
+                }
+                const bool done = (usedA && usedB) || (!one_pair && !active);
+                if (one_pair ? done : (__syncthreads_and((int)done) != 0)) { used = it + 1; break; }
+            }
+        }
+    } else
     for (int it = 0; it < A.n_iter; it++) {
         const bool last = (it == A.n_iter - 1);
         w32 weak = 0;
@@ -899,7 +978,7 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
             if (it >= 1) {
                 // SISO-1 with decisions; stop when the natural-order decisions of both codeblocks divide by the
                 // generator -- half an iteration after the SISO-2 pass that made them right
-                siso_pass<false, true, KP, KNW, KG, LM>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
+                siso_pass<0, 1, KP, KNW, KG, LM>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
                 const uint2 rem = crc_of_decisions(A, sm, flags, P, NW, t, active);
                 if (!rem.x && !usedA) usedA = it + 1;
                 if (!rem.y && !usedB) usedB = it + 1;
@@ -907,12 +986,13 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                 siso1_done = true;
             }
         }
-        if (!siso1_done) siso_pass<false, false, KP, KNW, KG, LM>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
-        if (A.early_term == 1 || last) {
+        if (!siso1_done) siso_pass<0, 0, KP, KNW, KG, LM>(c, g, sm, sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed, nullptr, weak);
+        if (A.early_term == 1 || last || A.bits_iters != nullptr) {
             // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
             // (by then dead) parity-1 array
-            const w32 chg = siso_pass<true, true, KP, KNW, KG, LM>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed,
+            const w32 chg = siso_pass<1, 1, KP, KNW, KG, LM>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed,
                                                                (want_soft && last) ? sm.par1 : nullptr, weak);
+            if (A.bits_iters && active) emit_iter_bits(A, sm, NW, P, PP, L, K, t, false, cbA, hasB, it, it + 1);
             if (A.early_term == 1) {
                 // stop: no decision of this iteration differs from the previous one and no
                 // a-posteriori value is weaker than the threshold -- per codeblock; a CTA leaves when
@@ -937,11 +1017,13 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                 if (one_pair ? done : (__syncthreads_and((int)done) != 0)) { used = it + 1; break; }
             }
         } else {
-            siso_pass<true, false, KP, KNW, KG, LM>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed, nullptr, weak);
+            siso_pass<1, 0, KP, KNW, KG, LM>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed, nullptr, weak);
         }
     }
     if (!usedA) usedA = used;
     if (!usedB) usedB = used;
+    if (A.bits_iters && active && (used < A.n_iter || natural))  // rows past an early stop repeat the last one
+        emit_iter_bits(A, sm, NW, P, PP, L, K, t, natural, cbA, hasB, natural ? used - 1 : used, A.n_iter);
 
     // ---- hard decisions, natural order: decision() :862-879 is the sign bit kept in sm.dec,
     //      random_deinterlvr_int :1264 is the scatter of those bits to byte n = pi(i) of a staging

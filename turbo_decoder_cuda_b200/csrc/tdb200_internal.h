@@ -113,6 +113,7 @@ struct FastArgs {
     int sm_count;
     // outputs (device, nullable)
     uint8_t *bits;
+    int32_t *bits_iters;  // [n_cb][n_iter][K] decisions after every iteration (diagnostic; forces a decision pass per iteration)
     int32_t *iters_used;
     float *llr2, *ext2;  // [n_cb][K+3]
 };
