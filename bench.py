@@ -107,22 +107,23 @@ def cpu_reference_decoder():
 
 
 def run_reference(args):
-    """--impl reference: the reference CPU Log-MAP (fp64, 8 iterations) on all host cores, rank 0 only."""
+    """--impl reference: the reference CPU Log-MAP (fp64, 8 iterations) on all host cores, rank 0 only.
+    Nothing of the product is imported here: frames, QPP parameters and the decoder all come from oracle/."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from turbo_decoder_cuda_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    o = Oracle()
     cores = host_cores()
     decode, kind = cpu_reference_decoder()
     # a bounded sample per step, sized from a calibration decode so that the whole run (all steps) stays
     # near two minutes of wall time whatever --steps is
-    _, cal = synth.make_batch(K, max(cores, 1), args.ebn0, seed=999, device="cpu", dtype=torch.float64)
-    _, t_cal = decode(cal.numpy(), cores)           # seconds for one codeword per core
+    _, cal = o.make_batch(K, max(cores, 1), args.ebn0, seed=999)
+    _, t_cal = decode(cal, cores)           # seconds for one codeword per core
     budget_s = 120.0
     n_sample = args.ref_sample or int(max(cores, min(args.batch, cores * budget_s / (max(args.steps, 1) * max(t_cal, 1e-3)))))
-    bits, llr = synth.make_batch(K, n_sample, args.ebn0, seed=1000, device="cpu", dtype=torch.float64)
-    llr = llr.numpy()
+    bits, llr = o.make_batch(K, n_sample, args.ebn0, seed=1000)
     for _ in range(args.warmup):
         decode(llr[:max(cores, 1)], cores)
     t = 0.0
@@ -130,13 +131,17 @@ def run_reference(args):
     for _ in range(args.steps):
         out, secs = decode(llr, cores)
         t += secs
-        errs += int((out != bits.numpy()).sum())
+        errs += int((out != bits).sum())
     value = n_sample * K * args.steps / t / 1e9
     line = {
         "impl": "reference", "metric": "decoded info Gbit/s, K=6144, 8 iterations", "value": value, "unit": "Gbit/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.batch, None),
+        "config": {"workload": "the reference's only CPU path for BASELINE configs[1]: LTE turbo K=6144 QPP(263,480), fp64 Log-MAP "
+                               "with the 16-step max* table (ITTC/log_map.cpp), 8 iterations, a sample of %d codeblocks per step" % n_sample,
+                   "K": K, "n_iter": N_ITER, "batch_per_gpu": n_sample, "ebn0_db": args.ebn0, "algo": "logmap_lut_f64",
+                   "llr_input": "float64 [n_cb, 3K+12], reference multiplex order",
+                   "parallelism": "one codeword per host thread, %d threads" % cores},
         "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": kind,
                          "sample": "%d codeblocks per step (K=6144, fp64 LUT Log-MAP, 8 iterations, one codeword per thread)" % n_sample},
         "e2e": {"value": value, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -231,7 +236,7 @@ def run_ours(args):
             step_et()
         g1.record(stream)
         torch.cuda.synchronize()
-        et_info = {"gbit_s_this_rank": batch * K * args.steps / (g0.elapsed_time(g1) * 1e-3) / 1e9,
+        et_info = {"_ms": g0.elapsed_time(g1) / args.steps,
                    "mean_iterations": float(et_iters.float().mean().item()),
                    "ber": float((et_bits != bits).sum().item()) / (batch * K),
                    "rule": "no hard decision changes and every |a-posteriori| >= 8.0, at most 8 iterations"}
@@ -255,12 +260,42 @@ def run_ours(args):
                 step_crc()
             g1.record(stream)
             torch.cuda.synchronize()
-            et_info["crc24b_rule"] = {"gbit_s_this_rank": batch * K * args.steps / (g0.elapsed_time(g1) * 1e-3) / 1e9,
-                                      "mean_iterations": float(et_iters.float().mean().item()),
-                                      "ber": float((et_bits != crc_bits).sum().item()) / (batch * K),
+            et_info["_crc_ms"] = g0.elapsed_time(g1) / args.steps
+            et_info["crc24b_rule"] = {"mean_iterations_this_rank": float(et_iters.float().mean().item()),
+                                      "ber_this_rank": float((et_bits != crc_bits).sum().item()) / (batch * K),
                                       "rule": "hard decisions of SISO-1 divide by the CRC24B generator (the last iteration counted is half-run)"}
             dec_crc.close()
             del crc_llr
+
+    # ---- the Log-MAP decoder in the same packed arithmetic (TDB200_ALGO_LOGMAP_S16): the mode that sits on the
+    #      reference's BER/FER curve (BASELINE configs[2]), same batch, device-resident, 8 fixed iterations
+    lm_info = None
+    if args.algo == "maxlog_s16" and not args.no_logmap:
+        dec_lm = TurboDecoder(K, n_iter=N_ITER, algo="logmap_s16", device=local, max_batch=batch)
+        lm_bits = torch.empty((batch, K), dtype=torch.uint8, device=dev)
+
+        def step_lm():
+            dec_lm.decode_raw(llr.data_ptr(), tdb.LLR_F32, tdb.MEM_DEVICE, batch, bits=lm_bits.data_ptr(), stream=sp)
+        for _ in range(3):
+            step_lm()
+        torch.cuda.synchronize()
+        n_lm = max(1, args.steps // 4)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(n_lm):
+            step_lm()
+        g1.record(stream)
+        torch.cuda.synchronize()
+        lm_ms = g0.elapsed_time(g1) / n_lm
+        pl = dec_lm.plan()
+        lm_info = {"ms_per_step": lm_ms, "steps": n_lm, "ber": float((lm_bits != bits).sum().item()) / (batch * K),
+                   "algo": "logmap_s16", "sub_block": pl["sub_block"], "guard": pl["warmup"], "frac_bits": 4,
+                   "correction": "max* = max + max(0, 0.625 - |d|/4), all 30 max* per trellis step"}
+        dec_lm.close()
+
+    # ---- measured issue rate of the add-compare-select mix (the denominator of roofline.alu)
+    rate_mix = dec.issue_rate(2)
+    rate_alu = dec.issue_rate(0)
 
     # ---- end to end through host buffers (pinned): H2D + decode + D2H inside the timed region
     h_llr = torch.empty(llr.shape, dtype=llr.dtype, pin_memory=True)
@@ -316,13 +351,40 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_e2e8 = 1e3 * (time.perf_counter() - t8) / n16
 
+    # per-rank host-to-device rate of the headline end-to-end leg (float32 LLRs), for the scaling diagnosis
+    h2d_gbs = batch * (3 * K + 12) * 4 * args.steps / (ms_e2e * 1e-3) / 1e9
+    h2d_per_rank = [h2d_gbs]
+    et_ms = et_info.pop("_ms", None) if et_info else None
+    crc_ms = et_info.pop("_crc_ms", None) if et_info else None
+    lm_ms_all = lm_info["ms_per_step"] if lm_info else 0.0
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_e2e16, ms_e2e8, et_ms or 0.0, crc_ms or 0.0, lm_ms_all], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
-        b = torch.tensor([ber], device=dev, dtype=torch.float64)
+        ms, ms_e2e, ms_e2e16, ms_e2e8, lm_ms_all = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[6])
+        if et_ms is not None:
+            et_ms = float(t[4])
+        if crc_ms is not None:
+            crc_ms = float(t[5])
+        b = torch.tensor([ber, et_info["mean_iterations"] if et_info else 0.0, et_info["ber"] if et_info else 0.0,
+                          lm_info["ber"] if lm_info else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
         ber = float(b[0]) / world
+        if et_info:
+            et_info["mean_iterations"], et_info["ber"] = float(b[1]) / world, float(b[2]) / world
+        if lm_info:
+            lm_info["ber"] = float(b[3]) / world
+        g = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([h2d_gbs], device=dev, dtype=torch.float64))
+        h2d_per_rank = [float(x[0]) for x in g]
+    if et_info:
+        et_info["value"] = world * batch * K / (et_ms * 1e-3) / 1e9
+        et_info["unit"] = "Gbit/s, all ranks (max time over ranks)"
+        if crc_ms is not None:
+            et_info["crc24b_rule"]["value"] = world * batch * K / (crc_ms * 1e-3) / 1e9
+    if lm_info:
+        lm_info["ms_per_step"] = lm_ms_all
+        lm_info["value"] = world * batch * K / (lm_ms_all * 1e-3) / 1e9
+        lm_info["unit"] = "Gbit/s, all ranks"
 
     if rank == 0:
         total_bits = float(world) * batch * K * args.steps
@@ -336,7 +398,9 @@ def run_ours(args):
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        alu_peak = 148 * 128 * sm_max_mhz * 1e6 * 2  # packed 16-bit lane-ops/s
+        sm_count = plan["sm_count"]
+        alu_peak = sm_count * 128 * sm_max_mhz * 1e6 * 2  # packed 16-bit lane-ops/s
+        alu_peak_meas = sm_count * rate_mix * sm_max_mhz * 1e6 * 2  # the same with the measured issue rate of the mix
         alu_ach = (batch * K / (kernel_ms * 1e-3)) * OPS_PER_INFO_BIT
         line = {
             "metric": "decoded info Gbit/s, K=6144, 8 iterations", "value": value, "unit": "Gbit/s",
@@ -345,10 +409,12 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(args, batch, plan),
             "e2e": {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": batch * (3 * K + 12) * 4,
                     "d2h_bytes_per_step": batch * K, "matches_device_path": e2e_ok,
-                    "with_float16_llrs_this_rank": {"value": batch * K / (ms_e2e16 * 1e-3) / 1e9, "unit": "Gbit/s",
-                                                    "h2d_bytes_per_step": batch * (3 * K + 12) * 2},
-                    "with_int8_llrs_this_rank": {"value": batch * K / (ms_e2e8 * 1e-3) / 1e9, "unit": "Gbit/s",
-                                                 "h2d_bytes_per_step": batch * (3 * K + 12), "matches_device_path": e2e8_ok}},
+                    "h2d_gb_s_per_rank": h2d_per_rank,
+                    "with_float16_llrs": {"value": world * batch * K / (ms_e2e16 * 1e-3) / 1e9, "unit": "Gbit/s, all ranks",
+                                          "h2d_bytes_per_step": batch * (3 * K + 12) * 2},
+                    "with_int8_llrs": {"value": world * batch * K / (ms_e2e8 * 1e-3) / 1e9, "unit": "Gbit/s, all ranks",
+                                       "h2d_bytes_per_step": batch * (3 * K + 12), "matches_device_path": e2e8_ok,
+                                       "note": "the decoder's own channel format (8-bit fixed point, ITTC/log_map.cpp:1283 dectobin intent): the documented host wire format"}},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak,
@@ -356,11 +422,23 @@ def run_ours(args):
                          "peak_source": peak_src, "kernel": "fast_s16_kernel", "kernel_ms": kernel_ms,
                          "note": "secondary bound: the path is ALU-bound by design (SURVEY.md 8d); see roofline.alu",
                          "alu": {"achieved": alu_ach / 1e12, "peak": alu_peak / 1e12, "unit": "Tlane-op/s (packed 16-bit)",
-                                 "frac": alu_ach / alu_peak, "ops_per_info_bit": OPS_PER_INFO_BIT}},
+                                 "frac": alu_ach / alu_peak, "ops_per_info_bit": OPS_PER_INFO_BIT,
+                                 "peak_measured": alu_peak_meas / 1e12, "frac_of_measured": alu_ach / alu_peak_meas,
+                                 "issue_rate_measured": {"viaddmnmx_viadd_mix": rate_mix, "viaddmnmx_alone": rate_alu,
+                                                         "unit": "thread-ops/clk/SM (128 = one warp-instruction per clock per sub-partition)",
+                                                         "how": "tdb200_ubench_issue_rate, run in this process before the timed region"}}},
             "ber": ber,
         }
         if et_info:
             line["early_termination"] = et_info
+        if lm_info:
+            # 30 max* per trellis step, each max + |difference| + correction + add instead of one max: 71 + 4 * 30 operations
+            lm_ops = 2 * N_ITER * (71 + 4 * 30) * (K + 3) / K
+            lm_ach = (world * batch * K / (lm_info["ms_per_step"] * 1e-3)) * lm_ops / world
+            lm_info["roofline_alu"] = {"achieved": lm_ach / 1e12, "peak": alu_peak / 1e12, "peak_measured": alu_peak_meas / 1e12,
+                                       "unit": "Tlane-op/s (packed 16-bit), per GPU", "frac": lm_ach / alu_peak,
+                                       "frac_of_measured": lm_ach / alu_peak_meas, "ops_per_info_bit": lm_ops}
+            line["logmap_s16"] = lm_info
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()
             decode, kind = cpu_reference_decoder()
@@ -407,6 +485,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0, help="codeblocks per CPU-baseline step (0 = 4 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-early-term", action="store_true", help="skip the informational early-termination leg")
+    ap.add_argument("--no-logmap", action="store_true", help="skip the Log-MAP (logmap_s16) leg")
     ap.add_argument("--sub-block", type=int, default=0, help="trellis steps per sub-block (0 = the library's plan)")
     ap.add_argument("--guard", type=int, default=0, help="warm-up steps across sub-block boundaries (with --sub-block)")
     args = ap.parse_args()

@@ -51,7 +51,9 @@ typedef enum tdb200_algo {
     TDB200_ALGO_MAXLOG_S16 = 1,
     /* fp32 Log-MAP: max*(x,y) = max + ln(1+e^-|x-y|) evaluated exactly (the reference tabulates the
      * same correction in 16 steps), sub-block parallel with boundary-state initialisation -- the
-     * windowed Log-MAP.  One codeblock per CTA; extrinsic scale 1.0 as in the reference. */
+     * windowed Log-MAP.  One codeblock per CTA; extrinsic scale 1.0 as in the reference.  The three fp32 modes keep
+     * the channel LLRs in shared memory as IEEE binary16 (metrics and extrinsics are fp32): inputs are rounded to
+     * binary16 and clamped to +-65504 on the way in. */
     TDB200_ALGO_LOGMAP_F32 = 2,
     /* fp32 max-log-MAP on the same structure (extrinsic scale 0.75 by default). */
     TDB200_ALGO_MAXLOG_F32 = 3,
@@ -118,7 +120,11 @@ typedef struct tdb200_config {
  * decode call.  T = K + 3. */
 typedef struct tdb200_outputs {
     uint8_t *bits;        /* [n_cb][K]  hard decisions after the last iteration run, natural
-                             order, one byte per bit (LLR < 0 -> 0 else 1, log_map.cpp:862-879) */
+                             order, one byte per bit (LLR < 0 -> 0 else 1, log_map.cpp:862-879).
+                             With early_term = 1 a codeblock delivers the decisions of ITS OWN stopping
+                             iteration (iters_used), independent of the codeblocks it shares a CTA with.
+                             With the CRC rule (early_term = 2 / 3) the two codeblocks of a 32-bit lane pair
+                             leave together: a block's bits are those after max(iters_used) of the pair. */
     int32_t *bits_iters;  /* [n_cb][n_iter][K] decisions after EVERY iteration, as ints: one
                              codeblock's slab is exactly TurboDecoding's flow_decoded
                              (log_map.cpp:1264).  Rows past an early stop repeat the last one.
@@ -227,7 +233,12 @@ int tdb200_decode_symbols_batch(tdb200_decoder *dec, const void *sym_i, const vo
  * multiplexing into d0/d1/d2 (5.1.3.2.2), sub-block interleavers, circular buffer and bit selection
  * from k0(rv) with <NULL> pruning (5.1.4.1).  The turbo-code side keeps the reference's multiplex
  * order [n_cb][3K+12]; the channel side is [n_cb][E].  rv = redundancy version 0..3; ncb = soft
- * buffer size N_cb (0: the full circular buffer K_w = 3 * 32 * ceil((K+4)/32)). */
+ * buffer size N_cb (0: the full circular buffer K_w = 3 * 32 * ceil((K+4)/32)).
+ * Deviation from the standard, by design: FILLER BITS ARE ORDINARY ZEROS here.  5.1.3.2.1 / 5.1.4.1.2 turn the F
+ * filler positions of d0 and d1 of a transport block's first code block into <NULL>s that are never transmitted;
+ * these entry points prune only the interleaver's dummy <NULL>s, so for a transport block with F > 0 the bit
+ * selection of that one block differs from a standard-conformant transmitter (the chain here is self-consistent:
+ * transmitter and receiver of this library agree).  Pinned by a hand-derived K = 40 known answer (tests/test_oracle.py). */
 int tdb200_rate_match_batch(tdb200_decoder *dec, const uint8_t *coded, uint8_t *e_bits, int mem, int n_cb,
                             int E, int rv, int ncb, void *stream);
 
@@ -280,6 +291,12 @@ typedef struct tdb200_plan_info {
     int kernel_launches_last_call; /* kernels launched by the most recent decode call */
 } tdb200_plan_info;
 int tdb200_get_plan(const tdb200_decoder *dec, tdb200_plan_info *info);
+
+/* Measurement aid (no reference counterpart): issue rate of the add-compare-select instruction mix on `device`, in
+ * thread-operations per clock per SM (128 = one warp-instruction per clock on each of the four sub-partitions).
+ * mix 0: VIADDMNMX.S16x2 alone (ALU pipe), 1: VIADD.16x2 alone (fma-heavy pipe), 2: both interleaved -- the mix of the
+ * recursions.  bench.py turns it into the measured denominator of its ALU roofline. */
+int tdb200_ubench_issue_rate(int device, int mix, double *thread_ops_per_clk_per_sm);
 
 const char *tdb200_last_error(void);
 const char *tdb200_status_string(int status);

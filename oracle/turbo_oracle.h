@@ -100,6 +100,7 @@ typedef struct tdo_fx_params {
     int lm_warm_maxlog; /* exploration: warm-up recursions without the correction */
     int lm_upper_off; /* exploration */
     int lm_t4_lam;    /* exploration: T4 of the first a-posteriori level (0 = lm_t4) */
+    int lm_exact;     /* exploration: 1 = linear correction on the exact difference, 2 = exact correction (rounded) */
 } tdo_fx_params;
 
 /* Returns the number of iterations run.  bits_out[K] final decisions; le_out

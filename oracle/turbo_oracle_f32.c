@@ -40,6 +40,8 @@ static inline float mx(float x, float y)
 static inline float h16(float x)
 {
     if (!(x == x)) x = 0.0f; /* NaN -> erasure */
+    if (x > 65504.0f) x = 65504.0f; /* the finite range of binary16: no infinities in the recursions */
+    if (x < -65504.0f) x = -65504.0f;
     return (float)(_Float16)x; /* round to nearest even, like __float2half_rn */
 }
 

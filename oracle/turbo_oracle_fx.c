@@ -107,6 +107,8 @@ static int extrinsic(const int *a, const int *b, int v)
 static __thread int g_T4;      /* correction at d = 0, in fixed-point units */
 static __thread int g_upper;   /* how the upper levels of the a-posteriori max* trees are corrected: 0 linear, 1 trapezoid, 2 not at all */
 static __thread int g_T4L;     /* ... of the first level of the a-posteriori trees */
+static __thread int g_exact;   /* exploration: 1 = linear correction on the exact difference, 2 = the exact Jacobian correction, rounded */
+static __thread int g_F;
 static __thread int g_uoff;    /* rounding offset of the generic max* */
 static __thread int g_TT, g_TC;   /* trapezoid: c = min(TC, max(0, TT - |d|)) */
 
@@ -115,8 +117,15 @@ static inline int relu(int x) { return x > 0 ? x : 0; }
 static inline int imin(int a, int b) { return a < b ? a : b; }
 
 /* corrections of the two max* of a butterfly: ca for max*(p + g, q), cb for max*(q + g, p); g4 = floor(g / 4) */
-static inline void bfly_corr(int p, int q, int g4, int *ca, int *cb)
+static inline int corr_exact(int d)
 {
+    if (d < 0) d = -d;
+    if (g_exact == 1) return relu((4 * g_T4 + 2 - d) >> 2);
+    return (int)floor(log1p(exp(-(double)d / (double)(1 << g_F))) * (double)(1 << g_F) + 0.5);
+}
+static inline void bfly_corr_g(int p, int q, int g4, int g, int *ca, int *cb)
+{
+    if (g_exact) { *ca = corr_exact(p + g - q); *cb = corr_exact(q + g - p); return; }
     const int h = asr2(chk(p - q - 1)), nh = -h - 1;
     *ca = relu(imin(h + g4 + 1 + g_T4, nh - g4 + g_T4));
     *cb = relu(imin(nh + g4 + 1 + g_T4, h - g4 + g_T4));
@@ -126,16 +135,16 @@ static void alpha_step_lm(const int *a, int u, int v, int *o)
 {
     const int w = add(u, v), w4 = asr2(w), gm4 = asr2(chk(u - v - 1));
     int ca, cb;
-    bfly_corr(a[1], a[0], w4, &ca, &cb);
+    bfly_corr_g(a[1], a[0], w4, w, &ca, &cb);
     o[0] = add(imax(add(a[1], w), a[0]), ca);
     o[4] = add(imax(add(a[0], w), a[1]), cb);
-    bfly_corr(a[3], a[2], gm4, &ca, &cb);
+    bfly_corr_g(a[3], a[2], gm4, u - v, &ca, &cb);
     o[5] = add(imax(add(a[3], u), add(a[2], v)), ca);
     o[1] = add(imax(add(a[2], u), add(a[3], v)), cb);
-    bfly_corr(a[5], a[4], gm4, &ca, &cb);
+    bfly_corr_g(a[5], a[4], gm4, u - v, &ca, &cb);
     o[2] = add(imax(add(a[5], u), add(a[4], v)), ca);
     o[6] = add(imax(add(a[4], u), add(a[5], v)), cb);
-    bfly_corr(a[7], a[6], w4, &ca, &cb);
+    bfly_corr_g(a[7], a[6], w4, w, &ca, &cb);
     o[7] = add(imax(add(a[7], w), a[6]), ca);
     o[3] = add(imax(add(a[6], w), a[7]), cb);
 }
@@ -144,16 +153,16 @@ static void beta_step_lm(const int *b, int u, int v, int *o)
 {
     const int w = add(u, v), w4 = asr2(w), gm4 = asr2(chk(u - v - 1));
     int ca, cb;
-    bfly_corr(b[4], b[0], w4, &ca, &cb);
+    bfly_corr_g(b[4], b[0], w4, w, &ca, &cb);
     o[0] = add(imax(add(b[4], w), b[0]), ca);
     o[1] = add(imax(add(b[0], w), b[4]), cb);
-    bfly_corr(b[1], b[5], gm4, &ca, &cb);
+    bfly_corr_g(b[1], b[5], gm4, u - v, &ca, &cb);
     o[2] = add(imax(add(b[1], u), add(b[5], v)), ca);
     o[3] = add(imax(add(b[5], u), add(b[1], v)), cb);
-    bfly_corr(b[6], b[2], gm4, &ca, &cb);
+    bfly_corr_g(b[6], b[2], gm4, u - v, &ca, &cb);
     o[4] = add(imax(add(b[6], u), add(b[2], v)), ca);
     o[5] = add(imax(add(b[2], u), add(b[6], v)), cb);
-    bfly_corr(b[3], b[7], w4, &ca, &cb);
+    bfly_corr_g(b[3], b[7], w4, w, &ca, &cb);
     o[6] = add(imax(add(b[3], w), b[7]), ca);
     o[7] = add(imax(add(b[7], w), b[3]), cb);
 }
@@ -164,7 +173,8 @@ static inline int maxstar_generic(int x, int y)
     const int mx = imax(x, y), mn = imin(x, y);
     const int e1 = chk(mn - mx - 1); /* -|d| - 1 */
     int c;
-    if (g_upper == 2) c = 0;
+    if (g_exact) c = corr_exact(mx - mn);
+    else if (g_upper == 2) c = 0;
     else if (g_upper == 1) c = imin(g_TC, relu(e1 + 1 + g_TT));
     else c = relu(asr2(e1) + g_uoff + g_T4);
     return add(mx, c);
@@ -178,8 +188,9 @@ static inline void lam_pair(int ai, int aj, int bm, int bn, int *same, int *cros
     /* same: max*(aj + bn, ai + bm), d = (aj - ai) + (bn - bm);  cross: max*(aj + bm, ai + bn), d = (aj - ai) - (bn - bm) */
     const int hA = asr2(chk(aj - ai - 1)), nhA = -hA - 1;
     const int hB = asr2(chk(bn - bm - 1)), nhB = -hB - 1;
-    const int c1 = relu(imin(hA + hB + 1 + g_T4L, nhA + nhB + 1 + g_T4L));
-    const int c2 = relu(imin(hA + nhB + 1 + g_T4L, nhA + hB + 1 + g_T4L));
+    int c1 = relu(imin(hA + hB + 1 + g_T4L, nhA + nhB + 1 + g_T4L));
+    int c2 = relu(imin(hA + nhB + 1 + g_T4L, nhA + hB + 1 + g_T4L));
+    if (g_exact) { c1 = corr_exact((aj + bn) - (ai + bm)); c2 = corr_exact((aj + bm) - (ai + bn)); }
     *same = add(imax(add(aj, bn), add(ai, bm)), c1);
     *cross = add(imax(add(aj, bm), add(ai, bn)), c2);
 }
@@ -217,6 +228,7 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
     g_upper = p->lm_upper;
     g_TT = p->lm_tt; g_TC = p->lm_tc;
     g_uoff = p->lm_upper_off;
+    g_exact = p->lm_exact; g_F = F;
     g_T4L = p->lm_t4_lam > 0 ? p->lm_t4_lam : g_T4;
 #define ASTEP(lmf, a_, u_, v_, o_) ((lmf) ? alpha_step_lm(a_, u_, v_, o_) : alpha_step(a_, u_, v_, o_))
 #define BSTEP(lmf, b_, u_, v_, o_) ((lmf) ? beta_step_lm(b_, u_, v_, o_) : beta_step(b_, u_, v_, o_))

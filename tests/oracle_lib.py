@@ -44,7 +44,7 @@ class FxParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "K", "n_iter", "sub_len", "warmup", "frac_bits", "llr_clip", "ext_clip",
         "ext_scale_q2", "early_term", "et_threshold", "crc_poly",
-        "logmap", "lm_t4", "lm_upper", "lm_tt", "lm_tc", "lm_warm_maxlog", "lm_upper_off", "lm_t4_lam")]
+        "logmap", "lm_t4", "lm_upper", "lm_tt", "lm_tc", "lm_warm_maxlog", "lm_upper_off", "lm_t4_lam", "lm_exact")]
 
 
 class F32Params(C.Structure):

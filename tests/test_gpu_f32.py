@@ -119,3 +119,29 @@ def test_early_termination_f32(oracle, algo, logmap):
         assert out["iters_used"].tolist() == its
     assert out["iters_used"].min() >= 2 and out["iters_used"].max() < n_iter
     assert np.array_equal(out["bits"], bits.astype(np.uint8))
+
+
+@pytest.mark.parametrize("algo,lm", [("maxlog_f32", 0), ("linlogmap_f32", 2), ("logmap_f32", 1)])
+def test_extreme_llrs_stay_finite(oracle, algo, lm):
+    """Channel values far beyond the binary16 range (the shared-memory format of these modes) are clamped to +-65504
+    on the way in: no infinity reaches the recursions, the outputs stay finite and equal the model's, and a strongly
+    received codeword decodes to itself."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_iter = 1024, 4
+    pi = oracle.qpp(K)
+    bits, llr = oracle.make_batch(K, 3, 3.0, seed=23)
+    llr32 = llr.astype(np.float32)
+    llr32[0] *= 1e6                       # |LLR| up to ~1e7: +-inf as binary16 without the clamp
+    llr32[1, ::5] = np.float32(3.0e38)
+    llr32[1, 1::5] = np.float32(-3.0e38)
+    dec = TurboDecoder(K, n_iter=n_iter, algo=algo)
+    plan = dec.plan()
+    out = dec.decode(llr32, want=("bits", "llr_siso2"))
+    assert np.isfinite(out["llr_siso2"]).all()
+    assert np.array_equal(out["bits"][0], bits[0].astype(np.uint8))
+    for c in range(3):
+        b, l, _, _ = oracle.f32_decode(llr32[c], pi, _params(K, n_iter, plan["sub_block"], plan["warmup"], lm), want_soft=True)
+        if lm != 1:     # the exact Log-MAP mode uses the hardware ex2/lg2: tolerance-based (test_logmap_f32_matches_model)
+            assert np.array_equal(out["bits"][c], b.astype(np.uint8))
+            assert np.array_equal(out["llr_siso2"][c][:K], l)

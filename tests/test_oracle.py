@@ -182,7 +182,8 @@ def test_modem_vs_live_reference(oracle, M):
 
 # ---- TS 36.212 rate matching: oracle/turbo_oracle_rm.c.  The reference only declares
 #      rate_match()/de_rate_match() (ITTC/main.h:23-24), so these are structural checks of the literal
-#      restatement of the specification -- parity with 3GPP test vectors is UNPINNED (none offline).
+#      restatement of the specification.  Pinned by a hand-derived known answer for K = 40 (below); no 3GPP
+#      conformance vector and no independent implementation exists offline.
 def test_rate_matching_structure(oracle):
     assert oracle.rm_geometry(40) == {"R": 2, "Kpi": 64, "ND": 20, "Kw": 192}
     assert oracle.rm_geometry(6144) == {"R": 193, "Kpi": 6176, "ND": 28, "Kw": 18528}
@@ -200,6 +201,57 @@ def test_rate_matching_structure(oracle):
         # then d1 and d2 interlaced: parity 1 of step i next to parity 2 of a neighbouring step
         p = w[g["Kpi"]:]
         assert all(v < 0 or v >= 3 * K or v % 3 == 1 for v in p[0::2]) and all(v < 0 or v >= 3 * K or v % 3 == 2 for v in p[1::2])
+
+
+def test_rate_matching_known_answer_k40_derived_from_ts36212(oracle):
+    """A known answer worked out BY HAND from the text of TS 36.212 (v8.8.0) for the smallest block, K = 40 -- not
+    produced by any code in this repository.  It pins the sub-block interleaver, the parity interlacing, the tail-bit
+    multiplexing and the redundancy-version start points of oracle/turbo_oracle_rm.c (and through the bit-exact GPU
+    tests, of build_rm_table in csrc/tdb200_ratematch.cu).
+
+    Derivation.
+    5.1.3.2.2 (trellis termination): each stream d(i) has D = K + 4 = 44 bits; d0[k] = x_k, d1[k] = z_k, d2[k] = z'_k for
+      k < K, then  d0[K..K+3] = x_K, z_{K+1}, x'_K, z'_{K+1};  d1[K..K+3] = z_K, x_{K+2}, z'_K, x'_{K+2};
+      d2[K..K+3] = x_{K+1}, z_{K+2}, x'_{K+1}, z'_{K+2}.
+      In the reference's multiplex order (ITTC/log_map.cpp:566-578) x_k, z_k, z'_k sit at 3k, 3k+1, 3k+2 and the tail
+      (x_K z_K x_{K+1} z_{K+1} x_{K+2} z_{K+2} | x'_K z'_K x'_{K+1} z'_{K+1} x'_{K+2} z'_{K+2}) at 3K .. 3K+11.
+    5.1.4.1.1 (sub-block interleaver): C = 32 columns, R = ceil(44/32) = 2 rows, K_pi = 64, N_D = 64 - 44 = 20 <NULL>s
+      in front: y[k] = <NULL> for k < 20, y[20+k] = d[k].  Written row by row (row 0 = y[0..31], row 1 = y[32..63]),
+      columns permuted by P = <0,16,8,24,4,20,12,28,2,18,10,26,6,22,14,30,1,17,9,25,5,21,13,29,3,19,11,27,7,23,15,31>,
+      read column by column:  v0 = y[0], y[32], y[16], y[48], y[8], y[40], y[24], y[56], y[4], y[36], y[20], y[52], ...
+      i.e. in terms of d0:      N,   d12,   N,     d28,   N,    d20,   d4,    d36,   N,    d16,   d0,    d32,  ...
+      d2 uses v2[k] = y[pi(k)], pi(k) = (P(floor(k/R)) + C*(k mod R) + 1) mod K_pi:
+      pi = 1, 33, 17, 49, 9, 41, 25, 57, ...  ->  v2 = N, d2[13], N, d2[29], N, d2[21], d2[5], d2[37], ...
+    5.1.4.1.2 (bit collection): w[k] = v0[k] (k < 64), w[64+2k] = v1[k], w[64+2k+1] = v2[k]; K_w = 192.
+      Bit selection starts at k0 = R * (2 * ceil(N_cb / (8R)) * rv + 2) = 2 * (24 rv + 2) = 4, 52, 100, 148 and skips <NULL>s.
+    """
+    K = 40
+    assert oracle.rm_geometry(K) == {"R": 2, "Kpi": 64, "ND": 20, "Kw": 192}
+    assert [oracle.rm_k0(K, rv) for rv in range(4)] == [4, 52, 100, 148]
+    N = -1
+    d0 = lambda k: 3 * k if k < K else {40: 3 * K + 0, 41: 3 * K + 3, 42: 3 * K + 6, 43: 3 * K + 9}[k]     # noqa: E731
+    d1 = lambda k: 3 * k + 1 if k < K else {40: 3 * K + 1, 41: 3 * K + 4, 42: 3 * K + 7, 43: 3 * K + 10}[k]  # noqa: E731
+    d2 = lambda k: 3 * k + 2 if k < K else {40: 3 * K + 2, 41: 3 * K + 5, 42: 3 * K + 8, 43: 3 * K + 11}[k]  # noqa: E731
+    w = oracle.rm_circular_buffer(K)
+    # systematic part, first 24 entries (columns 0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26)
+    assert list(w[:24]) == [N, d0(12), N, d0(28), N, d0(20), d0(4), d0(36), N, d0(16), d0(0), d0(32),
+                            N, d0(24), d0(8), d0(40), N, d0(14), N, d0(30), N, d0(22), d0(6), d0(38)]
+    # the last column read is 31: y[31] = d0[11], y[63] = d0[43] = z'_{K+1}
+    assert list(w[62:64]) == [d0(11), d0(43)]
+    # interlaced parity part: (v1[k], v2[k]) pairs for k = 0..7
+    assert list(w[64:80]) == [N, N, d1(12), d2(13), N, N, d1(28), d2(29), N, N, d1(20), d2(21), d1(4), d2(5), d1(36), d2(37)]
+    # the wrap of pi(): k = 63 -> P(31) + 32 + 1 = 64 = 0 (mod 64): the very last entry is y2[0], a <NULL>
+    assert w[191] == N and w[190] == d1(43)
+    # rv 0 starts at w[4]: the first 20 transmitted bits (hand-listed from the columns above, <NULL>s skipped)
+    sel = oracle.rm_selection(K, 20, 0)
+    assert list(sel) == [d0(20), d0(4), d0(36), d0(16), d0(0), d0(32), d0(24), d0(8), d0(40), d0(14), d0(30), d0(22),
+                         d0(6), d0(38), d0(18), d0(2), d0(34), d0(26), d0(10), d0(42)]
+    # rv 1 starts at w[52] = column P(26) = 11, row 0: y[11] is <NULL>, so the first bit sent is y[43] = d0[23],
+    # followed by column 27: y[27] = d0[7], y[59] = d0[39]
+    assert list(oracle.rm_selection(K, 3, 1)) == [d0(23), d0(7), d0(39)]
+    # rv 2 starts at w[100] = parity pair k = 18 (column P(9) = 18, row 0): v1 = y1[18] <NULL>, v2 = y2[pi(18)] with
+    # pi(18) = 18 + 0 + 1 = 19 <NULL>; pair k = 19 (row 1): v1 = y1[50] = d1[30], v2 = y2[18 + 32 + 1 = 51] = d2[31]
+    assert list(oracle.rm_selection(K, 2, 2)) == [d1(30), d2(31)]
 
 
 def test_rate_matching_round_trips(oracle):

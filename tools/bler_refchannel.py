@@ -75,15 +75,15 @@ def main():
                 p2, n2 = fe[it] / args.frames, args.frames
                 pp = (p1 * n1 + p2 * n2) / (n1 + n2)
                 sd = math.sqrt(max(pp * (1 - pp), 1e-12) * (1.0 / n1 + 1.0 / n2))
-                row["bler"].append(float(p2)); row["reference"].append(p1); row["z"].append((p2 - p1) / sd)
+                row["bler"].append(float(p2)); row["reference"].append(float(p1)); row["z"].append(float((p2 - p1) / sd))
             res["points"].append(row)
             print("%.1f dB  ours %s\n        ref  %s\n        z    %s" % (eb, ["%.4f" % v for v in row["bler"]],
                   ["%.4f" % v for v in row["reference"]], ["%+.1f" % v for v in row["z"]]), flush=True)
     zs = [abs(z) for r in res["points"] for z in r["z"]]
     res["cells"] = len(zs)
-    res["cells_outside_95pct"] = sum(z > 1.96 for z in zs)
-    res["cells_outside_3sigma"] = sum(z > 3 for z in zs)
-    res["max_abs_z"] = max(zs) if zs else 0.0
+    res["cells_outside_95pct"] = int(sum(z > 1.96 for z in zs))
+    res["cells_outside_3sigma"] = int(sum(z > 3 for z in zs))
+    res["max_abs_z"] = float(max(zs)) if zs else 0.0
     print("cells %d, |z| > 1.96: %d, |z| > 3: %d, max |z| %.2f" % (len(zs), res["cells_outside_95pct"], res["cells_outside_3sigma"], res["max_abs_z"]))
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)

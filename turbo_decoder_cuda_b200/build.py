@@ -46,6 +46,7 @@ KERNEL_TUS = [
     ("tdb200_modem.cu", ["-fmad=false"]),
     ("tdb200_ratematch.cu", ["-fmad=false"]),
     ("tdb200_crc.cu", []),
+    ("tdb200_ubench.cu", []),
 ]
 
 
@@ -99,7 +100,10 @@ def build(force=False, verbose=False):
                     raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
     so = os.path.join(LIB, "libtdb200.so")
     if force or _stale(so, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", so] + objs + ["-cudart", "static"]
+        # the shared CUDA runtime (found through the rpath, or already mapped by the host process): the shipped
+        # artefacts then carry only the runtime symbols they import, not a private copy of the whole runtime
+        cudart_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc))), "lib64")
+        cmd = [nvcc] + ARCH + ["-shared", "-o", so] + objs + ["-cudart", "shared", "-Xlinker", "-rpath", "-Xlinker", cudart_dir]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
@@ -115,8 +119,9 @@ def build(force=False, verbose=False):
     burst_exe = os.path.join(LIB, "tdb200_burst")
     if os.path.exists(burst_src) and (force or _stale(burst_exe, [burst_src, so] + hdrs)):
         # a plain C++ caller of the C ABI (one host thread per GPU); nvcc only to find the CUDA runtime
-        cmd = [nvcc, "-O2", "-std=c++17", "-I", INCLUDE, burst_src, "-o", burst_exe, "-L", LIB, "-ltdb200",
-               "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-Xcompiler", "-pthread"]
+        cmd = [nvcc, "-O2", "-std=c++17", "-I", INCLUDE, burst_src, "-o", burst_exe, "-L", LIB, "-ltdb200", "-cudart", "shared",
+               "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-Xlinker", "-rpath", "-Xlinker",
+               os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc))), "lib64"), "-Xcompiler", "-pthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("tdb200_burst build failed:\n%s\n%s" % (r.stdout, r.stderr))

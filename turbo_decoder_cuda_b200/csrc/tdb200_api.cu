@@ -36,6 +36,28 @@ static int fail(int status, const char *fmt, ...)
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Every entry point works on the decoder's device and leaves the caller's current device as it found it (a thread that
+// holds handles for several GPUs, or shares the process with torch, must not have its device switched under it).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err != cudaSuccess) prev = -1;
+        if (prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define TDB_DEVICE(dev)          \
+    DeviceGuard device_guard_(dev); \
+    TDB_CUDA(device_guard_.err)
+
 // ---------------------------------------------------------------------------- constants
 // RSC with feedback 13_8 = 1011 and feed-forward 15_8 = 1101 (ITTC/log_map.h:34-36); state =
 // 4*s0 + 2*s1 + s2 with s0 the newest register, as bin2int does (log_map.cpp:213-231).
@@ -208,7 +230,7 @@ int tdb200_default_config(tdb200_config *cfg, int K)
 void tdb200_destroy(tdb200_decoder *d)
 {
     if (!d) return;
-    cudaSetDevice(d->cfg.device);
+    DeviceGuard device_guard_(d->cfg.device);
     cudaFree(d->d_pi); cudaFree(d->d_pi_inv); cudaFree(d->ws64_block); cudaFree(d->d_tab2);
     cudaFree(d->siso_in); cudaFree(d->siso_out); cudaFree(d->dem);
     for (auto &t : d->rm_tables) { cudaFree(t.d_perm); cudaFree(t.d_inv); }
@@ -263,7 +285,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
             g = (g + g2) % K;
         }
     }
-    TDB_CUDA(cudaSetDevice(c.device));
+    TDB_DEVICE(c.device);
     cudaDeviceProp prop;
     TDB_CUDA(cudaGetDeviceProperties(&prop, c.device));
     d->sm_count = prop.multiProcessorCount;
@@ -562,7 +584,7 @@ static int rm_table(tdb200_decoder *d, int rv, int ncb, const tdb200_decoder::Rm
     if (!build_rm_table(d->cfg.K, rv, ncb, perm, inv)) return fail(TDB200_ERR_INVALID_ARG, "ncb=%d leaves no transmittable bit", ncb);
     tdb200_decoder::RmTable t;
     t.rv = rv; t.ncb = ncb; t.nnn = (int)perm.size();
-    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_DEVICE(d->cfg.device);
     TDB_CUDA(cudaMalloc(&t.d_perm, sizeof(int) * perm.size()));
     if (cudaMalloc(&t.d_inv, sizeof(int) * inv.size()) != cudaSuccess) { cudaFree(t.d_perm); return fail(TDB200_ERR_ALLOC, "device allocation failed"); }
     cudaError_t e = cudaMemcpy(t.d_perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice);
@@ -583,7 +605,7 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
     if (n_cb == 0) return TDB200_OK;
     const tdb200_config &c = d->cfg;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDB_CUDA(cudaSetDevice(c.device));
+    TDB_DEVICE(c.device);
     const int K = c.K, T = d->T, NL = d->NL;
     const bool sym = src.symbols(), rm = (src.rm != nullptr);
     if (mem == TDB200_MEM_DEVICE && !sym && !rm) {
@@ -788,7 +810,7 @@ int tdb200_modulate_flat(tdb200_decoder *d, const uint8_t *coded, void *sym_i, v
     if (nb % modulation) return fail(TDB200_ERR_INVALID_ARG, "%zu bits are not a whole number of %d-bit symbols", nb, modulation);
     if (nb == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_DEVICE(d->cfg.device);
     const size_t ns = nb / modulation, ssz = llr_elem_size(sym_type);
     if (mem == TDB200_MEM_DEVICE) {
         TDB_CUDA(launch_modulate(coded, sym_i, sym_q, sym_type, nb, modulation, st));
@@ -822,7 +844,7 @@ int tdb200_awgn_batch(tdb200_decoder *d, const void *x, void *y, int type, int m
     if (!(sigma >= 0.0)) return fail(TDB200_ERR_INVALID_ARG, "sigma must not be negative");
     if (n == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_DEVICE(d->cfg.device);
     if (mem == TDB200_MEM_DEVICE) {
         TDB_CUDA(launch_awgn(x, y, type, n, sigma, seed, st));
         return TDB200_OK;
@@ -850,7 +872,7 @@ int tdb200_demap_flat(tdb200_decoder *d, const void *sym_i, const void *sym_q, i
     if (n_llr % modulation) return fail(TDB200_ERR_INVALID_ARG, "%zu soft bits are not a whole number of %d-bit symbols", n_llr, modulation);
     if (n_llr == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_DEVICE(d->cfg.device);
     DemapArgs a{};
     a.sym_type = sym_type; a.llr_type = llr_type; a.n_llr = n_llr; a.modulation = modulation; a.kf = kf;
     a.frac_bits = d->cfg.frac_bits ? d->cfg.frac_bits : 3;
@@ -890,7 +912,7 @@ int tdb200_rate_match_batch(tdb200_decoder *d, const uint8_t *coded, uint8_t *e_
     if (s) return s;
     if (n_cb == 0 || E == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_DEVICE(d->cfg.device);
     if (mem == TDB200_MEM_DEVICE) {
         TDB_CUDA(launch_rate_match(coded, e_bits, t->d_perm, t->nnn, d->NL, E, n_cb, st));
         return TDB200_OK;
@@ -916,7 +938,7 @@ int tdb200_rate_dematch_batch(tdb200_decoder *d, const void *e_llr, void *llr, i
     if (s) return s;
     if (n_cb == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_DEVICE(d->cfg.device);
     RmArgs a{};
     a.in_type = a.out_type = llr_type; a.inv = t->d_inv; a.nnn = t->nnn; a.NL = d->NL; a.E = E; a.n_cb = n_cb; a.accumulate = accumulate ? 1 : 0;
     a.frac_bits = d->cfg.frac_bits ? d->cfg.frac_bits : 3; a.clip = 127;
@@ -947,7 +969,7 @@ static int crc_common(tdb200_decoder *d, uint8_t *bits, int row_bits, int which,
     if (K <= 24 || K > (1 << 24)) return fail(TDB200_ERR_INVALID_ARG, "row_bits=%d: need 24 < row_bits <= 2^24", K);
     if (n_cb == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_DEVICE(d->cfg.device);
     CrcArgs a{};
     a.K = K; a.n_cb = n_cb; a.poly = (which == TDB200_CRC24A) ? 0x864CFBu : 0x800063u; a.attach = attach;
     if (mem == TDB200_MEM_DEVICE) {
@@ -1014,7 +1036,7 @@ int tdb200_encode_batch(tdb200_decoder *d, const uint8_t *bits, uint8_t *coded, 
     if (n_cb < 0 || (mem != TDB200_MEM_HOST && mem != TDB200_MEM_DEVICE)) return fail(TDB200_ERR_INVALID_ARG, "n_cb=%d mem=%d", n_cb, mem);
     if (n_cb == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_DEVICE(d->cfg.device);
     const int K = d->cfg.K, NL = d->NL;
     EncodeArgs a{};
     a.pi = d->d_pi; a.K = K; a.n_cb = n_cb;
@@ -1046,7 +1068,7 @@ int tdb200_channel_batch(tdb200_decoder *d, const uint8_t *coded, void *llr, int
     if (!(sigma > 0.0)) return fail(TDB200_ERR_INVALID_ARG, "sigma must be positive");
     if (n_cb == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_DEVICE(d->cfg.device);
     const size_t n = (size_t)n_cb * d->NL, esz = llr_elem_size(llr_type);
     ChannelArgs a{};
     a.n = n; a.sigma = (float)sigma; a.seed = seed;
@@ -1078,7 +1100,7 @@ int tdb200_siso_batch(tdb200_decoder *d, const double *recs, const double *La, i
     d->launches_last = 0;
     if (n_cb == 0) return TDB200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDB_CUDA(cudaSetDevice(d->cfg.device));
+    TDB_DEVICE(d->cfg.device);
     const int T = d->T, chunk = d->cfg.max_batch;
     const bool host = (mem == TDB200_MEM_HOST);
     if (host) {

@@ -116,7 +116,9 @@ __device__ __forceinline__ float load_llr(const void *base, size_t idx)
     else if (LLR_T == TDB200_LLR_F64) x = (float)__ldg(static_cast<const double *>(base) + idx);
     else if (LLR_T == TDB200_LLR_F16) x = __half2float(__ldg(static_cast<const __half *>(base) + idx));
     else x = (float)__ldg(static_cast<const int8_t *>(base) + idx) * 0.125f;  // S8: 3 fractional bits
-    return (x == x) ? x : 0.f;  // NaN -> erasure
+    // NaN -> erasure; the channel values live in shared memory as binary16, so clamp to its finite range first
+    // (an LLR beyond +-65504 would become +-inf and inf - inf in the recursions NaN)
+    return (x == x) ? fminf(fmaxf(x, -65504.0f), 65504.0f) : 0.f;
 }
 
 // One SISO pass of one sub-block; see siso_pass in tdb200_fast_kernel.cuh for the schedule.

@@ -515,7 +515,7 @@ __device__ __forceinline__ w32 bwd_window(const bool IL, const bool WANT, const 
 template <int ILT, int WANTT, int KP, int KNW, int KG, bool LM>
 __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, const Smem &sm, const w32 *par, w32 (&na)[8], w32 (&nb)[8],
                                          const int t, const bool active, const bool first_fixed, const bool last_fixed, w32 *stage,
-                                         w32 &weak, const bool il_rt = false, const bool want_rt = false)
+                                         w32 &weak, const w32 live = 0xffffffffu, const bool il_rt = false, const bool want_rt = false)
 {
     // ILT / WANTT: 0 / 1 compile-time, -1 run-time (the Log-MAP kernels keep ONE copy of the pass: its body is three
     // times the max-log one, and four inlined copies would be a quarter of a megabyte of code)
@@ -642,8 +642,11 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
                 if (w & 1) hold = acc;
                 else {
                     const w32 word = (acc >> 8) | hold;
-                    changed |= word ^ sm.dec[(w >> 1) * P + t];
-                    sm.dec[(w >> 1) * P + t] = word;
+                    const w32 old = sm.dec[(w >> 1) * P + t];
+                    changed |= word ^ old;
+                    // a codeblock that has met its stopping rule keeps the decisions it stopped with (live: 0xffff per
+                    // lane still running), whatever its lane mate and the other pairs of the CTA go on to do
+                    sm.dec[(w >> 1) * P + t] = (word & live) | (old & ~live);
                     hold = 0;
                 }
             }
@@ -940,7 +943,8 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
             const bool want = il && (A.early_term == 1 || last || A.bits_iters != nullptr);
             w32 weak = 0;
             const w32 chg = siso_pass<-1, -1, KP, KNW, KG, true>(c, g, sm, il ? sm.par2 : sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed,
-                                                                 (want_soft && last && il) ? sm.par1 : nullptr, weak, il, want);
+                                                                 (want_soft && last && il) ? sm.par1 : nullptr, weak,
+                                                                 (usedA ? 0u : 0xffffu) | (usedB ? 0u : 0xffff0000u), il, want);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const w32 ta = na[0][j], tb2 = nb[0][j];
@@ -991,7 +995,8 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
             // with soft outputs requested, the last SISO-2 pass parks the a-posteriori values in the
             // (by then dead) parity-1 array
             const w32 chg = siso_pass<1, 1, KP, KNW, KG, LM>(c, g, sm, sm.par2, na[1], nb[1], t, active, first_fixed, last_fixed,
-                                                               (want_soft && last) ? sm.par1 : nullptr, weak);
+                                                               (want_soft && last) ? sm.par1 : nullptr, weak,
+                                                               CRC ? 0xffffffffu : ((usedA ? 0u : 0xffffu) | (usedB ? 0u : 0xffff0000u)));
             if (A.bits_iters && active) emit_iter_bits(A, sm, NW, P, PP, L, K, t, false, cbA, hasB, it, it + 1);
             if (A.early_term == 1) {
                 // stop: no decision of this iteration differs from the previous one and no

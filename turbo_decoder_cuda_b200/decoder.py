@@ -77,6 +77,7 @@ def load_library():
     L.tdb200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     L.tdb200_destroy.argtypes = [C.c_void_p]
     L.tdb200_destroy.restype = None
+    L.tdb200_ubench_issue_rate.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.tdb200_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.POINTER(Outputs), C.c_void_p]
     L.tdb200_siso_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
@@ -181,6 +182,12 @@ class TurboDecoder:
             self.close()
         except Exception:
             pass
+
+    def issue_rate(self, mix=2):
+        """Measured issue rate of the add-compare-select instruction mix on this decoder's GPU (thread-ops/clk/SM)."""
+        v = C.c_double(0.0)
+        _check(self._L.tdb200_ubench_issue_rate(self.device, int(mix), C.byref(v)))
+        return v.value
 
     def plan(self):
         info = PlanInfo()
