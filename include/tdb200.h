@@ -66,7 +66,7 @@ typedef enum tdb200_algo {
      * a-posteriori computations is max*(x,y) = max + c(|x-y|) with the linear correction
      * c = max(0, 0.625 - |x-y|/4), the reference's E_algorithm() table (log_map.cpp:779-801, :14-18) fitted by a
      * line, evaluated on quarter-differences shared by the two max* of a trellis butterfly.  Extrinsic scale 1.0
-     * as in the reference, 4 fractional bits, guard 32 by default.  The throughput mode that sits on the
+     * as in the reference, 4 fractional bits, guard 24 by default.  The throughput mode that sits on the
      * reference's BER/FER curve; bit-exact against its integer model (oracle/turbo_oracle_fx.c, logmap = 1). */
     TDB200_ALGO_LOGMAP_S16 = 5
 } tdb200_algo;

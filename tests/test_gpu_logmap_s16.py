@@ -43,7 +43,8 @@ def _check(oracle, dec, llr_in, llr_f32, pi, prm, n_cb, K, iters=None):
 
 
 @pytest.mark.parametrize("K,L,G,n_cb,n_iter,ebn0", [
-    (6144, 0, 0, 5, 8, 0.4),     # auto plan (L=48, G=32): compile-time geometry, odd batch, waterfall
+    (6144, 0, 0, 5, 8, 0.4),     # auto plan (L=48, G=24): compile-time geometry, odd batch, waterfall
+    (6144, 48, 32, 2, 4, 0.4),   # the longer guard
     (6144, 48, 16, 2, 4, 0.4),   # the faster guard
     (6144, 96, 32, 2, 3, 0.4),   # run-time geometry
     (5120, 40, 32, 3, 3, 0.8),
@@ -64,7 +65,7 @@ def test_bit_exact_vs_fixed_point_model(oracle, K, L, G, n_cb, n_iter, ebn0):
     dec = TurboDecoder(K, n_iter=n_iter, algo="logmap_s16", sub_block=L, warmup=G)
     plan = dec.plan()
     if L == 0 and K == 6144:
-        assert (plan["sub_block"], plan["warmup"]) == (48, 32)
+        assert (plan["sub_block"], plan["warmup"]) == (48, 24)
     prm = lm_params(K, n_iter, plan["sub_block"], plan["warmup"])
     _check(oracle, dec, torch.from_numpy(llr32).cuda(), llr32, pi, prm, n_cb, K)   # device path
     _check(oracle, dec, llr32, llr32, pi, prm, n_cb, K)                             # host path

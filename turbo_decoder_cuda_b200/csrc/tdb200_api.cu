@@ -356,7 +356,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
             return fail(TDB200_ERR_INVALID_ARG, "sub_block=%d must be a multiple of 8 dividing K=%d with K/sub_block <= 256", L, K);
         int G = c.warmup;
         if (G < 0 || G % 8) return fail(TDB200_ERR_INVALID_ARG, "warmup=%d must be a non-negative multiple of 8", G);
-        if (c.warmup == 0 && c.sub_block == 0) G = lm16 ? 32 : 16;  // auto plan: guard of 16 (BER vs (L,G)); Log-MAP: 32, which is what keeps it on the unsegmented curve
+        if (c.warmup == 0 && c.sub_block == 0) G = lm16 ? 24 : 16;  // auto plan: guard of 16 (BER vs (L,G)); Log-MAP: 24, from where on the block-error rate no longer moves
         if (G > L) G = L;
         g.K = K; g.L = L; g.P = K / L; g.NW = L / 8; g.G = (g.P == 1) ? 0 : G;
         g.PP = g.P | 1;  // odd row pitch: de-multiplex stores spread over the banks, walks stay conflict-free

@@ -136,6 +136,9 @@ struct GK {
 #ifndef TDB_LM_NOT_FMA
 #define TDB_LM_NOT_FMA 1
 #endif
+#ifndef TDB_LM_ALPHA_NOT_ALU
+#define TDB_LM_ALPHA_NOT_ALU 1  // the alpha butterflies' NOTs as LOP3: evens out the two pipes (ncu: fma-heavy 74 %, ALU 65 % busy without)
+#endif
 // ~x: as an IMAD with opaque constants (fma-heavy pipe) or as a LOP3 (ALU pipe) -- whichever pipe has slack
 __device__ __forceinline__ w32 vnot(w32 x, const PassCfg &c) { return TDB_LM_NOT_FMA ? x * c.neg1 + c.neg1 : ~x; }
 __device__ __forceinline__ w32 and_xor(w32 a, w32 b, w32 x)  // (a & b) ^ x in one LOP3 (the compiler shares the AND and spends three)
@@ -169,7 +172,7 @@ __device__ __forceinline__ void bfly_corr(w32 h, w32 nh, const GK &g, w32 &ca, w
 __device__ __forceinline__ void alpha_quarters(const w32 (&a)[8], const PassCfg &c, w32 (&h)[4], w32 (&nh)[4])
 {
 #pragma unroll
-    for (int i = 0; i < 4; i++) quarter(vadd(a[2 * i + 1], vnot(a[2 * i], c)), c, h[i], nh[i]);
+    for (int i = 0; i < 4; i++) quarter(vadd(a[2 * i + 1], TDB_LM_ALPHA_NOT_ALU ? ~a[2 * i] : vnot(a[2 * i], c)), c, h[i], nh[i]);
 }
 // ... of a beta vector: (b4,b0) (b1,b5) (b6,b2) (b3,b7)
 __device__ __forceinline__ void beta_quarters(const w32 (&b)[8], const PassCfg &c, w32 (&h)[4], w32 (&nh)[4])
@@ -476,6 +479,51 @@ __device__ __forceinline__ w32 bwd_window(const bool IL, const bool WANT, const 
     }
     norm8(b);
     w32 acc = 0;
+    if (LM) {
+        // The beta / a-posteriori body of a Log-MAP step is ~210 instructions: unrolled eight times the window would
+        // be 37 KB of code, more than the 32 KB instruction cache in front of the SM.  It runs as a ROLLED loop over
+        // the two halves of the window instead; the working registers of the second half are moved into place.
+        w32 wa[4][8], wh[4][4], wu[4], wv[4];
+        Elem we[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int s = 0; s < 8; s++) wa[k][s] = aw[4 + k][s];
+#pragma unroll
+            for (int s = 0; s < 4; s++) wh[k][s] = hA[4 + k][s];
+            wu[k] = u[4 + k]; wv[k] = v[4 + k]; we[k] = el[4 + k];
+        }
+#pragma unroll 1
+        for (int half = 1; half >= 0; half--) {
+#pragma unroll
+            for (int k = 3; k >= 0; k--) {
+                w32 hB[4], nhB[4];
+                beta_quarters(b, c, hB, nhB);
+                const w32 exm1 = extrinsic_m1_lm(wa[k], wh[k], b, hB, nhB, wv[k], c);
+                const w32 y = __viaddmin_s16x2_relu(exm1, c.lim1, c.limmax);
+                w32 es;
+                if (c.q2 == 3) es = __umulhi(y, c.k3q) & 0x3fff3fffu;
+                else es = y;
+                x_at(sm, we[k]) = vadd(vadd(sys_biased(c, sm, we[k]), es), c.unbias);
+                if (WANT) {
+                    const w32 lam = vadd(vadd(wu[k], exm1), 0x00010001u);
+                    acc = (acc >> 1) | (lam & 0x80008000u);
+                    weak |= __viaddmin_s16x2_relu(lam, c.etT, c.et2T) & c.etmask;
+                    if (stage) word_at(stage, we[k].xoff) = lam;
+                }
+                beta_step_lm(b, hB, nhB, wu[k], wv[k], c);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) wa[k][s] = aw[k][s];
+#pragma unroll
+                for (int s = 0; s < 4; s++) wh[k][s] = hA[k][s];
+                wu[k] = u[k]; wv[k] = v[k]; we[k] = el[k];
+            }
+        }
+        return acc;
+    }
 #pragma unroll
     for (int k = 7; k >= 0; k--) {
         w32 hB[4], nhB[4];
@@ -544,11 +592,23 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
             const int base_b = (G - 8 - g0) * PP + tb;
             norm8(a);
             norm8(b);
+            if (LM) {  // rolled by four steps: instruction-cache footprint (see bwd_window)
+#pragma unroll 1
+                for (int k0 = 0; k0 < 8; k0 += 4) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int ia = base_a + k * PP, ib = base_b + (7 - k) * PP;
-                alpha_step_x<LM>(a, x_at(sm, elem_at(IL, c, sm, ia)), par[ia], c);
-                beta_step_x<LM>(b, x_at(sm, elem_at(IL, c, sm, ib)), par[ib], c);
+                    for (int k = 0; k < 4; k++) {
+                        const int ia = base_a + (k0 + k) * PP, ib = base_b + (7 - k0 - k) * PP;
+                        alpha_step_x<LM>(a, x_at(sm, elem_at(IL, c, sm, ia)), par[ia], c);
+                        beta_step_x<LM>(b, x_at(sm, elem_at(IL, c, sm, ib)), par[ib], c);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int ia = base_a + k * PP, ib = base_b + (7 - k) * PP;
+                    alpha_step_x<LM>(a, x_at(sm, elem_at(IL, c, sm, ia)), par[ia], c);
+                    beta_step_x<LM>(b, x_at(sm, elem_at(IL, c, sm, ib)), par[ib], c);
+                }
             }
         }
 #pragma unroll
@@ -1133,15 +1193,17 @@ kernel_fn pick_kernel_t(const FastGeom &g)
     return fast_s16_kernel<LLR_T, 0, 0, 0, CRC>;
 }
 
-// TDB200_ALGO_LOGMAP_S16: compile-time geometry for 128 sub-blocks of 32 / 40 / 48 steps with guard 16 or 32
+// TDB200_ALGO_LOGMAP_S16: compile-time geometry for 128 sub-blocks of 32 / 40 / 48 steps with guard 16, 24 or 32
 // (K = 4096, 5120, 6144); every other plan runs the instantiation with run-time geometry
+template <int LLR_T, int G>
+kernel_fn pick_lm_nw(int NW)
+{
+    return NW == 6 ? fast_s16_kernel<LLR_T, 128, 6, G, false, true> : (NW == 5 ? fast_s16_kernel<LLR_T, 128, 5, G, false, true> : fast_s16_kernel<LLR_T, 128, 4, G, false, true>);
+}
 template <int LLR_T>
 kernel_fn pick_kernel_lm_t(const FastGeom &g)
 {
-    if (fast_spec_lm(g)) {
-        if (g.G == 32) return g.NW == 6 ? fast_s16_kernel<LLR_T, 128, 6, 32, false, true> : (g.NW == 5 ? fast_s16_kernel<LLR_T, 128, 5, 32, false, true> : fast_s16_kernel<LLR_T, 128, 4, 32, false, true>);
-        return g.NW == 6 ? fast_s16_kernel<LLR_T, 128, 6, 16, false, true> : (g.NW == 5 ? fast_s16_kernel<LLR_T, 128, 5, 16, false, true> : fast_s16_kernel<LLR_T, 128, 4, 16, false, true>);
-    }
+    if (fast_spec_lm(g)) return g.G == 32 ? pick_lm_nw<LLR_T, 32>(g.NW) : (g.G == 24 ? pick_lm_nw<LLR_T, 24>(g.NW) : pick_lm_nw<LLR_T, 16>(g.NW));
     return fast_s16_kernel<LLR_T, 0, 0, 0, false, true>;
 }
 

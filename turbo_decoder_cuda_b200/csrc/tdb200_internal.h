@@ -150,8 +150,8 @@ inline bool fast_spec_rt(const FastGeom &g) { return !fast_spec_pn(g) && g.P >= 
 // 129..192 sub-blocks of 32 or 40 steps: six warps per CTA at 168 registers, two CTAs per SM
 inline bool fast_spec_rt192(const FastGeom &g) { return !fast_spec192(g) && g.P > 128 && g.P <= 192 && (g.NW == 4 || g.NW == 5) && g.G == 16 && g.PP == (g.P | 1); }
 
-// Log-MAP kernels with compile-time geometry: 128 sub-blocks of 32 / 40 / 48 steps, guard 16 or 32
-inline bool fast_spec_lm(const FastGeom &g) { return g.P == 128 && g.NW >= 4 && g.NW <= 6 && (g.G == 16 || g.G == 32) && g.PP == 129; }
+// Log-MAP kernels with compile-time geometry: 128 sub-blocks of 32 / 40 / 48 steps, guard 16, 24 or 32
+inline bool fast_spec_lm(const FastGeom &g) { return g.P == 128 && g.NW >= 4 && g.NW <= 6 && (g.G == 16 || g.G == 24 || g.G == 32) && g.PP == 129; }
 
 cudaError_t fast_s16_configure(FastGeom &g, int sm_count, bool logmap);  // opt in to the dynamic shared memory size
 cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches);
