@@ -220,8 +220,13 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
 {
     const int K = p->K, L = p->sub_len, F = p->frac_bits;
     const int G = p->warmup;
-    if (L < 8 || L % 8 || K % L || G < 0 || G % 8 || G > L) return -1;
+    if (L < 8 || L % 8 || K % L || G < 0 || G % 8 || (G > L && G != 2 * L)) return -1;
     const int P = K / L;
+    /* A guard longer than the sub-block (G = 2L, used with the 8-step sub-blocks of block sizes K = 8 x prime) spans
+     * D = 2 sub-blocks: the warm-up of sub-block t starts from the START vector sub-block t-D had in the previous
+     * iteration (its end vector for beta); where it would start before the first / after the last trellis step it
+     * starts AT that step from the known vector instead. */
+    const int D = G > L ? G / L : 1;
     g_ovf = 0;
     const int lm = p->logmap, lmw = lm && !p->lm_warm_maxlog;
     g_T4 = p->lm_t4 > 0 ? p->lm_t4 : 5 << (F > 3 ? F - 3 : 0);
@@ -254,6 +259,8 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
         prev_bits[i] = -1;
     }
     /* boundary vectors: known start state; tail folded into beta at step K */
+    int fixedA[NS], tailB[2][NS];
+    for (int j = 0; j < NS; j++) fixedA[j] = j ? FX_NEG : 0;
     for (int s = 0; s < 2; s++) {
         int b[NS], o[NS];
         for (int j = 0; j < NS; j++) {
@@ -268,6 +275,7 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
         }
         normalise(b);
         memcpy(niiB[s * P + P - 1], b, sizeof(b));
+        memcpy(tailB[s], b, sizeof(b));
     }
 
     const int et_T = p->et_threshold < 1 ? 1 : p->et_threshold;
@@ -285,8 +293,13 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                  *      sub-block saved at its local step L-G in the previous iteration */
                 int *a = alpha;
                 memcpy(a, niiA[s * P + t], sizeof(int) * NS);
+                int ka = -G;
+                if (t > 0 && t * L + ka < 0) { /* (only with G > L) the warm-up would begin before step 0 */
+                    ka = -t * L;
+                    memcpy(a, fixedA, sizeof(fixedA));
+                }
                 if (t > 0)
-                    for (int k = -G; k < 0; k++) {
+                    for (int k = ka; k < 0; k++) {
                         int i = t * L + k, n = s ? pi[i] : i;
                         if ((k + G) % 8 == 0) normalise(a);
                         ASTEP(lmw, a, Xold[n], yp[i], o);
@@ -294,8 +307,13 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                     }
                 /* ---- beta warm-up over the first G steps of sub-block t+1 */
                 memcpy(b, niiB[s * P + t], sizeof(b));
+                int kb = G;
+                if (t < P - 1 && (t + 1) * L + kb > K) { /* (only with G > L) ... would begin after the last step */
+                    kb = K - (t + 1) * L;
+                    memcpy(b, tailB[s], sizeof(b));
+                }
                 if (t < P - 1)
-                    for (int k = G - 1; k >= 0; k--) {
+                    for (int k = kb - 1; k >= 0; k--) {
                         int i = (t + 1) * L + k, n = s ? pi[i] : i;
                         if (k % 8 == 7) normalise(b);
                         BSTEP(lmw, b, Xold[n], yp[i], o);
@@ -305,13 +323,13 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                 for (int k = 0; k < L; k++) {
                     int i = t * L + k, n = s ? pi[i] : i;
                     if (k % 8 == 0) normalise(a + k * NS);
-                    if (k == L - G) memcpy(newA[t], a + k * NS, sizeof(int) * NS);
+                    if (k == (G >= L ? 0 : L - G)) memcpy(newA[t], a + k * NS, sizeof(int) * NS);
                     ASTEP(lm, a + k * NS, X[n], yp[i], a + (k + 1) * NS);
                 }
                 if (G == 0) memcpy(newA[t], a + L * NS, sizeof(int) * NS);
                 normalise(newA[t]);
                 /* ---- backward: beta, extrinsic, a-posteriori, in-place update of X */
-                if (G == L) memcpy(newB[t], b, sizeof(b));
+                if (G >= L) memcpy(newB[t], b, sizeof(b));
                 for (int k = L - 1; k >= 0; k--) {
                     int i = t * L + k, n = s ? pi[i] : i;
                     if (k % 8 == 7) normalise(b);
@@ -334,9 +352,9 @@ int tdo_fx_decode(const float *llr_in, const int *pi, const tdo_fx_params *p,
                 normalise(newB[t]);
             }
             /* synchronous hand-over of the boundary metrics to the neighbours (used next iteration) */
-            for (int t = 0; t + 1 < P; t++) {
-                memcpy(niiA[s * P + t + 1], newA[t], sizeof(int) * NS);
-                memcpy(niiB[s * P + t], newB[t + 1], sizeof(int) * NS);
+            for (int t = 0; t + D < P; t++) {
+                memcpy(niiA[s * P + t + D], newA[t], sizeof(int) * NS);
+                memcpy(niiB[s * P + t], newB[t + D], sizeof(int) * NS);
             }
             /* CRC stopping rule: after SISO-1 of the second and later iterations */
             if (s == 0 && p->early_term == 2 && it >= 1 && tdo_crc24(nat_bits, K, (unsigned)p->crc_poly) == 0) {

@@ -141,3 +141,22 @@ def test_logmap_s16_paired_with_reference_decoder():
         half = 1.96 * math.sqrt(max(p * (1 - p), 1e-9) / N) + 1.0 / N
         assert abs(ku - kr) / N <= max(half, 0.15 * p), "iteration %d: ours %.4f reference %.4f" % (it + 1, ku / N, p)
     assert (err[:, -1] != ref_err[:, -1]).mean() <= 0.04
+
+
+@pytest.mark.parametrize("algo", ["maxlog_s16", "logmap_s16"])
+@pytest.mark.parametrize("K", [88, 104, 296, 328, 344, 1008, 6144])
+def test_auto_plan_is_on_the_unsegmented_curve(algo, K):
+    """BASELINE configs[3], BER side: the library's own sub-block plan for a block size must not cost more than 0.05 dB
+    against the same decoder with windows so long that segmentation cannot matter (one sub-block up to K = 1024).  The
+    sample holds the five sizes where only 8-step sub-blocks divide K (K = 8 x prime: guard 8 lost 0.06-0.09 dB there,
+    which is why their guard now spans two sub-blocks); the whole table, all 188 sizes, is
+    profiles/r02_plan_ber_parity_*.json (tools/plan_ber_parity.py)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import plan_ber_parity
+    row = plan_ber_parity.measure(K, algo, 16384)
+    assert not row["fail"] and row["worst_loss_db"] <= 0.05, row

@@ -125,6 +125,15 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("tdb200_burst build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    # measurement aid: the box's pinned host-to-device ceiling with N concurrent streams (tools/h2d_control.cpp)
+    ctl_src = os.path.join(ROOT, "tools", "h2d_control.cpp")
+    ctl_exe = os.path.join(LIB, "h2d_control")
+    if os.path.exists(ctl_src) and (force or _stale(ctl_exe, [ctl_src])):
+        cmd = [nvcc, "-O2", "-std=c++17", "-x", "cu", ctl_src, "-o", ctl_exe, "-cudart", "shared", "-Xlinker", "-rpath", "-Xlinker",
+               os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc))), "lib64"), "-Xcompiler", "-pthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("h2d_control build failed:\n%s\n%s" % (r.stdout, r.stderr))
     if verbose:
         sys.stderr.write("".join(log))
     if any(log):

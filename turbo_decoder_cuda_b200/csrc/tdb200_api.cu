@@ -357,7 +357,11 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         int G = c.warmup;
         if (G < 0 || G % 8) return fail(TDB200_ERR_INVALID_ARG, "warmup=%d must be a non-negative multiple of 8", G);
         if (c.warmup == 0 && c.sub_block == 0) G = lm16 ? 24 : 16;  // auto plan: guard of 16 (BER vs (L,G)); Log-MAP: 24, from where on the block-error rate no longer moves
-        if (G > L) G = L;
+        // A guard of two sub-blocks exists for 8-step sub-blocks only (the block sizes K = 8 x prime, where nothing but 8
+        // and K divides K): with guard 8 those plans lose 0.06-0.09 dB against the unsegmented recursion
+        // (profiles/r02_plan_ber_parity_*.json); the kernels with run-time geometry walk the guard across two neighbours.
+        if (c.warmup == 0 && c.sub_block == 0 && L == 8 && K / L > 2) G = 16;
+        if (G > L && !(L == 8 && G == 16 && K / L > 2)) G = L;
         g.K = K; g.L = L; g.P = K / L; g.NW = L / 8; g.G = (g.P == 1) ? 0 : G;
         g.PP = g.P | 1;  // odd row pitch: de-multiplex stores spread over the banks, walks stay conflict-free
         g.threads = ((g.P + 31) / 32) * 32;

@@ -65,7 +65,7 @@ bool fast_s16_specialised(const FastGeom &g, bool logmap)
 int fast_s16_pair_bytes(const FastGeom &g)
 {
     const int W = g.L * g.PP, Wp = (W + 7) & ~7;
-    int b = 3 * 4 * Wp + 2 * Wp + 4 * g.n_ckpt * 7 * g.P + 4 * ((g.NW + 1) / 2) * g.P;
+    int b = 3 * 4 * Wp + 2 * Wp + 4 * g.n_ckpt * 7 * g.P + 4 * ((g.NW + 1) / 2) * g.P + 4 * 16;  // ..., decisions, tail vectors
     b = (b + 3) & ~3;
     // Pairs that share a CTA sit side by side; thread (pair q, sub-block t) reads word q * stride + j * PP + t.
     // With stride = P (mod 32 words) that is bank tid + const: conflict-free across the pairs of a warp (a stride
@@ -77,7 +77,7 @@ int fast_s16_pair_bytes(const FastGeom &g)
 static int shared_bytes(const FastGeom &g, int threads, int np)
 {
     const int W = g.L * g.PP, Wp = (W + 7) & ~7;
-    return 2 * Wp + 4 * 16 * (threads / 32) + 4 * ((np + 3) & ~3);
+    return 2 * Wp + 4 * 32 * (threads / 32) + 4 * ((np + 3) & ~3);  // table, warp-edge words, stop flags
 }
 int fast_s16_smem_bytes(const FastGeom &g) { return ((g.pair_bytes * g.NP + 15) & ~15) + shared_bytes(g, g.threads, g.NP); }
 

@@ -387,6 +387,7 @@ struct Smem {
     uint8_t *sysA, *sysB;  // systematic value + 128 of codeblock A / B, one byte per trellis step
     uint16_t *tab;
     w32 *ckpt, *dec, *edge;
+    w32 *tail;  // [2][8]: the two SISOs' beta vectors at step K (tail bits folded in), for warm-ups that reach the trellis end
 };
 
 __device__ __forceinline__ w32 vnot_fma(w32 x, w32 neg1) { return x * neg1 + neg1; }  // ~x
@@ -565,13 +566,17 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
                                          const int t, const bool active, const bool first_fixed, const bool last_fixed, w32 *stage,
                                          w32 &weak, const w32 live = 0xffffffffu, const bool il_rt = false, const bool want_rt = false)
 {
+    // (which SISO this is -- the tail vector a long guard may need -- follows from the parity array: par2 <=> SISO-2)
     // ILT / WANTT: 0 / 1 compile-time, -1 run-time (the Log-MAP kernels keep ONE copy of the pass: its body is three
     // times the max-log one, and four inlined copies would be a quarter of a megabyte of code)
     const bool IL = ILT < 0 ? il_rt : (ILT != 0), WANT = WANTT < 0 ? want_rt : (WANTT != 0);
     const int P = KP > 0 ? KP : g.P, PP = KP > 0 ? (KP | 1) : g.PP, NW = KP ? KNW : g.NW, G = KP ? KG : g.G;  // KP < 0: run-time P
     const int L = 8 * NW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int w_sa = (L - G) >> 3, w_sb = G >> 3;
+    // A guard longer than the sub-block (G = 2L: the 8-step sub-blocks of K = 8 x prime, run-time geometry only) spans
+    // D = 2 sub-blocks: thread t warms up from the START vector thread t-D had in the previous iteration.
+    const int D = (KP == 0 && G > L) ? G / L : 1;
+    const int w_sa = (L > G ? L - G : 0) >> 3, w_sb = G >> 3;
     w32 a[8], b[8], a0[8], sa[8], sb[8];
     w32 changed = 0;
 #pragma unroll
@@ -588,8 +593,28 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
         const int ta = first_fixed ? t : t - 1, tb = last_fixed ? t : t + 1;
 #pragma unroll 1
         for (int g0 = 0; g0 < G; g0 += 8) {
-            const int base_a = (L - G + g0) * PP + ta;
-            const int base_b = (G - 8 - g0) * PP + tb;
+            int base_a = (L - G + g0) * PP + ta;
+            int base_b = (G - 8 - g0) * PP + tb;
+            if (KP == 0 && G > L) {
+                // the eight steps of this chunk by trellis position: sub-block ua (ub), local step la (lb).  A chunk
+                // that would lie outside the trellis runs on the thread's own data and is thrown away: where the walk
+                // reaches the first (last) trellis step it restarts from the known vector.
+                const int pa = t * L - G + g0, pb = (t + 1) * L + G - 8 - g0, K = P * L;
+                int ua = pa / L, la = pa - ua * L, ub = pb / L, lb = pb - ub * L;
+                if (pa < 0) { ua = t; la = 0; }
+                if (pb + 8 > K) { ub = t; lb = 0; }
+                base_a = la * PP + ua;
+                base_b = lb * PP + ub;
+                if (pa == 0) {
+#pragma unroll
+                    for (int s = 0; s < 8; s++) a[s] = s ? dup2(kFxNeg) : 0u;
+                }
+                if (pb + 8 == K) {
+                    const w32 *tv = sm.tail + (par == sm.par2 ? 8 : 0);
+#pragma unroll
+                    for (int s = 0; s < 8; s++) b[s] = tv[s];
+                }
+            }
             norm8(a);
             norm8(b);
             if (LM) {  // rolled by four steps: instruction-cache footprint (see bwd_window)
@@ -616,7 +641,7 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
             if (first_fixed) a[s] = na[s];
             if (last_fixed) b[s] = nb[s];
         }
-        if (G == L) {
+        if (G >= L) {
 #pragma unroll
             for (int s = 0; s < 8; s++) sb[s] = b[s];
         }
@@ -725,25 +750,26 @@ __device__ __forceinline__ w32 siso_pass(const PassCfg &c, const FastGeom &g, co
     w32 up[8], dn[8];
 #pragma unroll
     for (int s = 0; s < 8; s++) {
-        up[s] = __shfl_up_sync(0xffffffffu, sa[s], 1);
-        dn[s] = __shfl_down_sync(0xffffffffu, sb[s], 1);
+        up[s] = __shfl_up_sync(0xffffffffu, sa[s], D);
+        dn[s] = __shfl_down_sync(0xffffffffu, sb[s], D);
     }
-    if (lane == 31) {
+    // edge words: [state][distance slot 0..1][warp]
+    if (lane >= 32 - D) {
 #pragma unroll
-        for (int s = 0; s < 8; s++) sm.edge[s * nwarps + warp] = sa[s];
+        for (int s = 0; s < 8; s++) sm.edge[(s * 2 + (lane - (32 - D))) * nwarps + warp] = sa[s];
     }
-    if (lane == 0) {
+    if (lane < D) {
 #pragma unroll
-        for (int s = 0; s < 8; s++) sm.edge[(8 + s) * nwarps + warp] = sb[s];
+        for (int s = 0; s < 8; s++) sm.edge[((8 + s) * 2 + lane) * nwarps + warp] = sb[s];
     }
     __syncthreads();  // also orders this pass's X updates before the next pass's reads
-    if (lane == 0 && warp > 0) {
+    if (lane < D && warp > 0) {
 #pragma unroll
-        for (int s = 0; s < 8; s++) up[s] = sm.edge[s * nwarps + warp - 1];
+        for (int s = 0; s < 8; s++) up[s] = sm.edge[(s * 2 + lane) * nwarps + warp - 1];
     }
-    if (lane == 31 && warp + 1 < nwarps) {
+    if (lane >= 32 - D && warp + 1 < nwarps) {
 #pragma unroll
-        for (int s = 0; s < 8; s++) dn[s] = sm.edge[(8 + s) * nwarps + warp + 1];
+        for (int s = 0; s < 8; s++) dn[s] = sm.edge[((8 + s) * 2 + (lane + D - 32)) * nwarps + warp + 1];
     }
 #pragma unroll
     for (int s = 0; s < 8; s++) {
@@ -783,6 +809,7 @@ __device__ __forceinline__ Smem pair_smem(unsigned char *raw, const FastGeom &g,
     sm.sysB = sm.sysA + Wp;
     sm.ckpt = reinterpret_cast<w32 *>(sm.sysB + Wp);
     sm.dec = sm.ckpt + (size_t)g.n_ckpt * 7 * P;
+    sm.tail = sm.dec + (size_t)((NW + 1) / 2) * P;
     unsigned char *sh = raw + (((size_t)NP * g.pair_bytes + 15) & ~(size_t)15);  // pair regions are word-aligned only (bank-staggered)
     sm.tab = reinterpret_cast<uint16_t *>(sh);
     sm.edge = reinterpret_cast<w32 *>(sm.tab + Wp);
@@ -883,7 +910,7 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
     const bool active = KP > 0 ? true : (kSingle ? tid < P : (q < NP && pair < n_pairs));
     const bool one_pair = kSingle || NP == 1;  // CTA-uniform
     const Smem sm = pair_smem(smem_raw, g, P, NW, Wp, NP, active ? q : 0);
-    unsigned *flags = reinterpret_cast<unsigned *>(sm.edge + 16 * (nthr >> 5));
+    unsigned *flags = reinterpret_cast<unsigned *>(sm.edge + 32 * (nthr >> 5));
     const int cbA = 2 * (active ? pair : 0);
     const bool hasB = cbA + 1 < A.n_cb;
     const int cbB = hasB ? cbA + 1 : cbA;
@@ -983,7 +1010,7 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
             }
             norm8(bt);
 #pragma unroll
-            for (int j = 0; j < 8; j++) nb[s][j] = bt[j];
+            for (int j = 0; j < 8; j++) { nb[s][j] = bt[j]; sm.tail[8 * s + j] = bt[j]; }
         }
     }
     __syncthreads();
