@@ -226,3 +226,38 @@ def test_modem_error_paths():
     with pytest.raises(TdbError):
         dec.demap(s.astype(np.int8), s.astype(np.int8), 2, 1.0)   # symbols cannot be int8
     assert dec.decode_symbols(np.zeros((0, 66), np.float32), np.zeros((0, 66), np.float32), 2, 1.0)["bits"].shape == (0, 40)
+
+
+@pytest.mark.parametrize("algo", ["maxlog_s16", "logmap_s16"])
+@pytest.mark.parametrize("M", [1, 2])
+def test_fused_demapper_equals_two_call_form(oracle, algo, M, monkeypatch):
+    """BPSK / QPSK float symbols into the packed decoders are demapped inside the decoder's load stage
+    (ITTC/modanddem.cpp:189-260 fused in front of the branch metrics): decisions and extrinsics equal demapping to the
+    8-bit hand-over format and decoding that, from device and from host memory, for an odd batch, several chunks and a
+    short block with several pairs per CTA; the unfused path (TDB200_NO_FUSED_DEMAP) gives the same."""
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    for K, n_cb in ((6144, 5), (1008, 7), (40, 9)):
+        rate = K / (3.0 * K + 12.0)
+        ebn0 = 1.0 if K == 6144 else 2.5
+        sigma = 10 ** (-ebn0 / 20) * np.sqrt(0.5 / (rate * M))
+        bits, _, ri, rq, pi = _traffic(oracle, K, n_cb, M, sigma, seed=70 + M + K)
+        kf = 1.0 / (2.0 * sigma * sigma)
+        dec = TurboDecoder(K, n_iter=5, algo=algo, max_batch=4)
+        ti, tq = torch.from_numpy(ri).cuda(), torch.from_numpy(rq).cuda()
+        fused = dec.decode_symbols(ti, tq, M, kf, want=("bits", "ext_siso2"))
+        two = dec.decode(dec.demap(ti, tq, M, kf, dtype="int8"), want=("bits", "ext_siso2"))
+        assert torch.equal(fused["bits"], two["bits"]) and torch.equal(fused["ext_siso2"], two["ext_siso2"]), (K, "device")
+        host = dec.decode_symbols(ri, rq, M, kf, want=("bits", "ext_siso2"))
+        assert np.array_equal(host["bits"], two["bits"].cpu().numpy()) and np.array_equal(host["ext_siso2"], two["ext_siso2"].cpu().numpy())
+        monkeypatch.setenv("TDB200_NO_FUSED_DEMAP", "1")
+        unfused = dec.decode_symbols(ti, tq, M, kf, want=("bits",))
+        monkeypatch.delenv("TDB200_NO_FUSED_DEMAP")
+        assert torch.equal(unfused["bits"], two["bits"])
+        # a device view that breaks the 16-byte alignment falls back to the separate demapper, same result
+        if M == 1:
+            pad = torch.zeros(ti.numel() + 1, device="cuda")
+            pad[1:] = ti.ravel()
+            off = pad[1:].view_as(ti)
+            assert torch.equal(dec.decode_symbols(off, tq, M, kf, want=("bits",))["bits"], two["bits"])
+        dec.close()

@@ -41,6 +41,10 @@ KERNEL_TUS = [
     ("tdb200_fast_inst_lm_f64.cu", []),
     ("tdb200_fast_inst_lm_s8.cu", []),
     ("tdb200_fast_inst_lm_f16.cu", []),
+    ("tdb200_fast_inst_sym1.cu", []),
+    ("tdb200_fast_inst_sym2.cu", []),
+    ("tdb200_fast_inst_lm_sym1.cu", []),
+    ("tdb200_fast_inst_lm_sym2.cu", []),
     ("tdb200_f32.cu", ["-fmad=false", "-Xptxas", "-v"]),
     ("tdb200_encode.cu", []),
     ("tdb200_modem.cu", ["-fmad=false"]),

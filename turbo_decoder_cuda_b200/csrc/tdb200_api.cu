@@ -488,7 +488,7 @@ static int ensure_pipeline(tdb200_decoder *d)
 
 // One chunk of n codeblocks, all pointers device pointers, enqueued on st.
 static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int n, uint8_t *v_bits, int32_t *v_bits_iters,
-                        int32_t *v_iters, void *v_llr1, void *v_llr2, void *v_ext2, cudaStream_t st)
+                        int32_t *v_iters, void *v_llr1, void *v_llr2, void *v_ext2, cudaStream_t st, const void *v_sym_q = nullptr, double kf = 0.0)
 {
     const tdb200_config &c = d->cfg;
     if (c.algo == TDB200_ALGO_LOGMAP_F64) {
@@ -513,6 +513,7 @@ static int launch_chunk(tdb200_decoder *d, const void *v_llr, int llr_type, int 
     } else {
         FastArgs a{};
         a.llr = v_llr; a.llr_type = llr_type; a.n_cb = n; a.g = d->geom; a.n_iter = c.n_iter;
+        a.sym_q = v_sym_q; a.kf = (float)kf;
         a.frac_bits = c.frac_bits;
         a.llr_clip = std::min((1 << (c.frac_bits + 4)) - 1, 127);  // systematic values are kept as bytes in shared memory
         a.ext_lim = c.ext_clip + 1;
@@ -625,7 +626,15 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
     const size_t ssz = sym ? llr_elem_size(src.sym_type) : 0;
     const size_t NS = sym ? (size_t)NL / src.modulation : 0;  // symbols per codeblock
     const size_t rsz = rm ? llr_elem_size(src.llr_type) : 0, RE = rm ? (size_t)src.rm_E : 0;  // rate-matched row
-    const bool staged = sym || rm;
+    // BPSK / QPSK float symbols into a packed decoder: the demapper runs inside the decoder's load stage (no staging
+    // buffer, no demap kernel); every other combination demaps into the decoder's native format first
+    const bool fused_sym = sym && (c.algo == TDB200_ALGO_MAXLOG_S16 || c.algo == TDB200_ALGO_LOGMAP_S16) && c.early_term < 2 &&
+                           src.sym_type == TDB200_LLR_F32 && (src.modulation == 1 || src.modulation == 2) && !getenv("TDB200_NO_FUSED_DEMAP") &&
+                           (mem == TDB200_MEM_HOST ||  // staged planes are aligned; caller's device planes must allow the 128- / 64-bit loads
+                            ((reinterpret_cast<uintptr_t>(src.sym_i) & (src.modulation == 1 ? 15 : 7)) == 0 &&
+                             (src.modulation == 1 || (reinterpret_cast<uintptr_t>(src.sym_q) & 7) == 0)));
+    const int fused_type = src.modulation == 1 ? kLlrSymBpskF32 : kLlrSymQpskF32;
+    const bool staged = (sym && !fused_sym) || rm;
 
     const bool f64 = (c.algo == TDB200_ALGO_LOGMAP_F64);
     const size_t fsz = f64 ? sizeof(double) : sizeof(float);  // native float type of the LLR outputs
@@ -647,7 +656,7 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
         }
         for (int c0 = 0; c0 < n_cb; c0 += c.max_batch) {
             const int n = std::min(c.max_batch, n_cb - c0);
-            if (sym) {
+            if (sym && !fused_sym) {
                 int s = launch_demap_chunk(d, src, static_cast<const char *>(src.sym_i) + (size_t)c0 * NS * ssz,
                                            static_cast<const char *>(src.sym_q) + (size_t)c0 * NS * ssz, d->dem, n, st);
                 if (s) return s;
@@ -655,13 +664,16 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
                 int s = launch_dematch_chunk(d, src, static_cast<const char *>(llr) + (size_t)c0 * RE * rsz, d->dem, llr_type, n, st);
                 if (s) return s;
             }
-            int s = launch_chunk(d, staged ? d->dem : static_cast<const char *>(llr) + (size_t)c0 * NL * esz, llr_type, n,
+            const void *in = staged ? d->dem : (fused_sym ? static_cast<const char *>(src.sym_i) + (size_t)c0 * NS * ssz
+                                                          : static_cast<const char *>(llr) + (size_t)c0 * NL * esz);
+            int s = launch_chunk(d, in, fused_sym ? fused_type : llr_type, n,
                                  out->bits ? out->bits + (size_t)c0 * K : nullptr,
                                  out->bits_iters ? out->bits_iters + (size_t)c0 * c.n_iter * K : nullptr,
                                  out->iters_used ? out->iters_used + c0 : nullptr,
                                  out->llr_siso1 ? static_cast<char *>(out->llr_siso1) + fsz * (size_t)c0 * T : nullptr,
                                  out->llr_siso2 ? static_cast<char *>(out->llr_siso2) + fsz * (size_t)c0 * T : nullptr,
-                                 out->ext_siso2 ? static_cast<char *>(out->ext_siso2) + fsz * (size_t)c0 * T : nullptr, st);
+                                 out->ext_siso2 ? static_cast<char *>(out->ext_siso2) + fsz * (size_t)c0 * T : nullptr, st,
+                                 fused_sym ? static_cast<const char *>(src.sym_q) + (size_t)c0 * NS * ssz : nullptr, src.kf);
             if (s) return s;
         }
         if (f64 && out->iters_used) {  // the fp64 mode always runs every iteration
@@ -721,11 +733,12 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
         TDB_CUDA(cudaEventRecord(sl.in_ready, d->s_h2d));
         TDB_CUDA(cudaStreamWaitEvent(d->s_k, sl.in_ready, 0));
         if (reused) TDB_CUDA(cudaStreamWaitEvent(d->s_k, sl.out_done, 0));  // the copy-out of this slot's previous results
-        if (sym && (s = launch_demap_chunk(d, src, sl.d_in, d_q, sl.d_dem, n, d->s_k))) return s;
+        if (sym && !fused_sym && (s = launch_demap_chunk(d, src, sl.d_in, d_q, sl.d_dem, n, d->s_k))) return s;
         if (rm && (s = launch_dematch_chunk(d, src, sl.d_in, sl.d_dem, llr_type, n, d->s_k))) return s;
-        s = launch_chunk(d, staged ? sl.d_dem : sl.d_in, llr_type, n, out->bits ? sl.d_bits : nullptr, out->bits_iters ? sl.d_bits_iters : nullptr,
+        s = launch_chunk(d, staged ? sl.d_dem : sl.d_in, fused_sym ? fused_type : llr_type, n, out->bits ? sl.d_bits : nullptr,
+                         out->bits_iters ? sl.d_bits_iters : nullptr,
                          (out->iters_used && !f64) ? sl.d_iters_used : nullptr, out->llr_siso1 ? sl.d_llr1 : nullptr,
-                         out->llr_siso2 ? sl.d_llr2 : nullptr, out->ext_siso2 ? sl.d_ext2 : nullptr, d->s_k);
+                         out->llr_siso2 ? sl.d_llr2 : nullptr, out->ext_siso2 ? sl.d_ext2 : nullptr, d->s_k, fused_sym ? d_q : nullptr, src.kf);
         if (s) return s;
         TDB_CUDA(cudaEventRecord(sl.k_done, d->s_k));
         TDB_CUDA(cudaStreamWaitEvent(d->s_d2h, sl.k_done, 0));

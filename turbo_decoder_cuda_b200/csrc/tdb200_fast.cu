@@ -25,10 +25,18 @@ fast_kernel_fn fast_pick_lm_f32(const FastGeom &g);
 fast_kernel_fn fast_pick_lm_s8(const FastGeom &g);
 fast_kernel_fn fast_pick_lm_f16(const FastGeom &g);
 
+// received BPSK / QPSK float symbols, demapped in the load stage (tdb200_fast_inst_sym*.cu, tdb200_fast_inst_lm_sym*.cu)
+fast_kernel_fn fast_pick_sym1(const FastGeom &g);
+fast_kernel_fn fast_pick_sym2(const FastGeom &g);
+fast_kernel_fn fast_pick_lm_sym1(const FastGeom &g);
+fast_kernel_fn fast_pick_lm_sym2(const FastGeom &g);
+
 namespace {
 
 fast_kernel_fn pick_kernel(const FastGeom &g, int llr_type, bool crc = false, bool logmap = false)
 {
+    if (llr_type == kLlrSymBpskF32) return logmap ? fast_pick_lm_sym1(g) : fast_pick_sym1(g);
+    if (llr_type == kLlrSymQpskF32) return logmap ? fast_pick_lm_sym2(g) : fast_pick_sym2(g);
     if (logmap) {
         switch (llr_type) {
             case TDB200_LLR_F32: return fast_pick_lm_f32(g);
@@ -89,9 +97,9 @@ cudaError_t fast_s16_configure(FastGeom &g, int sm_count, bool logmap)
     cudaError_t e0 = cudaGetDevice(&dev);
     if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e0 != cudaSuccess) return e0;
-    for (int t = TDB200_LLR_F64; t <= TDB200_LLR_F16; t++) {
+    for (int t : {(int)TDB200_LLR_F64, (int)TDB200_LLR_F32, (int)TDB200_LLR_S8, (int)TDB200_LLR_F16, kLlrSymBpskF32, kLlrSymQpskF32}) {
         cudaError_t e = cudaFuncSetAttribute(pick_kernel(g, t, false, logmap), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-        if (e == cudaSuccess && !logmap) e = cudaFuncSetAttribute(pick_kernel(g, t, true), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        if (e == cudaSuccess && !logmap && t <= TDB200_LLR_F16) e = cudaFuncSetAttribute(pick_kernel(g, t, true), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
         if (e != cudaSuccess) return e;
     }
     int per_sm = 0;

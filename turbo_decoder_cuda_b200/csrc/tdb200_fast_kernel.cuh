@@ -298,16 +298,37 @@ __device__ __forceinline__ w32 quant2(float a, float b, float scale, w32 clipv, 
 // element 12*q, as loaded (128-bit loads for the float types)
 template <int LLR_T>
 struct Raw12 {
-    float4 f[LLR_T == TDB200_LLR_F32 ? 3 : 1];
+    float4 f[(LLR_T == TDB200_LLR_F32 || LLR_T == kLlrSymBpskF32) ? 3 : 1];
     double2 d[LLR_T == TDB200_LLR_F64 ? 6 : 1];
     int w[LLR_T == TDB200_LLR_S8 ? 3 : 1];
     uint2 h[LLR_T == TDB200_LLR_F16 ? 3 : 1];  // 4 halves each
+    float2 si[LLR_T == kLlrSymQpskF32 ? 3 : 1], sq[LLR_T == kLlrSymQpskF32 ? 3 : 1];  // six QPSK symbols: I and Q planes
 };
 
+// The soft demapper fused into the load stage (BPSK and QPSK, float symbols): the max-log metric of demodule()
+// (ITTC/modanddem.cpp:189-260) exactly as demap32_kernel evaluates it per axis (csrc/tdb200_modem.cu: axis32<1>) --
+// LLR = -Kf ((v - l1)^2 - (v - l0)^2) with the axis' two levels (l0, l1) = (-1, 1) for BPSK, (0.7071, -0.7071) for QPSK,
+// every operation rounded on its own (no contraction), so that decoding symbols equals demapping to the 8-bit
+// hand-over format and decoding that.
 template <int LLR_T>
-__device__ __forceinline__ void load12(const void *base, size_t row_elems, int cb, int q, Raw12<LLR_T> &r)
+__device__ __forceinline__ float demap1(float v, float kf)
 {
-    if (LLR_T == TDB200_LLR_F32) {
+    const float l0 = LLR_T == kLlrSymBpskF32 ? -1.0f : 0.7071f, l1 = LLR_T == kLlrSymBpskF32 ? 1.0f : -0.7071f;
+    const float t1 = __fsub_rn(v, l1), t0 = __fsub_rn(v, l0);
+    return __fmul_rn(-kf, __fsub_rn(__fmul_rn(t1, t1), __fmul_rn(t0, t0)));
+}
+
+template <int LLR_T>
+__device__ __forceinline__ void load12(const FastArgs &A, size_t row_elems, int cb, int q, Raw12<LLR_T> &r)
+{
+    const void *base = A.llr;
+    if (LLR_T == kLlrSymQpskF32) {
+        // 12 soft bits = 6 symbols; rows hold (3K+12)/2 symbols per plane (an even number: 8-byte aligned rows)
+        const float2 *pi = reinterpret_cast<const float2 *>(static_cast<const float *>(A.llr) + (size_t)cb * (row_elems / 2)) + 3 * q;
+        const float2 *pq = reinterpret_cast<const float2 *>(static_cast<const float *>(A.sym_q) + (size_t)cb * (row_elems / 2)) + 3 * q;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { r.si[k] = __ldg(pi + k); r.sq[k] = __ldg(pq + k); }
+    } else if (LLR_T == TDB200_LLR_F32 || LLR_T == kLlrSymBpskF32) {
         const float4 *p = reinterpret_cast<const float4 *>(static_cast<const float *>(base) + (size_t)cb * row_elems) + 3 * q;
 #pragma unroll
         for (int k = 0; k < 3; k++) r.f[k] = __ldg(p + k);
@@ -330,9 +351,25 @@ __device__ __forceinline__ float h_hi(unsigned w) { return __half2float(__ushort
 
 // quantise + pack the 12 values of codeblocks A and B into 12 s16x2 words
 template <int LLR_T>
-__device__ __forceinline__ void pack12(const Raw12<LLR_T> &a, const Raw12<LLR_T> &b, float scale, w32 clipv, w32 nclipv, w32 (&out)[12])
+__device__ __forceinline__ void pack12(const Raw12<LLR_T> &a, const Raw12<LLR_T> &b, float scale, w32 clipv, w32 nclipv, w32 (&out)[12], float kf)
 {
-    if (LLR_T == TDB200_LLR_F32) {
+    if (LLR_T == kLlrSymBpskF32) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            out[4 * k] = quant2(demap1<LLR_T>(a.f[k].x, kf), demap1<LLR_T>(b.f[k].x, kf), scale, clipv, nclipv);
+            out[4 * k + 1] = quant2(demap1<LLR_T>(a.f[k].y, kf), demap1<LLR_T>(b.f[k].y, kf), scale, clipv, nclipv);
+            out[4 * k + 2] = quant2(demap1<LLR_T>(a.f[k].z, kf), demap1<LLR_T>(b.f[k].z, kf), scale, clipv, nclipv);
+            out[4 * k + 3] = quant2(demap1<LLR_T>(a.f[k].w, kf), demap1<LLR_T>(b.f[k].w, kf), scale, clipv, nclipv);
+        }
+    } else if (LLR_T == kLlrSymQpskF32) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {   // soft bit 2m from I[m], 2m+1 from Q[m]
+            out[4 * k] = quant2(demap1<LLR_T>(a.si[k].x, kf), demap1<LLR_T>(b.si[k].x, kf), scale, clipv, nclipv);
+            out[4 * k + 1] = quant2(demap1<LLR_T>(a.sq[k].x, kf), demap1<LLR_T>(b.sq[k].x, kf), scale, clipv, nclipv);
+            out[4 * k + 2] = quant2(demap1<LLR_T>(a.si[k].y, kf), demap1<LLR_T>(b.si[k].y, kf), scale, clipv, nclipv);
+            out[4 * k + 3] = quant2(demap1<LLR_T>(a.sq[k].y, kf), demap1<LLR_T>(b.sq[k].y, kf), scale, clipv, nclipv);
+        }
+    } else if (LLR_T == TDB200_LLR_F32) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             out[4 * k] = quant2(a.f[k].x, b.f[k].x, scale, clipv, nclipv);
@@ -373,8 +410,15 @@ __device__ __forceinline__ void pack12(const Raw12<LLR_T> &a, const Raw12<LLR_T>
 }
 
 template <int LLR_T>
-__device__ __forceinline__ int load1(const void *base, size_t idx, float scale, int clip)
+__device__ __forceinline__ int load1(const FastArgs &A, int cb, size_t row_elems, size_t o, float scale, int clip)
 {
+    const void *base = A.llr;
+    const size_t idx = (size_t)cb * row_elems + o;
+    if (LLR_T == kLlrSymBpskF32) return quant(demap1<LLR_T>(__ldg(static_cast<const float *>(base) + idx), A.kf), scale, clip);
+    if (LLR_T == kLlrSymQpskF32) {
+        const float *pl = static_cast<const float *>((o & 1) ? A.sym_q : A.llr);
+        return quant(demap1<LLR_T>(__ldg(pl + (size_t)cb * (row_elems / 2) + (o >> 1)), A.kf), scale, clip);
+    }
     if (LLR_T == TDB200_LLR_F32) return quant(__ldg(static_cast<const float *>(base) + idx), scale, clip);
     if (LLR_T == TDB200_LLR_F64) return quant((float)__ldg(static_cast<const double *>(base) + idx), scale, clip);
     if (LLR_T == TDB200_LLR_F16) return quant(__half2float(__ldg(static_cast<const __half *>(base) + idx)), scale, clip);
@@ -925,7 +969,7 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
     //      (K/4 groups per pair < CTA size) still keep every thread loading.
     {
         const int np_here = kSingle ? 1 : min(NP, n_pairs - (int)blockIdx.x * NP);
-        constexpr int NG = (LLR_T == TDB200_LLR_F64) ? 2 : 4;
+        constexpr int NG = (LLR_T == TDB200_LLR_F64 || LLR_T == kLlrSymQpskF32) ? 2 : 4;
         const w32 clipv = dup2(clip), nclipv = dup2(-clip);
         const int nq = K / 4, total = np_here * nq;
         for (int i0 = tid; i0 < total; i0 += NG * nthr) {
@@ -935,8 +979,8 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                 const int ii = min(i0 + j * nthr, total - 1);  // the clamp re-reads the last group instead of branching
                 const int p = one_pair ? 0 : ii / nq, qq = ii - p * nq;
                 const int a_cb = 2 * ((int)blockIdx.x * NP + p), b_cb = (a_cb + 1 < A.n_cb) ? a_cb + 1 : a_cb;
-                load12<LLR_T>(A.llr, row, a_cb, qq, ra[j]);
-                load12<LLR_T>(A.llr, row, b_cb, qq, rb[j]);
+                load12<LLR_T>(A, row, a_cb, qq, ra[j]);
+                load12<LLR_T>(A, row, b_cb, qq, rb[j]);
             }
 #pragma unroll
             for (int j = 0; j < NG; j++) {
@@ -944,7 +988,7 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                 if (ii < total) {
                     const int p = one_pair ? 0 : ii / nq, qq = ii - p * nq;
                     w32 v[12];
-                    pack12<LLR_T>(ra[j], rb[j], scale, clipv, nclipv, v);
+                    pack12<LLR_T>(ra[j], rb[j], scale, clipv, nclipv, v, A.kf);
                     put4(pair_smem(smem_raw, g, P, NW, Wp, NP, p), qq, L, PP, v);
                 }
             }
@@ -959,11 +1003,11 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
     }
     // ---- pull the rows of the codeblock pair that will run on this SM slot next into L2 (bulk
     //      prefetch, a few KB per instruction; rows are 16-byte multiples)
-    if (KP && A.prefetch_stride > 0) {
+    if (KP && A.prefetch_stride > 0 && LLR_T != kLlrSymQpskF32) {
         const long long nxt = (long long)2 * NP * (blockIdx.x + A.prefetch_stride);
         if (nxt < A.n_cb) {
             const long long nrows = (A.n_cb - nxt < 2 * NP) ? (A.n_cb - nxt) : 2 * NP;
-            const size_t esz = LLR_T == TDB200_LLR_F64 ? 8 : (LLR_T == TDB200_LLR_F32 ? 4 : (LLR_T == TDB200_LLR_F16 ? 2 : 1));
+            const size_t esz = LLR_T == TDB200_LLR_F64 ? 8 : ((LLR_T == TDB200_LLR_F32 || LLR_T == kLlrSymBpskF32) ? 4 : (LLR_T == TDB200_LLR_F16 ? 2 : 1));
             // 16-byte granules: with one-byte channel values a row pair starts on an 8-byte boundary
             const size_t b0 = reinterpret_cast<size_t>(A.llr) + (size_t)nxt * row * esz;
             const size_t lo = b0 & ~(size_t)15, hi = (b0 + (size_t)nrows * row * esz) & ~(size_t)15;
@@ -1004,8 +1048,8 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
             for (int j = 0; j < 8; j++) bt[j] = j ? dup2(kFxNeg) : 0u;
             for (int m = 2; m >= 0; m--) {
                 const size_t o = (size_t)3 * K + 6 * s + 2 * m;
-                const w32 u = pack2(load1<LLR_T>(A.llr, cbA * row + o, scale, clip), load1<LLR_T>(A.llr, cbB * row + o, scale, clip));
-                const w32 v = pack2(load1<LLR_T>(A.llr, cbA * row + o + 1, scale, clip), load1<LLR_T>(A.llr, cbB * row + o + 1, scale, clip));
+                const w32 u = pack2(load1<LLR_T>(A, cbA, row, o, scale, clip), load1<LLR_T>(A, cbB, row, o, scale, clip));
+                const w32 v = pack2(load1<LLR_T>(A, cbA, row, o + 1, scale, clip), load1<LLR_T>(A, cbB, row, o + 1, scale, clip));
                 beta_step_x<LM>(bt, u, v, c);
             }
             norm8(bt);

@@ -81,6 +81,9 @@ cudaError_t launch_ref64_siso(const Ref64SisoArgs &a, cudaStream_t st, int *n_la
 // (pi(tL+j) = r_j + L*((q_j + A_t + j*B_t) mod P): same row r_j for all t, column a permutation
 // polynomial in t) bank-conflict free when 32 | P.
 constexpr int kFxNeg = -14000;  // metric of an impossible state (range analysis in DESIGN.md)
+// Internal channel-value sources of the packed decoders beyond tdb200_llr_type: received float symbols, demapped inside the
+// load stage (tdb200_decode_symbols_batch with BPSK / QPSK): llr = the I plane, sym_q = the Q plane, kf = 1 / (2 sigma^2)
+constexpr int kLlrSymBpskF32 = 8, kLlrSymQpskF32 = 9;
 
 struct FastGeom {
     int K, L, P, NW, G;
@@ -95,6 +98,8 @@ struct FastGeom {
 
 struct FastArgs {
     const void *llr;  // [n_cb][3K+12] device
+    const void *sym_q;  // kLlrSym*: the Q plane
+    float kf;           // kLlrSym*: 1 / (2 sigma^2)
     int llr_type;
     int n_cb;
     FastGeom g;
