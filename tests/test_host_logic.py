@@ -115,6 +115,35 @@ def test_fixed_point_model_subblocks_and_guard(oracle):
     assert oracle.fx_decode(llr[0].astype(np.float32), pi, _fx(K, 8, 50, 0))[2] == -1
 
 
+def test_logmap_fixed_point_model_tracks_the_reference_decoder(oracle):
+    """The integer specification of TDB200_ALGO_LOGMAP_S16 (oracle/turbo_oracle_fx.c, logmap = 1: max* with the linear
+    correction on shared quarter-differences) against the reference's fp64 Log-MAP (the restatement of
+    ITTC/log_map.cpp:898-1047 with E_algorithm :779-801) on the same frames in the waterfall (K = 6144, 0.4 dB, where the
+    max-log decoder of the same arithmetic fails most frames): no int16 overflow, nearly the same set of frames
+    decoded, and far ahead of max-log.  The statistically meaningful version of this statement (16 384 frames per
+    point, per iteration) is profiles/r02_bler_paired_*.json, made on the GPU by tools/bler_paired.py."""
+    from concurrent.futures import ThreadPoolExecutor
+    K, n, eb = 6144, 24, 0.4
+    pi = oracle.qpp(K)
+    bits, llr = oracle.make_batch(K, n, eb, seed=31337)
+    llr32 = llr.astype(np.float32)
+    lm = FxParams(K=K, n_iter=8, sub_len=48, warmup=24, frac_bits=4, llr_clip=127, ext_clip=511, ext_scale_q2=4, logmap=1, lm_upper_off=1)
+    ml = FxParams(K=K, n_iter=8, sub_len=48, warmup=16, frac_bits=3, llr_clip=127, ext_clip=511, ext_scale_q2=3)
+    with ThreadPoolExecutor(8) as pool:
+        ref = list(pool.map(lambda c: (oracle.decode(llr[c], pi, 8)[-1] != bits[c]).any(), range(n)))
+        a = list(pool.map(lambda c: oracle.fx_decode(llr32[c], pi, lm), range(n)))
+        b = list(pool.map(lambda c: oracle.fx_decode(llr32[c], pi, ml), range(n)))
+    assert all(r[3] == 0 for r in a), "int16 range exceeded"
+    e_ref = int(sum(ref))
+    e_lm = sum(int((r[0] != bits[c]).any()) for c, r in enumerate(a))
+    e_ml = sum(int((r[0] != bits[c]).any()) for c, r in enumerate(b))
+    assert e_lm <= e_ref + 2, (e_ref, e_lm, e_ml)
+    assert e_ml >= e_lm + 2, (e_ref, e_lm, e_ml)
+    # and the correction is what makes the difference: the same model without it is the max-log decoder
+    lm0 = FxParams(K=K, n_iter=8, sub_len=48, warmup=24, frac_bits=4, llr_clip=127, ext_clip=511, ext_scale_q2=4, logmap=0)
+    assert oracle.fx_decode(llr32[0], pi, lm0)[3] == 0
+
+
 def test_early_termination_model(oracle):
     K = 1024
     pi = oracle.qpp(K)

@@ -36,6 +36,12 @@ static int fail(int status, const char *fmt, ...)
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+__global__ void fill_i32_kernel(int32_t *p, int n, int v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 // Every entry point works on the decoder's device and leaves the caller's current device as it found it (a thread that
 // holds handles for several GPUs, or shares the process with torch, must not have its device switched under it).
 struct DeviceGuard {
@@ -676,10 +682,9 @@ static int decode_core(tdb200_decoder *d, const Source &src, int mem, int n_cb, 
                                  fused_sym ? static_cast<const char *>(src.sym_q) + (size_t)c0 * NS * ssz : nullptr, src.kf);
             if (s) return s;
         }
-        if (f64 && out->iters_used) {  // the fp64 mode always runs every iteration
-            std::vector<int32_t> v(n_cb, c.n_iter);
-            TDB_CUDA(cudaMemcpyAsync(out->iters_used, v.data(), sizeof(int32_t) * n_cb, cudaMemcpyHostToDevice, st));
-            TDB_CUDA(cudaStreamSynchronize(st));  // v goes out of scope
+        if (f64 && out->iters_used) {  // the fp64 mode always runs every iteration: a fill kernel, so that the call stays asynchronous
+            fill_i32_kernel<<<(n_cb + 255) / 256, 256, 0, st>>>(out->iters_used, n_cb, c.n_iter);
+            TDB_CUDA(cudaGetLastError());
         }
         return TDB200_OK;
     }
