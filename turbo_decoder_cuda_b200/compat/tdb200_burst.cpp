@@ -5,7 +5,7 @@
 // random bits -> tdb200_encode_batch -> tdb200_channel_batch -> tdb200_decode_batch -> error count,
 // everything device-resident, the decode timed with CUDA events.
 //
-//   tdb200_burst [--total N] [--gpus G] [--ebn0 dB] [--chunk C] [--early-term 0|1|2 (CRC24B)|3 (CRC24A)] [--K K]
+//   tdb200_burst [--total N] [--gpus G] [--ebn0 dB] [--chunk C] [--early-term 0|1|2 (CRC24B)|3 (CRC24A)] [--K K] [--algo maxlog_s16|logmap_s16]
 //                [--modulation 1|2|3|4|6] [--E bits-per-codeblock-after-rate-matching] [--rv 0..3]
 //
 // With --modulation > 1 or --E the loop is main.cpp's with the two commented-out stages restored:
@@ -29,6 +29,8 @@
 #include "tdb200.h"
 
 namespace {
+
+int g_algo = TDB200_ALGO_MAXLOG_S16;  // --algo maxlog_s16 | logmap_s16
 
 struct Result {
     double ms = 0;
@@ -54,7 +56,7 @@ void worker(int dev, int K, long long lo, long long hi, int chunk, double sigma,
     CK(cudaSetDevice(dev));
     tdb200_config cfg;
     tdb200_default_config(&cfg, K);
-    cfg.device = dev; cfg.max_batch = chunk; cfg.early_term = early_term;
+    cfg.device = dev; cfg.max_batch = chunk; cfg.early_term = early_term; cfg.algo = g_algo;
     tdb200_decoder *dec = nullptr;
     TK(tdb200_create(&cfg, &dec));
     const size_t NL = 3 * (size_t)K + 12;
@@ -174,6 +176,7 @@ int main(int argc, char **argv)
         else if (a == "--modulation") ch.modulation = std::atoi(argv[i + 1]);
         else if (a == "--E") ch.E = std::atoi(argv[i + 1]);
         else if (a == "--rv") ch.rv = std::atoi(argv[i + 1]);
+        else if (a == "--algo") g_algo = (std::string(argv[i + 1]) == "logmap_s16") ? TDB200_ALGO_LOGMAP_S16 : TDB200_ALGO_MAXLOG_S16;
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     int ndev = 0;
