@@ -305,7 +305,8 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         if (c.max_batch <= 0) c.max_batch = 4096;
         const size_t nb = (size_t)((c.max_batch + 3) / 4) * 4;  // warps own groups of four
         const size_t T = d->T;
-        const size_t per_cb = 7 * T + (T + 1) + 2 * 8 * (T + 1);
+        const size_t n_win = (T + kRef64Window - 1) / kRef64Window;
+        const size_t per_cb = 6 * T + 8 * n_win;
         TDB_CUDA(cudaMalloc(&d->ws64_block, sizeof(double) * per_cb * nb));
         double *p = static_cast<double *>(d->ws64_block);
         Ref64Workspace &w = d->ws64;
@@ -315,10 +316,8 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         w.xp2 = p; p += T * nb;
         w.La = p; p += T * nb;
         w.Le = p; p += T * nb;
-        w.LLR = p; p += T * nb;
-        w.tmax = p; p += (T + 1) * nb;
-        w.alpha = p; p += 8 * (T + 1) * nb;
-        w.beta = p; p += 8 * (T + 1) * nb;
+        w.ck = p; p += 8 * n_win * nb;
+        w.n_win = (int)n_win;
         w.max_batch = c.max_batch;
     } else if (c.algo == TDB200_ALGO_MAXLOG_S16 || c.algo == TDB200_ALGO_LOGMAP_F32 || c.algo == TDB200_ALGO_MAXLOG_F32 ||
                c.algo == TDB200_ALGO_LINLOGMAP_F32 || c.algo == TDB200_ALGO_LOGMAP_S16) {

@@ -43,12 +43,13 @@ __host__ __device__ constexpr double o0(int s) { return ((kPar0 >> s) & 1) ? 1.0
 __host__ __device__ constexpr double o1(int s) { return -o0(s); }
 
 // ------------------------------------------------------------------ fp64 reference-order path
+constexpr int kRef64Window = 32;  // trellis steps between the alpha vectors the forward sweep keeps
 struct Ref64Workspace {
     // per codeblock, T = K+3 doubles each unless noted
     double *xs1, *xp1, *xs2, *xp2;  // half-LLRs after demultiplex (yk_turbo, log_map.cpp:1083-1127)
-    double *La, *Le, *LLR;
-    double *tmax;         // [T+1]
-    double *alpha, *beta; // [T+1][8]
+    double *La, *Le;
+    double *ck;           // [n_win][8]: alpha at the start of every window (alpha and beta themselves stay on chip)
+    int n_win;            // ceil(T / kRef64Window)
     int max_batch;
 };
 

@@ -10,14 +10,24 @@
 // non-reproducible term in the reference is its uninitialised tempmax[], :925/:989; like the
 // oracle this kernel normalises by max_j alpha_j).
 //
-// Mapping (nothing like the reference's loops): one warp owns four codeblocks for the whole
-// decode.  The two sequential recursions run with ONE LANE PER TRELLIS STATE (8 lanes per
-// codeblock, 4 codeblocks per warp); predecessor/successor metrics are exchanged with
-// width-8 warp shuffles, the per-step max_j alpha_j is a 3-round shuffle butterfly, and the
-// (xs,xp,La) inputs of eight consecutive steps are fetched with one coalesced load per lane and
-// broadcast by shuffle.  alpha/beta go to an HBM workspace ([step][state], 64 B per step); the
-// LLR/extrinsic phase is then embarrassingly parallel over trellis positions and runs with all
-// 32 lanes.  Warps never talk to each other, so the only synchronisation is __syncwarp().
+// Mapping (nothing like the reference's loops).  The recursion cannot be cut into sub-blocks here
+// (that would change results), so one decode is 32 dependent sweeps of K+3 steps and the kernel is
+// bound by the LATENCY of one trellis step; everything is arranged around that chain
+// (tools/ubench_fp64.cu: DADD 8 clk, compare+select 14, 64-bit shuffle 26, shared round trip 35):
+//   * one warp owns four codeblocks for the whole decode, ONE LANE PER TRELLIS STATE;
+//   * alpha and beta never leave the SM: the forward sweep keeps one alpha vector per 32-step
+//     window (64 B per window in an L2-resident scratch), the backward sweep re-creates a window's
+//     alpha vectors (bit-identical: same operations on the same operands) into shared memory, runs
+//     beta over the window, and the a-posteriori sums of the window are then folded with one LANE
+//     PER TRELLIS POSITION (E_algorithm_seq is a serial fold over the states, :817-829);
+//   * an alpha step exchanges the un-normalised metrics ONCE through shared memory: every lane
+//     reads all eight (for max_j, :987-993) and its two predecessors, and subtracts the normaliser
+//     itself -- one round trip instead of a 3-round shuffle butterfly plus a predecessor exchange;
+//   * max* looks its correction up in a 58-entry HASHED table: the exponent and top three mantissa
+//     bits of |x-y| select an interval that holds at most one of the reference's 16 breakpoints,
+//     one exact comparison against that breakpoint picks the value -- the same result as the
+//     reference's linear scan for every double, in 10 instructions instead of a 15-compare tree;
+//   * the (xs,xp,La) inputs of the next window arrive by cp.async while the current one runs.
 // Compile with -fmad=false: products here are exact (x * +-1, x * 0.5) so contraction would not
 // change results, but the flag keeps that a non-question.
 #include <cuda_fp16.h>
@@ -30,23 +40,58 @@ namespace {
 
 constexpr double kInfty = 1E20;  // ITTC/log_map.h:72-74
 
-// max*(x,y), ITTC/log_map.cpp:779-801.  The linear LUT scan is restated as a 4-level select
-// tree over the same 16 breakpoints: region [idx[k], idx[k+1]) -> table[k], d >= 4.3758 -> 0.
-__device__ __forceinline__ double lut_corr(double d)
+constexpr int kW = kRef64Window;           // steps per window
+constexpr int kRow = 9;                    // doubles per alpha/beta row: 8 states + 1 (lane stride 18 banks: conflict-free position reads)
+constexpr int kCbStride = kW * kRow + 8;   // doubles per codeblock region; 592 words = 16 (mod 32): the two codeblocks of a half-warp do not collide
+constexpr int kLutEntries = 58;            // |d| < 2^-4, 7 binades x 8 sub-intervals, |d| >= 8
+
+struct Smem {  // one warp per CTA
+    double in[2][3][4][kW];      // staged xs, xp, La of two windows (cp.async double buffer)
+    double aw[4][kCbStride];     // alpha_i of the window, row = step, [state]
+    double bw[4][kCbStride];     // beta_{i+1} of the window
+    double mw[4][kW];            // normaliser max(0, max_j alpha_j) of step i+1 (tempmax[], :987-993)
+    double ex[2][4][8];          // alpha exchange, double-buffered by step parity
+    double lut[kLutEntries][4];  // {breakpoint, value below it, value from it on, -}
+};
+
+// The correction table of E_algorithm, hashed by the leading bits of d (see the header).  Entry e:
+// 0 covers d < 2^-4, 1..56 the intervals 2^(b-4) * [1 + s/8, 1 + (s+1)/8), 57 covers d >= 8.
+__device__ void build_lut(double (*lut)[4], int lane)
 {
-    return d < 1.0502
-               ? (d < 0.43275 ? (d < 0.19587 ? (d < 0.08824 ? 0.69315 : 0.65) : (d < 0.31026 ? 0.6 : 0.55))
-                              : (d < 0.70963 ? (d < 0.56508 ? 0.5 : 0.45) : (d < 0.86972 ? 0.4 : 0.35)))
-               : (d < 2.2522 ? (d < 1.5078 ? (d < 1.2587 ? 0.3 : 0.25) : (d < 1.8212 ? 0.2 : 0.15))
-                             : (d < 3.6764 ? (d < 2.9706 ? 0.1 : 0.05) : (d < 4.3758 ? 0.025 : 0.0)));
+    const double idx[16] = {0.0, 0.08824, 0.19587, 0.31026, 0.43275, 0.56508, 0.70963, 0.86972,
+                            1.0502, 1.2587, 1.5078, 1.8212, 2.2522, 2.9706, 3.6764, 4.3758};  // :14-16
+    const double val[16] = {0.69315, 0.65, 0.6, 0.55, 0.5, 0.45, 0.4, 0.35,
+                            0.3, 0.25, 0.2, 0.15, 0.1, 0.05, 0.025, 0.0};  // :17-18; from 4.3758 on the result is 0 (:784-787)
+    for (int e = lane; e < kLutEntries; e += 32) {
+        double bp = 1e300, below, above;
+        if (e == 0) below = above = val[0];
+        else if (e == kLutEntries - 1) below = above = 0.0;
+        else {
+            const int b = (e - 1) >> 3, s = (e - 1) & 7;
+            const double base = 1.0 / (double)(1 << 4) * (double)(1 << b);
+            const double lo = base * (1.0 + 0.125 * s), hi = lo + base * 0.125;
+            int k = 0;
+            for (int t = 1; t < 16; t++) if (idx[t] <= lo) k = t;  // region of lo: [idx[k], idx[k+1])
+            below = above = val[k];
+            if (k < 15 && idx[k + 1] < hi) { bp = idx[k + 1]; above = val[k + 1]; }
+        }
+        lut[e][0] = bp; lut[e][1] = below; lut[e][2] = above; lut[e][3] = 0.0;
+    }
 }
-__device__ __forceinline__ double max_star(double x, double y)
+
+// max*(x,y), ITTC/log_map.cpp:779-801
+__device__ __forceinline__ double max_star(double x, double y, const double (*lut)[4])
 {
-    double d = (y - x) > 0 ? (y - x) : (x - y);
-    return (x > y ? x : y) + lut_corr(d);
+    const double diff = y - x;  // d = (y-x) > 0 ? (y-x) : (x-y) = |diff|
+    int e = ((__double2hiint(diff) & 0x7fffffff) >> 17) - ((1023 - 4) * 8 - 1);
+    e = min(max(e, 0), kLutEntries - 1);
+    const double2 t = *reinterpret_cast<const double2 *>(&lut[e][0]);
+    const double above = lut[e][2];
+    return (x > y ? x : y) + (fabs(diff) < t.x ? t.y : above);
 }
 
 __device__ __forceinline__ double shfl8(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 8); }
+__device__ __forceinline__ double dmax(double a, double b) { return a < b ? b : a; }
 
 __device__ __forceinline__ double load_llr_half(const void *p, int type, size_t idx)
 {
@@ -57,121 +102,217 @@ __device__ __forceinline__ double load_llr_half(const void *p, int type, size_t 
     return static_cast<double>(static_cast<const int8_t *>(p)[idx]) * 0.0625;  // S8, 3 fractional bits
 }
 
-// One BCJR pass for the four codeblocks of this warp.  xs/xp/La/LLR/tmax/alpha/beta point at
-// the warp's first codeblock; strides are per codeblock.
-struct SisoPtrs {
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Inputs of one BCJR pass for the four codeblocks of this warp (planar, stride sT per codeblock).
+struct PassIn {
     const double *xs, *xp, *La;
-    double *LLR, *tmax, *alpha, *beta;
-    size_t sT;   // stride of T-long arrays
-    size_t sT1;  // stride of tmax (T+1)
-    size_t sAB;  // stride of alpha/beta (8*(T+1))
+    size_t sT;
+    double *ck;   // alpha at the start of every window: [4][n_win][8]
+    size_t sCk;   // = 8 * n_win
+    int T, terminated;
 };
 
-__device__ void siso_pass(const SisoPtrs &p, int T, int terminated, int lane)
+// Window w of the three input arrays -> sm.in[buf] (lane (g,j): steps j, j+8, j+16, j+24 of codeblock g).
+__device__ __forceinline__ void stage_window(Smem &sm, const PassIn &p, int w, int buf, int g, int j)
+{
+    if (w >= 0) {
+        const int i0 = w * kW;
+        const double *src[3] = {p.xs + g * p.sT, p.xp + g * p.sT, p.La + g * p.sT};
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int r = 0; r < kW / 8; r++) {
+                const int u = j + 8 * r;
+                if (i0 + u < p.T) cp_async8(&sm.in[buf][k][g][u], src[k] + i0 + u);
+            }
+    }
+    cp_async_commit();
+}
+
+// Steps [0, wlen) of window `buf`, forward.  On entry al = alpha_i(j) of the window's first step and
+// (a0, a1) = alpha_i of the two predecessors of state j; on exit the same for the step after the
+// window.  STORE: keep alpha_i (rows of sm.aw) and the normalisers (sm.mw) for the beta / LLR phase.
+template <bool STORE>
+__device__ __forceinline__ void alpha_window(Smem &sm, int buf, int g, int j, int wlen, double &al, double &a0, double &a1,
+                                             int ls0, int ls1, double sa0, double sa1)
+{
+    const double *is = sm.in[buf][0][g], *ip = sm.in[buf][1][g], *il = sm.in[buf][2][g];
+    double s = is[0], q = ip[0], h = il[0] * 0.5;
+    double g0 = (-s + q * sa0) - h;  // gamma(from ls0, input 0), :967-968
+    double g1 = (s + q * sa1) + h;   // gamma(from ls1, input 1), :969-970
+    if (STORE) sm.aw[g][j] = al;
+#pragma unroll 2
+    for (int u = 0; u < wlen; u++) {
+        const double v = max_star(g0 + a0, g1 + a1, sm.lut);
+        double *ex = sm.ex[u & 1][g];
+        ex[j] = v;
+        // the next step's branch metrics, in the shadow of the exchange
+        const int un = min(u + 1, kW - 1);
+        s = is[un]; q = ip[un]; h = il[un] * 0.5;
+        g0 = (-s + q * sa0) - h;
+        g1 = (s + q * sa1) + h;
+        __syncwarp();
+        const double2 *e2 = reinterpret_cast<const double2 *>(ex);
+        const double2 v01 = e2[0], v23 = e2[1], v45 = e2[2], v67 = e2[3];
+        const double x0 = ex[ls0], x1 = ex[ls1];
+        const double m = dmax(dmax(dmax(v01.x, v01.y), dmax(v23.x, v23.y)), dmax(dmax(v45.x, v45.y), dmax(v67.x, v67.y)));
+        // tempmax[i+1] = max(0, max_j alpha_j): the reference compares against an uninitialised
+        // tempmax[] (:925,:989); on a clean (zero-filled) heap that is this, which is what oracle/ pins
+        const bool neg = m < 0.0;
+        a0 = neg ? x0 : x0 - m;  // :996-999
+        a1 = neg ? x1 : x1 - m;
+        al = neg ? v : v - m;
+        if (STORE) {
+            if (j == 0) sm.mw[g][u] = neg ? 0.0 : m;
+            if (u + 1 < wlen) sm.aw[g][(u + 1) * kRow + j] = al;
+        }
+    }
+}
+
+// Steps [0, wlen) of window `buf`, backward.  be = beta_{i+1}(j) of the window's last step on entry,
+// beta_i(j) of its first step on exit.  Rows of sm.bw receive beta_{i+1}.
+__device__ __forceinline__ void beta_window(Smem &sm, int buf, int g, int j, int wlen, double &be, int ns0, int ns1, double sb0, double sb1)
+{
+    const double *is = sm.in[buf][0][g], *ip = sm.in[buf][1][g], *il = sm.in[buf][2][g];
+    sm.bw[g][(wlen - 1) * kRow + j] = be;
+#pragma unroll 2
+    for (int u = wlen - 1; u >= 0; u--) {
+        const double s = is[u], q = ip[u], h = il[u] * 0.5, m = sm.mw[g][u];
+        const double g0 = (-s + q * sb0) - h;
+        const double g1 = (s + q * sb1) + h;
+        const double tx = g0 + shfl8(be, ns0);
+        const double ty = g1 + shfl8(be, ns1);
+        be = max_star(tx, ty, sm.lut) - m;  // :1004-1021
+        if (u >= 1) sm.bw[g][(u - 1) * kRow + j] = be;
+    }
+}
+
+// LLR of the window, :1024-1039: lane = trellis position, one codeblock after the other.
+template <class Emit>
+__device__ __forceinline__ void fold_window(Smem &sm, int buf, int lane, int wlen, int i0, Emit &emit)
+{
+    if (lane >= wlen) return;
+#pragma unroll 2
+    for (int c = 0; c < 4; c++) {
+        const double s = sm.in[buf][0][c][lane], q = sm.in[buf][1][c][lane], l = sm.in[buf][2][c][lane];
+        const double h = l * 0.5;
+        const double g0m = (-s - q) - h, g0p = (-s + q) - h;  // input 0, parity -1 / +1
+        const double g1m = (s - q) + h, g1p = (s + q) + h;    // input 1
+        double a[8], b[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            a[k] = sm.aw[c][lane * kRow + k];
+            b[k] = sm.bw[c][lane * kRow + k];
+        }
+        double m0 = 0, m1 = 0;
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            const int l0 = tb(kLs0, jj), l1 = tb(kLs1, jj);
+            const double t0 = ((o0(l0) > 0 ? g0p : g0m) + a[l0]) + b[jj];  // :1028-1030
+            const double t1 = ((o1(l1) > 0 ? g1p : g1m) + a[l1]) + b[jj];  // :1032-1034
+            if (jj == 0) { m0 = t0; m1 = t1; }
+            else { m0 = max_star(m0, t0, sm.lut); m1 = max_star(m1, t1, sm.lut); }  // E_algorithm_seq, :817-829
+        }
+        emit(c, i0 + lane, m1 - m0, l, s);  // :1038
+    }
+}
+
+// One BCJR pass (Log_MAP_decoder, :898-1047) for the four codeblocks of this warp.
+template <class Emit>
+__device__ void siso_pass(Smem &sm, const PassIn &p, int lane, Emit &emit)
 {
     const int g = lane >> 3, j = lane & 7;
-    const double *xs = p.xs + g * p.sT, *xp = p.xp + g * p.sT, *La = p.La + g * p.sT;
-    double *tmax = p.tmax + g * p.sT1;
-    double *alpha = p.alpha + g * p.sAB, *beta = p.beta + g * p.sAB;
+    const int T = p.T, n_win = (T + kW - 1) / kW;
     const int ls0 = tb(kLs0, j), ls1 = tb(kLs1, j), ns0 = tb(kNs0, j), ns1 = tb(kNs1, j);
     const double sa0 = o0(ls0), sa1 = o1(ls1);  // parity signs of the branches ENTERING state j
     const double sb0 = o0(j), sb1 = o1(j);      // parity signs of the branches LEAVING state j
+    double *ck = p.ck + g * p.sCk + j;
 
-    // ---- alpha forward, :975-1001
+    // ---- alpha forward, :975-1001: only the window-start vectors are kept
     double al = (j == 0) ? 0.0 : -kInfty;  // :943-948
-    alpha[j] = al;
-    for (int i0 = 0; i0 < T; i0 += 8) {
-        const int ix = i0 + j;
-        const double vs = ix < T ? xs[ix] : 0.0, vp = ix < T ? xp[ix] : 0.0, vl = ix < T ? La[ix] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int i = i0 + u;
-            if (i >= T) break;  // uniform
-            const double s = shfl8(vs, u), q = shfl8(vp, u), l = shfl8(vl, u);
-            const double g0 = -s + q * sa0 - l / 2;  // gamma(from ls0, input 0), :967-968
-            const double g1 = s + q * sa1 + l / 2;   // gamma(from ls1, input 1), :969-970
-            const double tx = g0 + shfl8(al, ls0);
-            const double ty = g1 + shfl8(al, ls1);
-            const double v = max_star(tx, ty);
-            double m = v;  // tempmax[i+1] = max_j alpha_j, :987-993
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                const double t = __shfl_xor_sync(0xffffffffu, m, o, 8);
-                m = (m < t) ? t : m;
-            }
-            // the reference compares against an uninitialised tempmax[] (:925,:989); on a clean
-            // (zero-filled) heap that is max(0, max_j alpha_j), which is what oracle/ pins
-            m = (m < 0.0) ? 0.0 : m;
-            al = v - m;  // :996-999
-            alpha[(size_t)(i + 1) * 8 + j] = al;
-            if (j == 0) tmax[i + 1] = m;
-        }
+    double a0 = (ls0 == 0) ? 0.0 : -kInfty, a1 = (ls1 == 0) ? 0.0 : -kInfty;
+    stage_window(sm, p, 0, 0, g, j);
+    for (int w = 0; w < n_win; w++) {
+        ck[(size_t)w * 8] = al;
+        if (w == n_win - 1) break;  // the last window is re-created below anyway
+        stage_window(sm, p, w + 1, (w + 1) & 1, g, j);
+        cp_async_wait<1>();
+        __syncwarp();
+        alpha_window<false>(sm, w & 1, g, j, kW, al, a0, a1, ls0, ls1, sa0, sa1);
+        __syncwarp();
     }
-    __syncwarp();
-    // ---- beta backward, :1004-1021
-    double be = (j == 0) ? 0.0 : (terminated ? -kInfty : 0.0);  // :944-959
-    beta[(size_t)T * 8 + j] = be;
-    for (int i0 = ((T - 1) >> 3) << 3; i0 >= 0; i0 -= 8) {
-        const int ix = i0 + j;
-        const double vs = ix < T ? xs[ix] : 0.0, vp = ix < T ? xp[ix] : 0.0, vl = ix < T ? La[ix] : 0.0;
-        const double vm = ix < T ? tmax[ix + 1] : 0.0;
-#pragma unroll
-        for (int u = 7; u >= 0; u--) {
-            const int i = i0 + u;
-            if (i >= T) continue;  // uniform
-            const double s = shfl8(vs, u), q = shfl8(vp, u), l = shfl8(vl, u), m = shfl8(vm, u);
-            const double g0 = -s + q * sb0 - l / 2;
-            const double g1 = s + q * sb1 + l / 2;
-            const double tx = g0 + shfl8(be, ns0);
-            const double ty = g1 + shfl8(be, ns1);
-            be = max_star(tx, ty) - m;
-            beta[(size_t)i * 8 + j] = be;
+    // window n_win-1 is in flight (or, with a single window, staged by the first call)
+    // ---- backward: re-create alpha per window, beta :1004-1021, LLR :1024-1039
+    double be = (j == 0) ? 0.0 : (p.terminated ? -kInfty : 0.0);  // :944-959
+    double ck_next = 0.0;  // alpha at the start of window w-1, fetched one window ahead
+    for (int w = n_win - 1; w >= 0; w--) {
+        const int buf = w & 1, wlen = min(kW, T - w * kW);
+        stage_window(sm, p, w - 1, (w - 1) & 1, g, j);
+        cp_async_wait<1>();
+        __syncwarp();
+        if (w < n_win - 1) {  // otherwise (al, a0, a1) are what the forward sweep left
+            al = ck_next;
+            a0 = shfl8(al, ls0);
+            a1 = shfl8(al, ls1);
         }
+        if (w >= 1) ck_next = ck[(size_t)(w - 1) * 8];
+        alpha_window<true>(sm, buf, g, j, wlen, al, a0, a1, ls0, ls1, sa0, sa1);
+        __syncwarp();
+        beta_window(sm, buf, g, j, wlen, be, ns0, ns1, sb0, sb1);
+        __syncwarp();
+        fold_window(sm, buf, lane, wlen, w * kW, emit);
+        __syncwarp();
     }
-    __syncwarp();
-    // ---- LLR, :1024-1039: all 32 lanes over positions, one codeblock after the other
-    for (int c = 0; c < 4; c++) {
-        const double *cxs = p.xs + c * p.sT, *cxp = p.xp + c * p.sT, *cLa = p.La + c * p.sT;
-        const double *ca = p.alpha + c * p.sAB, *cb = p.beta + c * p.sAB;
-        double *cL = p.LLR + c * p.sT;
-        for (int i = lane; i < T; i += 32) {
-            const double s = cxs[i], q = cxp[i], l = cLa[i];
-            double a[8], b[8];
-            const double2 *a2 = reinterpret_cast<const double2 *>(ca + (size_t)i * 8);
-            const double2 *b2 = reinterpret_cast<const double2 *>(cb + (size_t)(i + 1) * 8);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                double2 t = a2[k];
-                a[2 * k] = t.x; a[2 * k + 1] = t.y;
-                t = b2[k];
-                b[2 * k] = t.x; b[2 * k + 1] = t.y;
-            }
-            double m0 = 0, m1 = 0;
-#pragma unroll
-            for (int jj = 0; jj < 8; jj++) {
-                const int l0 = tb(kLs0, jj), l1 = tb(kLs1, jj);
-                const double t0 = (-s + q * o0(l0) - l / 2) + a[l0] + b[jj];  // :1028-1030
-                const double t1 = (s + q * o1(l1) + l / 2) + a[l1] + b[jj];   // :1032-1034
-                if (jj == 0) { m0 = t0; m1 = t1; }
-                else { m0 = max_star(m0, t0); m1 = max_star(m1, t1); }        // E_algorithm_seq, :817-829
-            }
-            cL[i] = m1 - m0;  // :1038
-        }
-    }
-    __syncwarp();
+    cp_async_wait<0>();
 }
 
-__global__ void __launch_bounds__(128) ref64_decode_kernel(Ref64Args a)
+struct DecodeEmit {
+    const Ref64Args &a;
+    double *Le;  // workspace of the warp's four codeblocks
+    size_t sT;
+    int cb0, T, K, it, siso;
+    bool last;
+    __device__ __forceinline__ void operator()(int c, int i, double L, double la, double xs) const
+    {
+        // extrinsic, :1234-1238 / :1255-1259; decision + deinterleave, :1261-1264
+        const double le = L - la - 2 * xs;
+        Le[c * sT + i] = le;
+        const int cb = cb0 + c;
+        if (cb >= a.n_cb) return;
+        if (siso == 1 && i < K) {
+            const int bit = (L < 0) ? 0 : 1;
+            const int pos = a.pi[i];
+            if (a.bits_iters) a.bits_iters[((size_t)cb * a.n_iter + it) * K + pos] = bit;
+            if (last && a.bits) a.bits[(size_t)cb * K + pos] = (uint8_t)bit;
+        }
+        if (last) {
+            if (siso == 0 && a.llr1) a.llr1[(size_t)cb * T + i] = L;
+            if (siso == 1 && a.llr2) a.llr2[(size_t)cb * T + i] = L;
+            if (siso == 1 && a.ext2) a.ext2[(size_t)cb * T + i] = le;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(32) ref64_decode_kernel(Ref64Args a)
 {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int cb0 = warp * 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int lane = threadIdx.x;
+    const int cb0 = blockIdx.x * 4;
     if (cb0 >= a.n_cb) return;
     const int K = a.K, T = K + kTail, NL = 3 * K + 4 * kTail;
-    const size_t sT = T, sT1 = T + 1, sAB = (size_t)8 * (T + 1);
+    const size_t sT = T;
     const Ref64Workspace &w = a.ws;
     double *xs1 = w.xs1 + cb0 * sT, *xp1 = w.xp1 + cb0 * sT, *xs2 = w.xs2 + cb0 * sT, *xp2 = w.xp2 + cb0 * sT;
-    double *La = w.La + cb0 * sT, *Le = w.Le + cb0 * sT, *LLR = w.LLR + cb0 * sT;
+    double *La = w.La + cb0 * sT, *Le = w.Le + cb0 * sT;
+    build_lut(sm.lut, lane);
 
     // ---- x0.5 and demultiplex, :1202-1209, :1083-1127
     for (int c = 0; c < 4; c++) {
@@ -198,58 +339,50 @@ __global__ void __launch_bounds__(128) ref64_decode_kernel(Ref64Args a)
     }
     __syncwarp();
 
-    SisoPtrs sp;
-    sp.La = La; sp.LLR = LLR;
-    sp.tmax = w.tmax + cb0 * sT1; sp.alpha = w.alpha + cb0 * sAB; sp.beta = w.beta + cb0 * sAB;
-    sp.sT = sT; sp.sT1 = sT1; sp.sAB = sAB;
+    PassIn p;
+    p.La = La; p.sT = sT; p.T = T; p.terminated = 1;
+    p.sCk = (size_t)8 * w.n_win;
+    p.ck = w.ck + cb0 * p.sCk;
 
     for (int it = 0; it < a.n_iter; it++) {
-        const bool last = (it == a.n_iter - 1);
         for (int siso = 0; siso < 2; siso++) {
             // a-priori for this pass: SISO-1 La[pi(i)] = Le[i] (random_deinterlvr_double, :1221),
             // SISO-2 La[i] = Le[pi(i)] (randominterleaver_double, :1242); tail forced to 0.
             const int *idx = siso == 0 ? a.pi_inv : a.pi;
-            for (int c = 0; c < 4; c++)
-                for (int i = lane; i < T; i += 32) La[c * sT + i] = (i < K) ? Le[c * sT + idx[i]] : 0.0;
-            __syncwarp();
-            sp.xs = siso == 0 ? xs1 : xs2;
-            sp.xp = siso == 0 ? xp1 : xp2;
-            siso_pass(sp, T, 1, lane);
-            // extrinsic, :1234-1238 / :1255-1259; decision + deinterleave, :1261-1264
             for (int c = 0; c < 4; c++) {
-                const int cb = cb0 + c;
-                const bool valid = cb < a.n_cb;
-                for (int i = lane; i < T; i += 32) {
-                    const double L = LLR[c * sT + i];
-                    Le[c * sT + i] = L - La[c * sT + i] - 2 * sp.xs[c * sT + i];
-                    if (!valid) continue;
-                    if (siso == 1 && i < K) {
-                        const int bit = (L < 0) ? 0 : 1;
-                        const int pos = a.pi[i];
-                        if (a.bits_iters) a.bits_iters[((size_t)cb * a.n_iter + it) * K + pos] = bit;
-                        if (last && a.bits) a.bits[(size_t)cb * K + pos] = (uint8_t)bit;
-                    }
-                    if (last) {
-                        if (siso == 0 && a.llr1) a.llr1[(size_t)cb * T + i] = L;
-                        if (siso == 1 && a.llr2) a.llr2[(size_t)cb * T + i] = L;
-                        if (siso == 1 && a.ext2) a.ext2[(size_t)cb * T + i] = Le[c * sT + i];
-                    }
-                }
+#pragma unroll 4
+                for (int i = lane; i < T; i += 32) La[c * sT + i] = (i < K) ? Le[c * sT + idx[i]] : 0.0;
             }
+            __syncwarp();
+            p.xs = siso == 0 ? xs1 : xs2;
+            p.xp = siso == 0 ? xp1 : xp2;
+            DecodeEmit emit{a, Le, sT, cb0, T, K, it, siso, it == a.n_iter - 1};
+            siso_pass(sm, p, lane, emit);
             __syncwarp();
         }
     }
 }
 
-__global__ void __launch_bounds__(128) ref64_siso_kernel(Ref64SisoArgs a)
+struct SisoEmit {
+    const Ref64SisoArgs &a;
+    int cb0;
+    __device__ __forceinline__ void operator()(int c, int i, double L, double, double) const
+    {
+        if (cb0 + c < a.n_cb) a.LLR[(size_t)(cb0 + c) * a.T + i] = L;
+    }
+};
+
+__global__ void __launch_bounds__(32) ref64_siso_kernel(Ref64SisoArgs a)
 {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int cb0 = warp * 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int lane = threadIdx.x;
+    const int cb0 = blockIdx.x * 4;
     if (cb0 >= a.n_cb) return;
     const int T = a.T;
-    const size_t sT = T, sT1 = T + 1, sAB = (size_t)8 * (T + 1);
+    const size_t sT = T;
     const Ref64Workspace &w = a.ws;
+    build_lut(sm.lut, lane);
     // de-interleave recs (xs,xp pairs) into the planar workspace
     for (int c = 0; c < 4; c++) {
         const int cb = min(cb0 + c, a.n_cb - 1);
@@ -260,36 +393,27 @@ __global__ void __launch_bounds__(128) ref64_siso_kernel(Ref64SisoArgs a)
         }
     }
     __syncwarp();
-    SisoPtrs sp;
-    sp.xs = w.xs1 + cb0 * sT; sp.xp = w.xp1 + cb0 * sT; sp.La = w.La + cb0 * sT; sp.LLR = w.LLR + cb0 * sT;
-    sp.tmax = w.tmax + cb0 * sT1; sp.alpha = w.alpha + cb0 * sAB; sp.beta = w.beta + cb0 * sAB;
-    sp.sT = sT; sp.sT1 = sT1; sp.sAB = sAB;
-    siso_pass(sp, T, a.terminated, lane);
-    for (int c = 0; c < 4; c++) {
-        const int cb = cb0 + c;
-        if (cb >= a.n_cb) break;
-        for (int i = lane; i < T; i += 32) a.LLR[(size_t)cb * T + i] = w.LLR[(cb0 + c) * sT + i];
-    }
+    PassIn p;
+    p.xs = w.xs1 + cb0 * sT; p.xp = w.xp1 + cb0 * sT; p.La = w.La + cb0 * sT;
+    p.sT = sT; p.T = T; p.terminated = a.terminated;
+    p.sCk = (size_t)8 * w.n_win;
+    p.ck = w.ck + cb0 * p.sCk;
+    SisoEmit emit{a, cb0};
+    siso_pass(sm, p, lane, emit);
 }
 
 }  // namespace
 
 cudaError_t launch_ref64_decode(const Ref64Args &a, cudaStream_t st, int *n_launches)
 {
-    const int warps = (a.n_cb + 3) / 4;
-    const int wpb = 2;  // 64-thread CTAs: spreads a small batch over more SMs
-    const int blocks = (warps + wpb - 1) / wpb;
-    ref64_decode_kernel<<<blocks, wpb * 32, 0, st>>>(a);
+    ref64_decode_kernel<<<(a.n_cb + 3) / 4, 32, sizeof(Smem), st>>>(a);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t launch_ref64_siso(const Ref64SisoArgs &a, cudaStream_t st, int *n_launches)
 {
-    const int warps = (a.n_cb + 3) / 4;
-    const int wpb = 2;
-    const int blocks = (warps + wpb - 1) / wpb;
-    ref64_siso_kernel<<<blocks, wpb * 32, 0, st>>>(a);
+    ref64_siso_kernel<<<(a.n_cb + 3) / 4, 32, sizeof(Smem), st>>>(a);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
