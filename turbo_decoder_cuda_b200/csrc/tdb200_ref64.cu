@@ -43,50 +43,54 @@ constexpr double kInfty = 1E20;  // ITTC/log_map.h:72-74
 constexpr int kW = kRef64Window;           // steps per window
 constexpr int kRow = 9;                    // doubles per alpha/beta row: 8 states + 1 (lane stride 18 banks: conflict-free position reads)
 constexpr int kCbStride = kW * kRow + 8;   // doubles per codeblock region; 592 words = 16 (mod 32): the two codeblocks of a half-warp do not collide
+constexpr int kGtStride = kW * 4 + 8;      // branch-metric table of one codeblock, same staggering
 constexpr int kLutEntries = 58;            // |d| < 2^-4, 7 binades x 8 sub-intervals, |d| >= 8
 
 struct Smem {  // one warp per CTA
-    double in[2][3][4][kW];      // staged xs, xp, La of two windows (cp.async double buffer)
+    double raw[2][3][4][kW];     // staged xs, xp, La of two windows (cp.async double buffer)
+    double gt[4][kGtStride];     // branch metrics of the window: [step]{(-s-q)-h, (-s+q)-h, (s-q)+h, (s+q)+h}, h = La/2 (gama_Log, :962-972)
     double aw[4][kCbStride];     // alpha_i of the window, row = step, [state]
     double bw[4][kCbStride];     // beta_{i+1} of the window
     double mw[4][kW];            // normaliser max(0, max_j alpha_j) of step i+1 (tempmax[], :987-993)
     double ex[2][4][8];          // alpha exchange, double-buffered by step parity
-    double lut[kLutEntries][4];  // {breakpoint, value below it, value from it on, -}
+    double lut[kLutEntries + 2][2];  // {breakpoint inside the interval, value below it}; the value from it on is the next entry's
 };
 
 // The correction table of E_algorithm, hashed by the leading bits of d (see the header).  Entry e:
 // 0 covers d < 2^-4, 1..56 the intervals 2^(b-4) * [1 + s/8, 1 + (s+1)/8), 57 covers d >= 8.
-__device__ void build_lut(double (*lut)[4], int lane)
+// No breakpoint is a multiple of 2^(b-7), so "value from the breakpoint on" = "value at the start
+// of the next interval" and one 16-byte entry per interval is enough.
+__device__ void build_lut(double (*lut)[2], int lane)
 {
     const double idx[16] = {0.0, 0.08824, 0.19587, 0.31026, 0.43275, 0.56508, 0.70963, 0.86972,
                             1.0502, 1.2587, 1.5078, 1.8212, 2.2522, 2.9706, 3.6764, 4.3758};  // :14-16
     const double val[16] = {0.69315, 0.65, 0.6, 0.55, 0.5, 0.45, 0.4, 0.35,
                             0.3, 0.25, 0.2, 0.15, 0.1, 0.05, 0.025, 0.0};  // :17-18; from 4.3758 on the result is 0 (:784-787)
-    for (int e = lane; e < kLutEntries; e += 32) {
-        double bp = 1e300, below, above;
-        if (e == 0) below = above = val[0];
-        else if (e == kLutEntries - 1) below = above = 0.0;
+    for (int e = lane; e < kLutEntries + 2; e += 32) {
+        double bp = 1e300, below;
+        if (e == 0) below = val[0];
+        else if (e >= kLutEntries - 1) below = 0.0;
         else {
             const int b = (e - 1) >> 3, s = (e - 1) & 7;
             const double base = 1.0 / (double)(1 << 4) * (double)(1 << b);
             const double lo = base * (1.0 + 0.125 * s), hi = lo + base * 0.125;
             int k = 0;
             for (int t = 1; t < 16; t++) if (idx[t] <= lo) k = t;  // region of lo: [idx[k], idx[k+1])
-            below = above = val[k];
-            if (k < 15 && idx[k + 1] < hi) { bp = idx[k + 1]; above = val[k + 1]; }
+            below = val[k];
+            if (k < 15 && idx[k + 1] < hi) bp = idx[k + 1];
         }
-        lut[e][0] = bp; lut[e][1] = below; lut[e][2] = above; lut[e][3] = 0.0;
+        lut[e][0] = bp; lut[e][1] = below;
     }
 }
 
 // max*(x,y), ITTC/log_map.cpp:779-801
-__device__ __forceinline__ double max_star(double x, double y, const double (*lut)[4])
+__device__ __forceinline__ double max_star(double x, double y, const double (*lut)[2])
 {
     const double diff = y - x;  // d = (y-x) > 0 ? (y-x) : (x-y) = |diff|
     int e = ((__double2hiint(diff) & 0x7fffffff) >> 17) - ((1023 - 4) * 8 - 1);
     e = min(max(e, 0), kLutEntries - 1);
     const double2 t = *reinterpret_cast<const double2 *>(&lut[e][0]);
-    const double above = lut[e][2];
+    const double above = lut[e + 1][1];
     return (x > y ? x : y) + (fabs(diff) < t.x ? t.y : above);
 }
 
@@ -119,7 +123,7 @@ struct PassIn {
     int T, terminated;
 };
 
-// Window w of the three input arrays -> sm.in[buf] (lane (g,j): steps j, j+8, j+16, j+24 of codeblock g).
+// Window w of the three input arrays -> sm.raw[buf] (lane (g,j): steps j, j+8, j+16, j+24 of codeblock g).
 __device__ __forceinline__ void stage_window(Smem &sm, const PassIn &p, int w, int buf, int g, int j)
 {
     if (w >= 0) {
@@ -130,23 +134,35 @@ __device__ __forceinline__ void stage_window(Smem &sm, const PassIn &p, int w, i
 #pragma unroll
             for (int r = 0; r < kW / 8; r++) {
                 const int u = j + 8 * r;
-                if (i0 + u < p.T) cp_async8(&sm.in[buf][k][g][u], src[k] + i0 + u);
+                if (i0 + u < p.T) cp_async8(&sm.raw[buf][k][g][u], src[k] + i0 + u);
             }
     }
     cp_async_commit();
 }
 
-// Steps [0, wlen) of window `buf`, forward.  On entry al = alpha_i(j) of the window's first step and
+// The four branch metrics of every step of the staged window (each lane converts what it staged itself).
+__device__ __forceinline__ void gamma_window(Smem &sm, int buf, int g, int j)
+{
+#pragma unroll
+    for (int r = 0; r < kW / 8; r++) {
+        const int u = j + 8 * r;
+        const double s = sm.raw[buf][0][g][u], q = sm.raw[buf][1][g][u], h = sm.raw[buf][2][g][u] * 0.5;
+        double2 *o = reinterpret_cast<double2 *>(&sm.gt[g][u * 4]);
+        o[0] = make_double2((-s - q) - h, (-s + q) - h);  // input 0, parity -1 / +1, :967-968
+        o[1] = make_double2((s - q) + h, (s + q) + h);    // input 1, :969-970
+    }
+}
+
+// Steps [0, wlen) of the window, forward.  On entry al = alpha_i(j) of the window's first step and
 // (a0, a1) = alpha_i of the two predecessors of state j; on exit the same for the step after the
 // window.  STORE: keep alpha_i (rows of sm.aw) and the normalisers (sm.mw) for the beta / LLR phase.
+// c0 / c1: this lane's columns of a step's branch-metric row (gamma from ls0 with input 0, from ls1 with input 1).
 template <bool STORE>
-__device__ __forceinline__ void alpha_window(Smem &sm, int buf, int g, int j, int wlen, double &al, double &a0, double &a1,
-                                             int ls0, int ls1, double sa0, double sa1)
+__device__ __forceinline__ void alpha_window(Smem &sm, int g, int j, int wlen, double &al, double &a0, double &a1,
+                                             int ls0, int ls1, int c0, int c1)
 {
-    const double *is = sm.in[buf][0][g], *ip = sm.in[buf][1][g], *il = sm.in[buf][2][g];
-    double s = is[0], q = ip[0], h = il[0] * 0.5;
-    double g0 = (-s + q * sa0) - h;  // gamma(from ls0, input 0), :967-968
-    double g1 = (s + q * sa1) + h;   // gamma(from ls1, input 1), :969-970
+    const double *gt = sm.gt[g];
+    double g0 = gt[c0], g1 = gt[c1];
     if (STORE) sm.aw[g][j] = al;
 #pragma unroll 2
     for (int u = 0; u < wlen; u++) {
@@ -155,9 +171,8 @@ __device__ __forceinline__ void alpha_window(Smem &sm, int buf, int g, int j, in
         ex[j] = v;
         // the next step's branch metrics, in the shadow of the exchange
         const int un = min(u + 1, kW - 1);
-        s = is[un]; q = ip[un]; h = il[un] * 0.5;
-        g0 = (-s + q * sa0) - h;
-        g1 = (s + q * sa1) + h;
+        g0 = gt[un * 4 + c0];
+        g1 = gt[un * 4 + c1];
         __syncwarp();
         const double2 *e2 = reinterpret_cast<const double2 *>(ex);
         const double2 v01 = e2[0], v23 = e2[1], v45 = e2[2], v67 = e2[3];
@@ -176,52 +191,51 @@ __device__ __forceinline__ void alpha_window(Smem &sm, int buf, int g, int j, in
     }
 }
 
-// Steps [0, wlen) of window `buf`, backward.  be = beta_{i+1}(j) of the window's last step on entry,
+// Steps [0, wlen) of the window, backward.  be = beta_{i+1}(j) of the window's last step on entry,
 // beta_i(j) of its first step on exit.  Rows of sm.bw receive beta_{i+1}.
-__device__ __forceinline__ void beta_window(Smem &sm, int buf, int g, int j, int wlen, double &be, int ns0, int ns1, double sb0, double sb1)
+__device__ __forceinline__ void beta_window(Smem &sm, int g, int j, int wlen, double &be, int ns0, int ns1, int c0, int c1)
 {
-    const double *is = sm.in[buf][0][g], *ip = sm.in[buf][1][g], *il = sm.in[buf][2][g];
+    const double *gt = sm.gt[g], *mw = sm.mw[g];
     sm.bw[g][(wlen - 1) * kRow + j] = be;
+    double g0 = gt[(wlen - 1) * 4 + c0], g1 = gt[(wlen - 1) * 4 + c1], m = mw[wlen - 1];
 #pragma unroll 2
     for (int u = wlen - 1; u >= 0; u--) {
-        const double s = is[u], q = ip[u], h = il[u] * 0.5, m = sm.mw[g][u];
-        const double g0 = (-s + q * sb0) - h;
-        const double g1 = (s + q * sb1) + h;
         const double tx = g0 + shfl8(be, ns0);
         const double ty = g1 + shfl8(be, ns1);
-        be = max_star(tx, ty, sm.lut) - m;  // :1004-1021
+        const double mm = m;
+        const int un = max(u - 1, 0);  // the next step's operands, ahead of this step's chain
+        g0 = gt[un * 4 + c0];
+        g1 = gt[un * 4 + c1];
+        m = mw[un];
+        be = max_star(tx, ty, sm.lut) - mm;  // :1004-1021
         if (u >= 1) sm.bw[g][(u - 1) * kRow + j] = be;
     }
 }
 
-// LLR of the window, :1024-1039: lane = trellis position, one codeblock after the other.
+// LLR of the window, :1024-1039: lane = trellis position.  E_algorithm_seq (:817-829) is a serial fold over the
+// eight states -- two chains of seven max* per position -- so the four codeblocks of the warp are folded side by
+// side (eight independent chains per lane) to fill the latency of one max*.
 template <class Emit>
 __device__ __forceinline__ void fold_window(Smem &sm, int buf, int lane, int wlen, int i0, Emit &emit)
 {
     if (lane >= wlen) return;
-#pragma unroll 2
-    for (int c = 0; c < 4; c++) {
-        const double s = sm.in[buf][0][c][lane], q = sm.in[buf][1][c][lane], l = sm.in[buf][2][c][lane];
-        const double h = l * 0.5;
-        const double g0m = (-s - q) - h, g0p = (-s + q) - h;  // input 0, parity -1 / +1
-        const double g1m = (s - q) + h, g1p = (s + q) + h;    // input 1
-        double a[8], b[8];
+    const int tgt = emit.target(i0 + lane);
+    double m0[4], m1[4];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            a[k] = sm.aw[c][lane * kRow + k];
-            b[k] = sm.bw[c][lane * kRow + k];
-        }
-        double m0 = 0, m1 = 0;
+    for (int jj = 0; jj < 8; jj++) {
+        const int l0 = tb(kLs0, jj), l1 = tb(kLs1, jj);
 #pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-            const int l0 = tb(kLs0, jj), l1 = tb(kLs1, jj);
-            const double t0 = ((o0(l0) > 0 ? g0p : g0m) + a[l0]) + b[jj];  // :1028-1030
-            const double t1 = ((o1(l1) > 0 ? g1p : g1m) + a[l1]) + b[jj];  // :1032-1034
-            if (jj == 0) { m0 = t0; m1 = t1; }
-            else { m0 = max_star(m0, t0, sm.lut); m1 = max_star(m1, t1, sm.lut); }  // E_algorithm_seq, :817-829
+        for (int c = 0; c < 4; c++) {
+            const double *gt = &sm.gt[c][lane * 4], *a = &sm.aw[c][lane * kRow], *b = &sm.bw[c][lane * kRow];
+            const double t0 = (gt[o0(l0) > 0 ? 1 : 0] + a[l0]) + b[jj];  // :1028-1030
+            const double t1 = (gt[o1(l1) > 0 ? 3 : 2] + a[l1]) + b[jj];  // :1032-1034
+            if (jj == 0) { m0[c] = t0; m1[c] = t1; }
+            else { m0[c] = max_star(m0[c], t0, sm.lut); m1[c] = max_star(m1[c], t1, sm.lut); }
         }
-        emit(c, i0 + lane, m1 - m0, l, s);  // :1038
     }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        emit(c, i0 + lane, tgt, m1[c] - m0[c], sm.raw[buf][2][c][lane], sm.raw[buf][0][c][lane]);  // :1038
 }
 
 // One BCJR pass (Log_MAP_decoder, :898-1047) for the four codeblocks of this warp.
@@ -231,8 +245,10 @@ __device__ void siso_pass(Smem &sm, const PassIn &p, int lane, Emit &emit)
     const int g = lane >> 3, j = lane & 7;
     const int T = p.T, n_win = (T + kW - 1) / kW;
     const int ls0 = tb(kLs0, j), ls1 = tb(kLs1, j), ns0 = tb(kNs0, j), ns1 = tb(kNs1, j);
-    const double sa0 = o0(ls0), sa1 = o1(ls1);  // parity signs of the branches ENTERING state j
-    const double sb0 = o0(j), sb1 = o1(j);      // parity signs of the branches LEAVING state j
+    // this lane's columns of a branch-metric row: parity signs of the branches ENTERING state j ...
+    const int oa0 = o0(ls0) > 0 ? 1 : 0, oa1 = o1(ls1) > 0 ? 3 : 2;
+    // ... and of the branches LEAVING it
+    const int ob0 = o0(j) > 0 ? 1 : 0, ob1 = o1(j) > 0 ? 3 : 2;
     double *ck = p.ck + g * p.sCk + j;
 
     // ---- alpha forward, :975-1001: only the window-start vectors are kept
@@ -244,8 +260,9 @@ __device__ void siso_pass(Smem &sm, const PassIn &p, int lane, Emit &emit)
         if (w == n_win - 1) break;  // the last window is re-created below anyway
         stage_window(sm, p, w + 1, (w + 1) & 1, g, j);
         cp_async_wait<1>();
+        gamma_window(sm, w & 1, g, j);
         __syncwarp();
-        alpha_window<false>(sm, w & 1, g, j, kW, al, a0, a1, ls0, ls1, sa0, sa1);
+        alpha_window<false>(sm, g, j, kW, al, a0, a1, ls0, ls1, oa0, oa1);
         __syncwarp();
     }
     // window n_win-1 is in flight (or, with a single window, staged by the first call)
@@ -256,6 +273,7 @@ __device__ void siso_pass(Smem &sm, const PassIn &p, int lane, Emit &emit)
         const int buf = w & 1, wlen = min(kW, T - w * kW);
         stage_window(sm, p, w - 1, (w - 1) & 1, g, j);
         cp_async_wait<1>();
+        gamma_window(sm, buf, g, j);
         __syncwarp();
         if (w < n_win - 1) {  // otherwise (al, a0, a1) are what the forward sweep left
             al = ck_next;
@@ -263,9 +281,9 @@ __device__ void siso_pass(Smem &sm, const PassIn &p, int lane, Emit &emit)
             a1 = shfl8(al, ls1);
         }
         if (w >= 1) ck_next = ck[(size_t)(w - 1) * 8];
-        alpha_window<true>(sm, buf, g, j, wlen, al, a0, a1, ls0, ls1, sa0, sa1);
+        alpha_window<true>(sm, g, j, wlen, al, a0, a1, ls0, ls1, oa0, oa1);
         __syncwarp();
-        beta_window(sm, buf, g, j, wlen, be, ns0, ns1, sb0, sb1);
+        beta_window(sm, g, j, wlen, be, ns0, ns1, ob0, ob1);
         __syncwarp();
         fold_window(sm, buf, lane, wlen, w * kW, emit);
         __syncwarp();
@@ -275,22 +293,25 @@ __device__ void siso_pass(Smem &sm, const PassIn &p, int lane, Emit &emit)
 
 struct DecodeEmit {
     const Ref64Args &a;
-    double *Le;  // workspace of the warp's four codeblocks
+    double *La_next;  // a-priori array of the next pass (the warp's four codeblocks)
+    const int *scat;  // where this pass's position i sits in the next pass's order
     size_t sT;
     int cb0, T, K, it, siso;
     bool last;
-    __device__ __forceinline__ void operator()(int c, int i, double L, double la, double xs) const
+    __device__ __forceinline__ int target(int i) const { return i < K ? scat[i] : -1; }
+    __device__ __forceinline__ void operator()(int c, int i, int tgt, double L, double la, double xs) const
     {
-        // extrinsic, :1234-1238 / :1255-1259; decision + deinterleave, :1261-1264
+        // extrinsic, :1234-1238 / :1255-1259, stored where the next pass reads it as a-priori value:
+        // SISO-1 -> SISO-2 La[i'] = Le[pi(i')] (randominterleaver_double, :1242), i.e. i' = pi^-1(i);
+        // SISO-2 -> SISO-1 La[pi(i)] = Le[i] (random_deinterlvr_double, :1221); tails stay 0 (:1224-1227)
         const double le = L - la - 2 * xs;
-        Le[c * sT + i] = le;
+        if (tgt >= 0) La_next[c * sT + tgt] = le;
         const int cb = cb0 + c;
         if (cb >= a.n_cb) return;
-        if (siso == 1 && i < K) {
+        if (siso == 1 && tgt >= 0) {  // decision + deinterleave, :1261-1264 (tgt = pi(i))
             const int bit = (L < 0) ? 0 : 1;
-            const int pos = a.pi[i];
-            if (a.bits_iters) a.bits_iters[((size_t)cb * a.n_iter + it) * K + pos] = bit;
-            if (last && a.bits) a.bits[(size_t)cb * K + pos] = (uint8_t)bit;
+            if (a.bits_iters) a.bits_iters[((size_t)cb * a.n_iter + it) * K + tgt] = bit;
+            if (last && a.bits) a.bits[(size_t)cb * K + tgt] = (uint8_t)bit;
         }
         if (last) {
             if (siso == 0 && a.llr1) a.llr1[(size_t)cb * T + i] = L;
@@ -311,7 +332,7 @@ __global__ void __launch_bounds__(32) ref64_decode_kernel(Ref64Args a)
     const size_t sT = T;
     const Ref64Workspace &w = a.ws;
     double *xs1 = w.xs1 + cb0 * sT, *xp1 = w.xp1 + cb0 * sT, *xs2 = w.xs2 + cb0 * sT, *xp2 = w.xp2 + cb0 * sT;
-    double *La = w.La + cb0 * sT, *Le = w.Le + cb0 * sT;
+    double *La = w.La + cb0 * sT, *Ln = w.Le + cb0 * sT;  // a-priori values of this pass / of the next
     build_lut(sm.lut, lane);
 
     // ---- x0.5 and demultiplex, :1202-1209, :1083-1127
@@ -334,31 +355,26 @@ __global__ void __launch_bounds__(32) ref64_decode_kernel(Ref64Args a)
                 p2 = load_llr_half(a.llr, a.llr_type, base + 3 * K + 2 * kTail + 2 * m + 1);
             }
             xs1[c * sT + i] = s1; xp1[c * sT + i] = p1; xs2[c * sT + i] = s2; xp2[c * sT + i] = p2;
-            Le[c * sT + i] = 0.0;  // :1212-1215
+            La[c * sT + i] = 0.0;  // :1212-1215
+            Ln[c * sT + i] = 0.0;  // the tail entries of both stay 0
         }
     }
     __syncwarp();
 
     PassIn p;
-    p.La = La; p.sT = sT; p.T = T; p.terminated = 1;
+    p.sT = sT; p.T = T; p.terminated = 1;
     p.sCk = (size_t)8 * w.n_win;
     p.ck = w.ck + cb0 * p.sCk;
 
     for (int it = 0; it < a.n_iter; it++) {
         for (int siso = 0; siso < 2; siso++) {
-            // a-priori for this pass: SISO-1 La[pi(i)] = Le[i] (random_deinterlvr_double, :1221),
-            // SISO-2 La[i] = Le[pi(i)] (randominterleaver_double, :1242); tail forced to 0.
-            const int *idx = siso == 0 ? a.pi_inv : a.pi;
-            for (int c = 0; c < 4; c++) {
-#pragma unroll 4
-                for (int i = lane; i < T; i += 32) La[c * sT + i] = (i < K) ? Le[c * sT + idx[i]] : 0.0;
-            }
-            __syncwarp();
             p.xs = siso == 0 ? xs1 : xs2;
             p.xp = siso == 0 ? xp1 : xp2;
-            DecodeEmit emit{a, Le, sT, cb0, T, K, it, siso, it == a.n_iter - 1};
+            p.La = La;
+            DecodeEmit emit{a, Ln, siso == 0 ? a.pi_inv : a.pi, sT, cb0, T, K, it, siso, it == a.n_iter - 1};
             siso_pass(sm, p, lane, emit);
             __syncwarp();
+            double *t = La; La = Ln; Ln = t;
         }
     }
 }
@@ -366,7 +382,8 @@ __global__ void __launch_bounds__(32) ref64_decode_kernel(Ref64Args a)
 struct SisoEmit {
     const Ref64SisoArgs &a;
     int cb0;
-    __device__ __forceinline__ void operator()(int c, int i, double L, double, double) const
+    __device__ __forceinline__ int target(int) const { return 0; }
+    __device__ __forceinline__ void operator()(int c, int i, int, double L, double, double) const
     {
         if (cb0 + c < a.n_cb) a.LLR[(size_t)(cb0 + c) * a.T + i] = L;
     }
