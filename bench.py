@@ -293,6 +293,33 @@ def run_ours(args):
                    "correction": "max* = max + max(0, 0.625 - |d|/4), all 30 max* per trellis step"}
         dec_lm.close()
 
+    # ---- the fp64 reference-order decoder (TDB200_ALGO_LOGMAP_F64): the mode that meets the 1e-3 LLR bar (bit-identical
+    #      to the reference's TurboDecoding), same batch, device-resident fp64 LLRs, 8 iterations
+    f64_info = None
+    if args.algo == "maxlog_s16" and not args.no_f64:
+        dec64 = TurboDecoder(K, n_iter=N_ITER, algo="logmap_f64", device=local, max_batch=batch)
+        f64_bits = torch.empty((batch, K), dtype=torch.uint8, device=dev)
+        llr64 = llr.double()
+
+        def step_f64():
+            dec64.decode_raw(llr64.data_ptr(), tdb.LLR_F64, tdb.MEM_DEVICE, batch, bits=f64_bits.data_ptr(), stream=sp)
+        step_f64()
+        torch.cuda.synchronize()
+        n64 = 2
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(n64):
+            step_f64()
+        g1.record(stream)
+        torch.cuda.synchronize()
+        f64_ms = g0.elapsed_time(g1) / n64
+        f64_info = {"ms_per_step": f64_ms, "steps": n64, "gbit_s_this_rank": batch * K / (f64_ms * 1e-3) / 1e9,
+                    "ber_this_rank": float((f64_bits != bits).sum().item()) / (batch * K), "algo": "logmap_f64",
+                    "what": "unsegmented fp64 Log-MAP in the reference's operation order (LLRs bit-identical to the CPU reference); "
+                            "bound by the latency of one trellis step and by shared-memory bandwidth (DESIGN.md 2.2)"}
+        dec64.close()
+        del llr64
+
     # ---- measured issue rate of the add-compare-select mix (the denominator of roofline.alu)
     rate_mix = dec.issue_rate(2)
     rate_alu = dec.issue_rate(0)
@@ -439,6 +466,8 @@ def run_ours(args):
                                        "unit": "Tlane-op/s (packed 16-bit), per GPU", "frac": lm_ach / alu_peak,
                                        "frac_of_measured": lm_ach / alu_peak_meas, "ops_per_info_bit": lm_ops}
             line["logmap_s16"] = lm_info
+        if f64_info:
+            line["logmap_f64"] = f64_info
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()
             decode, kind = cpu_reference_decoder()
@@ -486,6 +515,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-early-term", action="store_true", help="skip the informational early-termination leg")
     ap.add_argument("--no-logmap", action="store_true", help="skip the Log-MAP (logmap_s16) leg")
+    ap.add_argument("--no-f64", action="store_true", help="skip the fp64 reference-order (logmap_f64) leg")
     ap.add_argument("--sub-block", type=int, default=0, help="trellis steps per sub-block (0 = the library's plan)")
     ap.add_argument("--guard", type=int, default=0, help="warm-up steps across sub-block boundaries (with --sub-block)")
     args = ap.parse_args()

@@ -285,3 +285,46 @@ def test_header_is_plain_c99(lib, tmp_path):
                         "-L", libdir, "-ltdb200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_hashed_max_star_table_equals_the_linear_scan(oracle):
+    """csrc/tdb200_ref64.cu looks the max* correction up through a table hashed by the exponent and the top three
+    mantissa bits of |x-y| (entry = the one breakpoint inside that interval and the value below it; the value from it on
+    is the next entry's).  Restated here in numpy and compared with the oracle's scan of the reference's 16-entry table
+    (E_algorithm, ITTC/log_map.cpp:779-801) on the breakpoints, their neighbours in the last place, the interval
+    boundaries and a dense sweep -- the two must agree for every double."""
+    idx = np.array([0.0, 0.08824, 0.19587, 0.31026, 0.43275, 0.56508, 0.70963, 0.86972,
+                    1.0502, 1.2587, 1.5078, 1.8212, 2.2522, 2.9706, 3.6764, 4.3758])
+    val = np.array([0.69315, 0.65, 0.6, 0.55, 0.5, 0.45, 0.4, 0.35, 0.3, 0.25, 0.2, 0.15, 0.1, 0.05, 0.025, 0.0])
+    n_ent = 58
+    bp = np.full(n_ent + 2, 1e300)
+    below = np.zeros(n_ent + 2)
+    below[0] = val[0]
+    for e in range(1, n_ent - 1):
+        b, s = (e - 1) >> 3, (e - 1) & 7
+        base = 2.0 ** (b - 4)
+        lo = base * (1.0 + 0.125 * s)
+        hi = lo + base * 0.125
+        k = int(np.searchsorted(idx, lo, side="right")) - 1
+        below[e] = val[k]
+        inside = [t for t in range(1, 16) if lo <= idx[t] < hi]
+        assert len(inside) <= 1, "two breakpoints in one interval"      # what the hash relies on
+        assert all(idx[t] != lo for t in inside), "breakpoint on an interval boundary"
+        if inside:
+            bp[e] = idx[inside[0]]
+
+    def hashed(d):
+        hi_word = (np.abs(d).view(np.uint64) >> np.uint64(32)).astype(np.int64)
+        e = np.clip((hi_word >> 17) - ((1023 - 4) * 8 - 1), 0, n_ent - 1)
+        return np.where(np.abs(d) < bp[e], below[e], below[e + 1])
+
+    pts = [np.linspace(0.0, 9.0, 200001), idx, np.nextafter(idx, 10.0), np.nextafter(idx, -10.0)]
+    edges = np.array([2.0 ** (b - 4) * (1 + s / 8.0) for b in range(8) for s in range(8)])
+    pts += [edges, np.nextafter(edges, 10.0), np.nextafter(edges, -10.0), np.array([1e-300, 0.06249999, 8.0, 1e3, 2e20])]
+    d = np.abs(np.concatenate(pts))
+    want = np.array([oracle.max_star(0.0, float(x)) - max(0.0, float(x)) for x in d])   # max*(0, d) = d + corr(d)
+    got = hashed(d)
+    # max*(0,d) - d carries the rounding of the sum for large d; compare where the scan is exact, and the sum otherwise
+    assert np.array_equal(d + got, np.array([oracle.max_star(0.0, float(x)) for x in d]))
+    small = d < 1.0
+    assert np.allclose(got[small], want[small], rtol=0, atol=1e-15)

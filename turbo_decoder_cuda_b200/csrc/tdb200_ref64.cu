@@ -26,7 +26,8 @@
 //   * max* looks its correction up in a 58-entry HASHED table: the exponent and top three mantissa
 //     bits of |x-y| select an interval that holds at most one of the reference's 16 breakpoints,
 //     one exact comparison against that breakpoint picks the value -- the same result as the
-//     reference's linear scan for every double, in 10 instructions instead of a 15-compare tree;
+//     reference's linear scan for every double (tests/test_host_logic.py restates and checks it), in 10 instructions
+//     instead of a 15-compare tree;
 //   * the (xs,xp,La) inputs of the next window arrive by cp.async while the current one runs.
 // Compile with -fmad=false: products here are exact (x * +-1, x * 0.5) so contraction would not
 // change results, but the flag keeps that a non-question.
@@ -51,16 +52,17 @@ struct Smem {  // one warp per CTA
     double gt[4][kGtStride];     // branch metrics of the window: [step]{(-s-q)-h, (-s+q)-h, (s-q)+h, (s+q)+h}, h = La/2 (gama_Log, :962-972)
     double aw[4][kCbStride];     // alpha_i of the window, row = step, [state]
     double bw[4][kCbStride];     // beta_{i+1} of the window
-    double mw[4][kW];            // normaliser max(0, max_j alpha_j) of step i+1 (tempmax[], :987-993)
+    double mw[4][kW + 2];        // normaliser max(0, max_j alpha_j) of step i+1 (tempmax[], :987-993); +2: the four codeblocks' words in different banks
     double ex[2][4][8];          // alpha exchange, double-buffered by step parity
-    double lut[kLutEntries + 2][2];  // {breakpoint inside the interval, value below it}; the value from it on is the next entry's
+    double lut[2][kLutEntries + 2];  // [0]: the breakpoint inside an interval, [1]: the value below it; the value from it on is the next entry's
 };
 
 // The correction table of E_algorithm, hashed by the leading bits of d (see the header).  Entry e:
 // 0 covers d < 2^-4, 1..56 the intervals 2^(b-4) * [1 + s/8, 1 + (s+1)/8), 57 covers d >= 8.
 // No breakpoint is a multiple of 2^(b-7), so "value from the breakpoint on" = "value at the start
-// of the next interval" and one 16-byte entry per interval is enough.
-__device__ void build_lut(double (*lut)[2], int lane)
+// of the next interval": a breakpoint and one value per interval are enough.  They sit in two planes of 8-byte words
+// (a 16-byte {breakpoint, value} load measured 4 % slower: the comparison waits for the whole quad).
+__device__ void build_lut(double (*lut)[kLutEntries + 2], int lane)
 {
     const double idx[16] = {0.0, 0.08824, 0.19587, 0.31026, 0.43275, 0.56508, 0.70963, 0.86972,
                             1.0502, 1.2587, 1.5078, 1.8212, 2.2522, 2.9706, 3.6764, 4.3758};  // :14-16
@@ -79,19 +81,18 @@ __device__ void build_lut(double (*lut)[2], int lane)
             below = val[k];
             if (k < 15 && idx[k + 1] < hi) bp = idx[k + 1];
         }
-        lut[e][0] = bp; lut[e][1] = below;
+        lut[0][e] = bp; lut[1][e] = below;
     }
 }
 
 // max*(x,y), ITTC/log_map.cpp:779-801
-__device__ __forceinline__ double max_star(double x, double y, const double (*lut)[2])
+__device__ __forceinline__ double max_star(double x, double y, const double (*lut)[kLutEntries + 2])
 {
     const double diff = y - x;  // d = (y-x) > 0 ? (y-x) : (x-y) = |diff|
     int e = ((__double2hiint(diff) & 0x7fffffff) >> 17) - ((1023 - 4) * 8 - 1);
     e = min(max(e, 0), kLutEntries - 1);
-    const double2 t = *reinterpret_cast<const double2 *>(&lut[e][0]);
-    const double above = lut[e + 1][1];
-    return (x > y ? x : y) + (fabs(diff) < t.x ? t.y : above);
+    const double bp = lut[0][e], below = lut[1][e], above = lut[1][e + 1];  // three 8-byte loads: the breakpoint is back first
+    return (x > y ? x : y) + (fabs(diff) < bp ? below : above);
 }
 
 __device__ __forceinline__ double shfl8(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 8); }
