@@ -51,6 +51,25 @@ def test_decode_matches_oracle(oracle, K, ebn0, n_cb, n_iter):
     assert dec.plan()["kernel_launches_last_call"] >= 1
 
 
+def test_llrs_are_bit_identical_to_the_oracle(oracle):
+    """Stronger than the 1e-3 bar of north_star and the 1e-6 of the test above: the kernel performs the reference's
+    floating-point operations on the same operands in the same order (re-created alpha windows and the hashed max*
+    table included), so every a-posteriori and extrinsic LLR of the waterfall case equals the CPU restatement bit for bit
+    (tools/llr_parity_report.py does the same against the compiled reference: profiles/r02_llr_parity_report.txt)."""
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    K, n_iter = 6144, 8
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, 5, 0.4, seed=77)   # ragged: one warp of four codeblocks and one of one
+    dec = TurboDecoder(K, n_iter=n_iter, algo="logmap_f64", max_batch=8)
+    out = dec.decode(torch.from_numpy(llr).cuda(), want=("bits_iters", "llr_siso1", "llr_siso2", "ext_siso2"))
+    for c in range(5):
+        ob, o1, o2, ole = oracle.decode(llr[c], pi, n_iter, want_llr=True)
+        assert np.array_equal(out["bits_iters"][c].cpu().numpy(), ob)
+        for name, ref in (("llr_siso1", o1), ("llr_siso2", o2), ("ext_siso2", ole)):
+            assert np.array_equal(out[name][c].cpu().numpy(), ref), name
+
+
 def test_llr_input_types(oracle):
     """float32 input is widened exactly; the decode of float32-rounded LLRs matches the oracle on them."""
     _torch_cuda()
