@@ -1,6 +1,6 @@
 """Throughput of the auto plan for every LTE block size (BASELINE configs[3]: all 188 K), 8 fixed iterations and with
 the decisions + magnitude stopping rule at 1.5 dB; batch 16384 (65536 for K <= 512).
-    python tools/sweep_all_sizes.py --json gpurun_out/all_sizes.json"""
+    python tools/sweep_all_sizes.py --json gpurun_out/all_sizes.json [--algo logmap_s16]"""
 import argparse
 import json
 import os
@@ -32,13 +32,15 @@ def timed(fn, reps=4):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default="gpurun_out/all_sizes.json")
+    ap.add_argument("--algo", default="maxlog_s16", help="maxlog_s16 | logmap_s16")
     a = ap.parse_args()
     rows = []
     for K in lte_sizes():
         N = 16384 if K > 512 else 65536
         bits, llr = synth.make_batch(K, 2048, 1.5, seed=K, device="cuda")
         llr = llr.repeat(N // 2048, 1).contiguous()
-        dec, det = TurboDecoder(K, n_iter=8, max_batch=N), TurboDecoder(K, n_iter=8, max_batch=N, early_term=True)
+        dec = TurboDecoder(K, n_iter=8, max_batch=N, algo=a.algo)
+        det = TurboDecoder(K, n_iter=8, max_batch=N, early_term=True, algo=a.algo)
         plan = dec.plan()
         ms, ms_et = timed(lambda: dec.decode(llr)), timed(lambda: det.decode(llr))
         out = det.decode(llr, want=("bits", "iters_used"))

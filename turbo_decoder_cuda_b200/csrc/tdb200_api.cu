@@ -13,6 +13,7 @@
 
 #include "tdb200_internal.h"
 #include "tdb200_plan_table.h"
+#include "tdb200_plan_table_lm.h"
 
 namespace tdb200 {
 
@@ -341,11 +342,13 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         // ---- sub-block geometry: K = P * L, L = 8 * NW, P <= 256 threads
         FastGeom &g = d->geom;
         int L = c.sub_block;
-        if (s16 && !lm16 && L == 0 && c.warmup == 0) {
+        if (s16 && L == 0 && c.warmup == 0) {
             // measured on a B200 for every LTE block size (tools/tune_subblock.py): which admissible L is fastest
-            // depends on how the sub-block count fills warps and how many CTAs fit an SM, not on L alone
+            // depends on how the sub-block count fills warps and how many CTAs fit an SM, not on L alone -- and it is
+            // not the same L for the Log-MAP kernels (245 registers, one more guard window): they have their own table
+            const unsigned char *tuned = lm16 ? kTunedL8Lm : kTunedL8;
             for (int i = 0; i < 188; i++)
-                if (kLte[i][0] == K && kTunedL8[i]) { L = 8 * kTunedL8[i]; break; }
+                if (kLte[i][0] == K && tuned[i]) { L = 8 * tuned[i]; break; }
             if (L && (K % L || K / L > 256)) L = 0;
         }
         if (L == 0 && K <= 56) L = K;  // shortest blocks: one thread walks the whole trellis (shared memory admits >= 256 threads per SM only for L <= 56)
