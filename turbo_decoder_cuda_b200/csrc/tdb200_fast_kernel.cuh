@@ -1272,9 +1272,21 @@ kernel_fn pick_lm_nw(int NW)
     return NW == 6 ? fast_s16_kernel<LLR_T, 128, 6, G, false, true> : (NW == 5 ? fast_s16_kernel<LLR_T, 128, 5, G, false, true> : fast_s16_kernel<LLR_T, 128, 4, G, false, true>);
 }
 template <int LLR_T>
+kernel_fn pick_lm_rt(int NW)
+{
+    switch (NW) {
+        case 4: return fast_s16_kernel<LLR_T, -1, 4, 24, false, true>;
+        case 5: return fast_s16_kernel<LLR_T, -1, 5, 24, false, true>;
+        case 6: return fast_s16_kernel<LLR_T, -1, 6, 24, false, true>;
+        case 7: return fast_s16_kernel<LLR_T, -1, 7, 24, false, true>;
+        default: return fast_s16_kernel<LLR_T, -1, 8, 24, false, true>;
+    }
+}
+template <int LLR_T>
 kernel_fn pick_kernel_lm_t(const FastGeom &g)
 {
     if (fast_spec_lm(g)) return g.G == 32 ? pick_lm_nw<LLR_T, 32>(g.NW) : (g.G == 24 ? pick_lm_nw<LLR_T, 24>(g.NW) : pick_lm_nw<LLR_T, 16>(g.NW));
+    if (fast_spec_lm_rt(g)) return pick_lm_rt<LLR_T>(g.NW);
     return fast_s16_kernel<LLR_T, 0, 0, 0, false, true>;
 }
 

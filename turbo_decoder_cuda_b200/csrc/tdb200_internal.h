@@ -159,6 +159,9 @@ inline bool fast_spec_rt192(const FastGeom &g) { return !fast_spec192(g) && g.P 
 // Log-MAP kernels with compile-time geometry: 128 sub-blocks of 32 / 40 / 48 steps, guard 16, 24 or 32
 inline bool fast_spec_lm(const FastGeom &g) { return g.P == 128 && g.NW >= 4 && g.NW <= 6 && (g.G == 16 || g.G == 24 || g.G == 32) && g.PP == 129; }
 
+// ... and with the sub-block count at run time: 2..128 sub-blocks of 32..64 steps, guard 24 (the auto plan's)
+inline bool fast_spec_lm_rt(const FastGeom &g) { return !fast_spec_lm(g) && g.P >= 2 && g.P <= 128 && g.NW >= 4 && g.NW <= 8 && g.G == 24 && g.PP == (g.P | 1); }
+
 cudaError_t fast_s16_configure(FastGeom &g, int sm_count, bool logmap);  // opt in to the dynamic shared memory size
 cudaError_t launch_fast_s16(const FastArgs &a, cudaStream_t st, int *n_launches);
 int fast_s16_smem_bytes(const FastGeom &g);
