@@ -208,9 +208,9 @@ int main(int argc, char **argv)
         ms_max = std::max(ms_max, r.ms);
         be += r.bit_err; fe += r.frame_err; it += r.iters; n += r.n;
     }
-    std::printf("{\"tool\": \"tdb200_burst (C++ over the C ABI, one host thread per GPU)\", \"n_gpus\": %d, \"K\": %d, "
+    std::printf("{\"tool\": \"tdb200_burst (C++ over the C ABI, one host thread per GPU)\", \"algo\": \"%s\", \"n_gpus\": %d, \"K\": %d, "
                 "\"modulation\": %d, \"E\": %d, \"rv\": %d, \"codeblocks\": %lld, \"ebn0_db\": %.2f, \"early_term\": %d, \"decode_ms_max_over_gpus\": %.3f, "
                 "\"gbit_s\": %.3f, \"bit_errors\": %lld, \"frame_errors\": %lld, \"mean_iters\": %.3f}\n",
-                gpus, K, ch.modulation, ch.E > 0 ? ch.E : 3 * K + 12, ch.rv, n, ebn0, early_term, ms_max, (double)n * K / (ms_max * 1e-3) / 1e9, be, fe, n ? (double)it / n : 0.0);
+                g_algo == TDB200_ALGO_LOGMAP_S16 ? "logmap_s16" : "maxlog_s16", gpus, K, ch.modulation, ch.E > 0 ? ch.E : 3 * K + 12, ch.rv, n, ebn0, early_term, ms_max, (double)n * K / (ms_max * 1e-3) / 1e9, be, fe, n ? (double)it / n : 0.0);
     return 0;
 }
