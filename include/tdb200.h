@@ -96,7 +96,8 @@ typedef struct tdb200_config {
                        sub-block boundary; 0 = next-iteration initialisation only */
     int early_term; /* 1 = stop a codeblock when an iteration leaves every hard decision unchanged AND
                        every a-posteriori magnitude is at least et_threshold (min 2 iterations);
-                       2 / 3 (TDB200_ALGO_MAXLOG_S16 only) = stop when the K hard decisions divide by the
+                       2 / 3 (the packed 16-bit decoders, TDB200_ALGO_MAXLOG_S16 and TDB200_ALGO_LOGMAP_S16)
+                       = stop when the K hard decisions divide by the
                        CRC24B / CRC24A generator (TS 36.212 5.1.1: a code block of a segmented transport
                        block ends in a CRC24B, an unsegmented one in the transport block's CRC24A) --
                        the stop rule the reference leaves as a placeholder (previous/Decoder.cc:1026,

@@ -115,6 +115,45 @@ def test_transport_block_round_trip(oracle, A):
         assert torch.equal(out2[0], payload[0]) and torch.equal(out2[2], payload[2])
 
 
+@pytest.mark.parametrize("K,which,ebn0", [(6144, "crc24b", 1.0), (5824, "crc24b", 1.2), (1056, "crc24a", 1.8), (104, "crc24a", 3.5)])
+def test_crc_stopping_rule_logmap_s16_bit_exact(oracle, K, which, ebn0):
+    """The CRC stopping rule in the Log-MAP kernels (a run-time mode of their one pass): decisions and iteration counts
+    equal the integer model's (logmap = 1, early_term = 2) block by block, for compile-time geometry (6144), the
+    run-time-P instantiations (5824, 1056) and the fully run-time kernel (104)."""
+    torch = _torch_cuda()
+    from oracle_lib import FxParams
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    from turbo_decoder_cuda_b200.decoder import CRC24A, CRC24B
+    n_cb, n_iter = 5, 8
+    dec = TurboDecoder(K, n_iter=n_iter, early_term=which, max_batch=8, algo="logmap_s16")
+    hda = TurboDecoder(K, n_iter=n_iter, early_term=True, max_batch=8, algo="logmap_s16")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(K + 1)
+    bits = torch.randint(0, 2, (n_cb, K), dtype=torch.uint8, device="cuda", generator=g)
+    no_crc = bits[2].clone()
+    dec.crc24_attach(bits, CRC24B if which == "crc24b" else CRC24A)
+    bits[2] = no_crc                                  # this one does not divide by the generator
+    llr = dec.channel(dec.encode(bits), oracle.sigma(ebn0, K), seed=9)
+    out = dec.decode(llr, want=("bits", "iters_used"))
+    got_bits, got_it = out["bits"].cpu().numpy(), out["iters_used"].cpu().numpy()
+    plan = dec.plan()
+    poly = oracle.CRC24B if which == "crc24b" else oracle.CRC24A
+    prm = FxParams(K=K, n_iter=n_iter, sub_len=plan["sub_block"], warmup=plan["warmup"], frac_bits=4, llr_clip=127,
+                   ext_clip=511, ext_scale_q2=4, early_term=2, et_threshold=128, crc_poly=poly, logmap=1, lm_upper_off=1)
+    pi = oracle.qpp(K)
+    h_llr = llr.cpu().numpy()
+    for c in range(n_cb):
+        want_bits, _, it, ovf = oracle.fx_decode(h_llr[c], pi, prm, want_le=True)
+        assert ovf == 0
+        assert np.array_equal(got_bits[c], want_bits.astype(np.uint8)), "cb %d" % c
+        assert int(got_it[c]) == it, "cb %d: %d vs %d iterations" % (c, got_it[c], it)
+    assert got_it[2] == n_iter
+    assert np.array_equal(got_bits, bits.cpu().numpy()), "operating point decodes cleanly"
+    it_hda = hda.decode(llr, want=("iters_used",))["iters_used"].cpu().numpy()
+    keep = np.arange(n_cb) != 2
+    assert got_it[keep].mean() <= it_hda[keep].mean(), "the CRC rule never needs more iterations than decisions + magnitude"
+
+
 @pytest.mark.parametrize("K,which,ebn0", [(6144, "crc24b", 1.0), (5824, "crc24b", 1.2), (1056, "crc24a", 1.8), (512, "crc24a", 2.2), (104, "crc24a", 3.5)])
 def test_crc_stopping_rule_bit_exact(oracle, K, which, ebn0):
     """early_term = CRC: decisions and the iteration count equal the integer model's, block by block; a block

@@ -326,7 +326,7 @@ static int create_impl(const tdb200_config *cfg, tdb200_decoder *d)
         const bool s16 = (c.algo == TDB200_ALGO_MAXLOG_S16) || lm16;
         if (c.max_batch <= 0) c.max_batch = 16384;
         if (c.early_term < 0 || c.early_term > 3) return fail(TDB200_ERR_INVALID_ARG, "early_term=%d (0..3)", c.early_term);
-        if (c.early_term >= 2 && (!s16 || lm16)) return fail(TDB200_ERR_UNSUPPORTED, "the CRC stopping rule exists in TDB200_ALGO_MAXLOG_S16 only");
+        if (c.early_term >= 2 && !s16) return fail(TDB200_ERR_UNSUPPORTED, "the CRC stopping rule exists in the packed 16-bit decoders only (TDB200_ALGO_MAXLOG_S16, TDB200_ALGO_LOGMAP_S16)");
         if (c.early_term >= 2 && K <= 24) return fail(TDB200_ERR_INVALID_ARG, "K=%d leaves no room for a 24-bit CRC", K);
         if (c.frac_bits == 0) c.frac_bits = lm16 ? 4 : 3;
         if (lm16 && c.frac_bits < 3) return fail(TDB200_ERR_INVALID_ARG, "frac_bits=%d: TDB200_ALGO_LOGMAP_S16 needs 3 or 4 (the correction is 5 << (frac_bits - 3) at most)", c.frac_bits);

@@ -1071,11 +1071,14 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
             const bool il = (hp & 1) != 0;
             const int it = hp >> 1;
             const bool last = (it == A.n_iter - 1);
-            const bool want = il && (A.early_term == 1 || last || A.bits_iters != nullptr);
+            // the CRC stopping rule is a run-time mode of the Log-MAP kernels (the pass has run-time flags anyway): from the
+            // second iteration on SISO-1 keeps its natural-order decisions and the pair stops when both codeblocks divide
+            const bool crc_pass = (A.early_term == 2) && !il && it >= 1;
+            const bool want = (il && (A.early_term == 1 || last || A.bits_iters != nullptr)) || crc_pass;
             w32 weak = 0;
             const w32 chg = siso_pass<-1, -1, KP, KNW, KG, true>(c, g, sm, il ? sm.par2 : sm.par1, na[0], nb[0], t, active, first_fixed, last_fixed,
                                                                  (want_soft && last && il) ? sm.par1 : nullptr, weak,
-                                                                 (usedA ? 0u : 0xffffu) | (usedB ? 0u : 0xffff0000u), il, want);
+                                                                 (A.early_term == 2) ? 0xffffffffu : ((usedA ? 0u : 0xffffu) | (usedB ? 0u : 0xffff0000u)), il, want);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const w32 ta = na[0][j], tb2 = nb[0][j];
@@ -1083,6 +1086,12 @@ __global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 1
                 na[1][j] = ta; nb[1][j] = tb2;
             }
             if (il && A.bits_iters && active) emit_iter_bits(A, sm, NW, P, PP, L, K, t, false, cbA, hasB, it, it + 1);
+            if (crc_pass) {
+                const uint2 rem = crc_of_decisions(A, sm, flags, P, NW, t, active);
+                if (!rem.x && !usedA) usedA = it + 1;
+                if (!rem.y && !usedB) usedB = it + 1;
+                if (usedA && usedB) { used = it + 1; natural = true; break; }
+            }
             if (il && A.early_term == 1) {
                 int chA, chB;
                 if (one_pair) {
