@@ -65,12 +65,13 @@ def test_crc24_on_transport_block_rows(oracle):
         assert dec.crc24_check(t, CRC24A).cpu().numpy().all()
 
 
-@pytest.mark.parametrize("A", [1000, 6120, 6121, 20000, 75376])
-def test_transport_block_round_trip(oracle, A):
+@pytest.mark.parametrize("A,algo", [(1000, "maxlog_s16"), (6120, "maxlog_s16"), (6121, "maxlog_s16"), (20000, "maxlog_s16"),
+                                    (75376, "maxlog_s16"), (6121, "logmap_s16"), (75376, "logmap_s16")])
+def test_transport_block_round_trip(oracle, A, algo):
     torch = _torch_cuda()
     from turbo_decoder_cuda_b200.transport import TransportBlockCodec
     n_tb = 3
-    tb = TransportBlockCodec(A, n_iter=8, early_term=True)
+    tb = TransportBlockCodec(A, n_iter=8, early_term=True, algo=algo)
     seg = oracle.segmentation(A + 24)
     assert tb.seg == seg
     g = torch.Generator(device="cuda")

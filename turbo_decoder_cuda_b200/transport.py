@@ -17,7 +17,7 @@ from .decoder import CRC24A, CRC24B, TurboDecoder, segmentation
 
 class TransportBlockCodec:
     def __init__(self, A, device=0, n_iter=8, algo="maxlog_s16", early_term=True, max_batch=0):
-        """early_term: True = the CRC stopping rule (s16 decoder), "hda" = decisions + magnitude, False = none."""
+        """early_term: True = the CRC stopping rule (the packed 16-bit decoders), "hda" = decisions + magnitude, False = none."""
         self.A = int(A)
         self.B = self.A + 24                                    # with the transport-block CRC24A
         s = self.seg = segmentation(self.B)
@@ -25,7 +25,7 @@ class TransportBlockCodec:
         # blocks r = 0 .. C_minus-1 have K_minus bits, the rest K_plus (5.1.2)
         self.groups = ([(s["K_minus"], s["C_minus"])] if s["C_minus"] else []) + [(s["K_plus"], s["C_plus"])]
         kw = dict(n_iter=n_iter, algo=algo, device=device, max_batch=max_batch)
-        if algo == "maxlog_s16" and early_term is True:
+        if algo in ("maxlog_s16", "logmap_s16") and early_term is True:
             # every code block ends in a CRC: its own CRC24B, or the transport block's CRC24A when there is one block
             # (leading filler zeros do not change a CRC): stop each block as soon as its decisions divide
             kw["early_term"] = "crc24b" if s["C"] > 1 else "crc24a"
