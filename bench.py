@@ -218,6 +218,7 @@ def run_ours(args):
 
     # ---- the same batch with early termination (informational; the headline is 8 fixed iterations)
     et_info = None
+    crc_llr = crc_bits = None
     if args.algo == "maxlog_s16" and not args.no_early_term:
         dec_et = TurboDecoder(K, n_iter=N_ITER, algo=args.algo, device=local, max_batch=batch, sub_block=args.sub_block,
                               warmup=args.guard, early_term=True)
@@ -265,7 +266,6 @@ def run_ours(args):
                                       "ber_this_rank": float((et_bits != crc_bits).sum().item()) / (batch * K),
                                       "rule": "hard decisions of SISO-1 divide by the CRC24B generator (the last iteration counted is half-run)"}
             dec_crc.close()
-            del crc_llr
 
     # ---- the Log-MAP decoder in the same packed arithmetic (TDB200_ALGO_LOGMAP_S16): the mode that sits on the
     #      reference's BER/FER curve (BASELINE configs[2]), same batch, device-resident, 8 fixed iterations
@@ -292,6 +292,28 @@ def run_ours(args):
                    "algo": "logmap_s16", "sub_block": pl["sub_block"], "guard": pl["warmup"], "frac_bits": 4,
                    "correction": "max* = max + max(0, 0.625 - |d|/4), all 30 max* per trellis step"}
         dec_lm.close()
+        if crc_llr is not None:
+            # the CRC stopping rule in the Log-MAP kernels, on the CRC-carrying frames of the leg above
+            dec_lc = TurboDecoder(K, n_iter=N_ITER, algo="logmap_s16", device=local, max_batch=batch, early_term="crc24b")
+            lc_iters = torch.empty((batch,), dtype=torch.int32, device=dev)
+
+            def step_lc():
+                dec_lc.decode_raw(crc_llr.data_ptr(), tdb.LLR_F32, tdb.MEM_DEVICE, batch, bits=lm_bits.data_ptr(),
+                                  iters_used=lc_iters.data_ptr(), stream=sp)
+            for _ in range(3):
+                step_lc()
+            torch.cuda.synchronize()
+            g0.record(stream)
+            for _ in range(n_lm):
+                step_lc()
+            g1.record(stream)
+            torch.cuda.synchronize()
+            lc_ms = g0.elapsed_time(g1) / n_lm
+            lm_info["crc24b_rule"] = {"gbit_s_this_rank": batch * K / (lc_ms * 1e-3) / 1e9,
+                                      "mean_iterations_this_rank": float(lc_iters.float().mean().item()),
+                                      "ber_this_rank": float((lm_bits != crc_bits).sum().item()) / (batch * K)}
+            dec_lc.close()
+    crc_llr = None
 
     # ---- the fp64 reference-order decoder (TDB200_ALGO_LOGMAP_F64): the mode that meets the 1e-3 LLR bar (bit-identical
     #      to the reference's TurboDecoding), same batch, device-resident fp64 LLRs, 8 iterations
