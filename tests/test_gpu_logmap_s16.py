@@ -182,3 +182,48 @@ def test_per_iteration_decisions(oracle, algo, K, early):
     # host path delivers the same slab
     out_h = dec.decode(llr32, want=("bits_iters",))
     assert np.array_equal(out_h["bits_iters"], rows)
+
+
+def test_every_lte_block_size_logmap(oracle):
+    """BASELINE configs[3], correctness side, for the Log-MAP kernels: all 188 LTE block sizes decode bit-exactly against the
+    integer model with the library's own plan for that K (own plan table, csrc/tdb200_plan_table_lm.h; compile-time,
+    run-time-P and fully run-time instantiations)."""
+    _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    sizes = oracle.lte_sizes()
+    n_iter = 2
+    kinds = set()
+    for K in sizes:
+        pi = oracle.qpp(K)
+        _, llr = oracle.make_batch(K, 3, 1.5, seed=K + 7)      # odd batch: one CTA runs half empty
+        llr32 = llr.astype(np.float32)
+        dec = TurboDecoder(K, n_iter=n_iter, algo="logmap_s16", max_batch=4)
+        plan = dec.plan()
+        assert plan["sub_block"] * plan["n_sub_blocks"] == K
+        kinds.add((plan["sub_block"], plan["warmup"]))
+        out = dec.decode(llr32, want=("bits",))
+        prm = lm_params(K, n_iter, plan["sub_block"], plan["warmup"])
+        b, _, _, ovf = oracle.fx_decode(llr32[2], pi, prm)
+        assert ovf == 0 and np.array_equal(out["bits"][2], b.astype(np.uint8)), "K=%d" % K
+        dec.close()
+    assert len(kinds) >= 8   # the plans really differ
+
+
+@pytest.mark.parametrize("K,early,n_cb", [(1312, False, 1801), (656, True, 1801), (512, False, 2401)])
+def test_packed_pairs_large_batch_logmap(oracle, K, early, n_cb):
+    """Several codeblock pairs per CTA in the Log-MAP kernels (a large batch is what makes the planner pack them): bit-exact,
+    with and without early termination, on a sample of the batch."""
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TurboDecoder
+    pi = oracle.qpp(K)
+    _, llr = oracle.make_batch(K, 32, 1.5, seed=K)
+    llr32 = np.tile(llr.astype(np.float32), ((n_cb + 31) // 32, 1))[:n_cb]
+    dec = TurboDecoder(K, n_iter=4, algo="logmap_s16", early_term=early, max_batch=n_cb)
+    plan = dec.plan()
+    out = dec.decode(torch.from_numpy(llr32).cuda(), want=("bits", "iters_used"))
+    got, its = out["bits"].cpu().numpy(), out["iters_used"].cpu().numpy()
+    prm = lm_params(K, 4, plan["sub_block"], plan["warmup"], early_term=1 if early else 0, et_threshold=128 if early else 0)
+    for c in (0, 1, 31, 32, n_cb - 1):
+        b, _, it, ovf = oracle.fx_decode(llr32[c], pi, prm)
+        assert ovf == 0 and np.array_equal(got[c], b.astype(np.uint8)), "cb %d" % c
+        assert int(its[c]) == it
