@@ -235,11 +235,15 @@ int tdb200_decode_symbols_batch(tdb200_decoder *dec, const void *sym_i, const vo
  * from k0(rv) with <NULL> pruning (5.1.4.1).  The turbo-code side keeps the reference's multiplex
  * order [n_cb][3K+12]; the channel side is [n_cb][E].  rv = redundancy version 0..3; ncb = soft
  * buffer size N_cb (0: the full circular buffer K_w = 3 * 32 * ceil((K+4)/32)).
- * Deviation from the standard, by design: FILLER BITS ARE ORDINARY ZEROS here.  5.1.3.2.1 / 5.1.4.1.2 turn the F
- * filler positions of d0 and d1 of a transport block's first code block into <NULL>s that are never transmitted;
- * these entry points prune only the interleaver's dummy <NULL>s, so for a transport block with F > 0 the bit
- * selection of that one block differs from a standard-conformant transmitter (the chain here is self-consistent:
- * transmitter and receiver of this library agree).  Pinned by a hand-derived K = 40 known answer (tests/test_oracle.py). */
+ * FILLER BITS (5.1.2: the first F bits of a transport block's first code block): 5.1.3.2.1 turns d0_k and d1_k,
+ * k < F, into <NULL>s that are never transmitted.  tdb200_set_filler_bits(dec, F) declares them for every code block
+ * that goes through this handle afterwards (use one handle for the first blocks, F > 0, and one for the rest): the
+ * bit selection then skips those 2F positions like the interleaver's dummy bits, and the soft inverse writes a fixed
+ * confident "0" (-100; -127 in the 8-bit format) at the F systematic and F parity-1 positions -- the receiver knows
+ * them (the encoder starts in state 0 and stays there while it reads zeros).  F = 0 (the default): no filler bits.
+ * Pinned by a hand-derived K = 40 known answer (tests/test_oracle.py). */
+int tdb200_set_filler_bits(tdb200_decoder *dec, int F);
+
 int tdb200_rate_match_batch(tdb200_decoder *dec, const uint8_t *coded, uint8_t *e_bits, int mem, int n_cb,
                             int E, int rv, int ncb, void *stream);
 

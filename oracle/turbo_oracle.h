@@ -151,6 +151,12 @@ int tdo_rm_selection(int K, int E, int rv, int Ncb, int *sel /*E*/);
 int tdo_rate_match(const int *coded, int K, int E, int rv, int Ncb, int *e_bits);
 int tdo_rate_dematch(const double *e_llr, int K, int E, int rv, int Ncb, int accumulate, double *llr);
 int tdo_rate_dematch_f32(const float *e_llr, int K, int E, int rv, int Ncb, int accumulate, float *llr);
+/* the same with F filler bits at the head of the code block (<NULL> in d0 and d1, 36.212 5.1.3.2.1): never transmitted;
+ * the soft inverse sets them (and their parity-1 positions) to `fill` */
+void tdo_rm_circular_buffer_f(int K, int F, int *w);
+int tdo_rm_selection_f(int K, int E, int rv, int Ncb, int F, int *sel);
+int tdo_rate_match_f(const int *coded, int K, int E, int rv, int Ncb, int F, int *e_bits);
+int tdo_rate_dematch_f(const double *e_llr, int K, int E, int rv, int Ncb, int F, int accumulate, double fill, double *llr);
 
 /* ------------------------------------------------------------------------
  * LTE CRC24A / CRC24B and code-block segmentation (turbo_oracle_crc.c; TS 36.212 5.1.1, 5.1.2). */

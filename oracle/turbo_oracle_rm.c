@@ -51,14 +51,16 @@ int tdo_rm_geometry(int K, int *R, int *Kpi, int *ND)
     return 3 * 32 * r; /* K_w */
 }
 
-/* The circular buffer as a list of multiplex positions, -1 for <NULL>.  w[K_w]. */
-void tdo_rm_circular_buffer(int K, int *w)
+/* The circular buffer as a list of multiplex positions, -1 for <NULL>.  w[K_w].
+ * F filler bits (5.1.2: the first F bits of a transport block's first code block): c_k = <NULL> for k < F, and
+ * 5.1.3.2.1 sets d0_k = d1_k = <NULL> for those k (the encoder reads them as 0; d2 is transmitted). */
+void tdo_rm_circular_buffer_f(int K, int F, int *w)
 {
     int R, Kpi, ND;
     tdo_rm_geometry(K, &R, &Kpi, &ND);
     int *y = (int *)malloc(sizeof(int) * Kpi), *v = (int *)malloc(sizeof(int) * Kpi);
     for (int s = 0; s < 3; s++) {
-        for (int k = 0; k < Kpi; k++) y[k] = (k < ND) ? -1 : mux_pos(K, s, k - ND);
+        for (int k = 0; k < Kpi; k++) y[k] = (k < ND || (s < 2 && k - ND < F)) ? -1 : mux_pos(K, s, k - ND);
         if (s < 2) {
             /* rows of 32, columns permuted, read out column by column */
             for (int c = 0; c < 32; c++)
@@ -75,6 +77,8 @@ void tdo_rm_circular_buffer(int K, int *w)
     free(v);
 }
 
+void tdo_rm_circular_buffer(int K, int *w) { tdo_rm_circular_buffer_f(K, 0, w); }
+
 int tdo_rm_k0(int K, int rv, int Ncb)
 {
     int R;
@@ -84,13 +88,13 @@ int tdo_rm_k0(int K, int rv, int Ncb)
 }
 
 /* bit selection and pruning: sel[E] = multiplex position transmitted at e */
-int tdo_rm_selection(int K, int E, int rv, int Ncb, int *sel)
+int tdo_rm_selection_f(int K, int E, int rv, int Ncb, int F, int *sel)
 {
     int R;
     const int Kw = tdo_rm_geometry(K, &R, NULL, NULL);
     if (Ncb <= 0 || Ncb > Kw) Ncb = Kw;
     int *w = (int *)malloc(sizeof(int) * Kw);
-    tdo_rm_circular_buffer(K, w);
+    tdo_rm_circular_buffer_f(K, F, w);
     int any = 0;
     for (int k = 0; k < Ncb; k++) any |= (w[k] >= 0);
     if (!any) { free(w); return -1; }
@@ -104,11 +108,31 @@ int tdo_rm_selection(int K, int E, int rv, int Ncb, int *sel)
     return 0;
 }
 
-int tdo_rate_match(const int *coded, int K, int E, int rv, int Ncb, int *e_bits)
+int tdo_rm_selection(int K, int E, int rv, int Ncb, int *sel) { return tdo_rm_selection_f(K, E, rv, Ncb, 0, sel); }
+
+int tdo_rate_match_f(const int *coded, int K, int E, int rv, int Ncb, int F, int *e_bits)
 {
     int *sel = (int *)malloc(sizeof(int) * (E > 0 ? E : 1));
-    if (tdo_rm_selection(K, E, rv, Ncb, sel)) { free(sel); return -1; }
+    if (tdo_rm_selection_f(K, E, rv, Ncb, F, sel)) { free(sel); return -1; }
     for (int e = 0; e < E; e++) e_bits[e] = coded[sel[e]];
+    free(sel);
+    return 0;
+}
+int tdo_rate_match(const int *coded, int K, int E, int rv, int Ncb, int *e_bits) { return tdo_rate_match_f(coded, K, E, rv, Ncb, 0, e_bits); }
+
+/* soft inverse with filler bits: the receiver knows the F filler bits and their parity-1 bits are 0 (the encoder starts in
+ * state 0 and stays there while it reads zeros), so those positions -- never transmitted -- come out as the fixed value
+ * `fill` (a confident "0": negative in this library's sign convention); with accumulate they are set, not added */
+int tdo_rate_dematch_f(const double *e_llr, int K, int E, int rv, int Ncb, int F, int accumulate, double fill, double *llr)
+{
+    int *sel = (int *)malloc(sizeof(int) * (E > 0 ? E : 1));
+    if (tdo_rm_selection_f(K, E, rv, Ncb, F, sel)) { free(sel); return -1; }
+    const int NL = 3 * K + 12;
+    double *sum = (double *)calloc(NL, sizeof(double));
+    for (int e = 0; e < E; e++) sum[sel[e]] += e_llr[e];
+    for (int n = 0; n < NL; n++) llr[n] = accumulate ? llr[n] + sum[n] : sum[n];
+    for (int k = 0; k < F; k++) llr[3 * k] = llr[3 * k + 1] = fill;
+    free(sum);
     free(sel);
     return 0;
 }

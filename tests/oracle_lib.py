@@ -84,6 +84,10 @@ class Oracle:
         L.tdo_rm_circular_buffer.argtypes = [C.c_int, _ip]
         L.tdo_rm_k0.argtypes = [C.c_int, C.c_int, C.c_int]
         L.tdo_rm_selection.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip]
+        L.tdo_rm_selection_f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip]
+        L.tdo_rm_circular_buffer_f.argtypes = [C.c_int, C.c_int, _ip]
+        L.tdo_rate_match_f.argtypes = [_ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip]
+        L.tdo_rate_dematch_f.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp]
         L.tdo_rate_match.argtypes = [_ip, C.c_int, C.c_int, C.c_int, C.c_int, _ip]
         L.tdo_rate_dematch.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
         L.tdo_rate_dematch_f32.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]
@@ -129,6 +133,31 @@ class Oracle:
         llr = np.zeros(3 * K + 12, dt) if into is None else np.array(into, dt)
         fn = self.lib.tdo_rate_dematch_f32 if f32 else self.lib.tdo_rate_dematch
         if fn(e if e.size else np.zeros(1, dt), K, e.size, rv, Ncb, 0 if into is None else 1, llr):
+            raise ValueError("rate matching: empty circular buffer")
+        return llr
+
+    # ... with F filler bits at the head of the code block (<NULL> in d0 / d1)
+    def rm_circular_buffer_f(self, K, F):
+        w = np.zeros(self.rm_geometry(K)["Kw"], np.int32)
+        self.lib.tdo_rm_circular_buffer_f(K, F, w)
+        return w
+
+    def rm_selection_f(self, K, E, rv, Ncb, F):
+        sel = np.zeros(max(E, 1), np.int32)
+        if self.lib.tdo_rm_selection_f(K, E, rv, Ncb, F, sel):
+            raise ValueError("rate matching: empty circular buffer")
+        return sel[:E]
+
+    def rate_match_f(self, coded, K, E, rv, Ncb, F):
+        out = np.zeros(max(E, 1), np.int32)
+        if self.lib.tdo_rate_match_f(np.ascontiguousarray(coded, np.int32), K, E, rv, Ncb, F, out):
+            raise ValueError("rate matching: empty circular buffer")
+        return out[:E]
+
+    def rate_dematch_f(self, e_llr, K, rv, Ncb, F, fill=-100.0, into=None):
+        e = np.ascontiguousarray(e_llr, np.float64)
+        llr = np.zeros(3 * K + 12, np.float64) if into is None else np.array(into, np.float64)
+        if self.lib.tdo_rate_dematch_f(e if e.size else np.zeros(1), K, e.size, rv, Ncb, F, 0 if into is None else 1, fill, llr):
             raise ValueError("rate matching: empty circular buffer")
         return llr
 

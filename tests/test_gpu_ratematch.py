@@ -41,6 +41,57 @@ def test_every_block_size_matches_the_specification_restatement(oracle):
         dec.close()
 
 
+def test_filler_bits_match_the_specification_restatement(oracle):
+    """tdb200_set_filler_bits: the F filler positions of d0 / d1 are <NULL> (TS 36.212 5.1.3.2.1) -- never selected, and
+    the soft inverse writes the fixed confident 0 there; device == oracle for random (K, F, rv, E, N_cb), all four soft
+    types, and a first code block with filler bits decodes through rate matching."""
+    torch = _torch_cuda()
+    from turbo_decoder_cuda_b200 import TdbError, TurboDecoder
+    rng = np.random.default_rng(11)
+    for K in (40, 104, 512, 1056, 3136, 6144):
+        NL = 3 * K + 12
+        Kw = oracle.rm_geometry(K)["Kw"]
+        dec = TurboDecoder(K, n_iter=1, max_batch=2)
+        for F in (int(rng.integers(1, min(K, 64))), int(rng.integers(1, K))):
+            rv = int(rng.integers(0, 4))
+            E = int(rng.integers(1, 3 * NL))
+            ncb = 0 if rng.random() < 0.5 else int(rng.integers(Kw // 2, Kw))
+            dec.set_filler_bits(F)
+            coded = rng.integers(0, 2, size=(2, NL), dtype=np.uint8)
+            got = dec.rate_match(torch.from_numpy(coded).cuda(), E, rv, ncb).cpu().numpy()
+            e = rng.standard_normal((2, E))
+            back = dec.rate_dematch(torch.from_numpy(e).cuda(), rv, ncb).cpu().numpy()
+            back32 = dec.rate_dematch(torch.from_numpy(e.astype(np.float32)).cuda(), rv, ncb).cpu().numpy()
+            back8 = dec.rate_dematch(torch.from_numpy(np.clip(np.rint(e * 8), -127, 127).astype(np.int8)).cuda(), rv, ncb).cpu().numpy()
+            for c in range(2):
+                assert np.array_equal(got[c], oracle.rate_match_f(coded[c], K, E, rv, ncb, F).astype(np.uint8)), (K, F, E, rv, ncb)
+                assert np.array_equal(back[c], oracle.rate_dematch_f(e[c], K, rv, ncb, F)), (K, F, E, rv, ncb)
+                fill = np.zeros(NL, bool)
+                fill[0:3 * F:3] = fill[1:3 * F:3] = True
+                assert (back32[c][fill] == -100.0).all() and (back8[c][fill] == -127).all()
+        dec.set_filler_bits(0)
+        coded = rng.integers(0, 2, size=(1, NL), dtype=np.uint8)
+        assert np.array_equal(dec.rate_match(torch.from_numpy(coded).cuda(), NL, 0, 0).cpu().numpy()[0],
+                              oracle.rate_match(coded[0], K, NL, 0, 0).astype(np.uint8))
+        with pytest.raises(TdbError):
+            dec.set_filler_bits(K)
+        dec.close()
+    # a first code block with F = 40 filler zeros, rate 1/2, through the whole chain: the fillers are never sent
+    K, F = 6144, 40
+    dec = TurboDecoder(K, n_iter=8, max_batch=4)
+    dec.set_filler_bits(F)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    bits = torch.randint(0, 2, (4, K), dtype=torch.uint8, device="cuda", generator=g)
+    bits[:, :F] = 0
+    E = 2 * K
+    tx = dec.rate_match(dec.encode(bits), E, 0, 0)
+    sigma = 0.7
+    rx = (2.0 * tx.float() - 1.0) + sigma * torch.randn(tx.shape, device="cuda", generator=g)
+    out = dec.decode_rm(rx * (2.0 / sigma ** 2), 0, 0)
+    assert torch.equal(out["bits"], bits)
+
+
 def test_dematch_types_combining_and_host_path(oracle):
     torch = _torch_cuda()
     from turbo_decoder_cuda_b200 import TurboDecoder

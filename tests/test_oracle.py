@@ -254,6 +254,40 @@ def test_rate_matching_known_answer_k40_derived_from_ts36212(oracle):
     assert list(oracle.rm_selection(K, 2, 2)) == [d1(30), d2(31)]
 
 
+def test_rate_matching_filler_bits_k40_by_hand(oracle):
+    """F filler bits (TS 36.212 5.1.2; 5.1.3.2.1: d0_k = d1_k = <NULL> for k < F, d2 is transmitted).  Continues the hand
+    derivation of the K = 40 case above with F = 8: the <NULL>s of d0[0..7] and d1[0..7] join the 20 dummy ones of each
+    stream, so in the listing of w[0..23] above d0(4), d0(0), d0(6) disappear, and so does d1(4) among the first parity
+    pairs -- d2(5) next to it stays."""
+    K, F = 40, 8
+    N = -1
+    d0 = lambda k: 3 * k if k < K else {40: 3 * K + 0, 41: 3 * K + 3, 42: 3 * K + 6, 43: 3 * K + 9}[k]     # noqa: E731
+    d1 = lambda k: 3 * k + 1                                                                                # noqa: E731
+    d2 = lambda k: 3 * k + 2                                                                                # noqa: E731
+    w = oracle.rm_circular_buffer_f(K, F)
+    assert list(w[:24]) == [N, d0(12), N, d0(28), N, d0(20), N, d0(36), N, d0(16), N, d0(32),
+                            N, d0(24), d0(8), d0(40), N, d0(14), N, d0(30), N, d0(22), N, d0(38)]
+    assert list(w[64:80]) == [N, N, d1(12), d2(13), N, N, d1(28), d2(29), N, N, d1(20), d2(21), N, d2(5), d1(36), d2(37)]
+    # rv 0 from w[4]: d0(20), [d0(4) is a filler], d0(36), d0(16), [d0(0)], d0(32), d0(24), d0(8), ...
+    assert list(oracle.rm_selection_f(K, 8, 0, 0, F)) == [d0(20), d0(36), d0(16), d0(32), d0(24), d0(8), d0(40), d0(14)]
+    for K2, F2 in ((40, 8), (512, 40), (6144, 56), (1024, 1023)):
+        g = oracle.rm_geometry(K2)
+        w0, wf = oracle.rm_circular_buffer(K2), oracle.rm_circular_buffer_f(K2, F2)
+        gone = set(w0[w0 != wf])                                   # what the filler bits removed from the buffer
+        assert gone == {3 * k for k in range(F2)} | {3 * k + 1 for k in range(F2)}
+        assert np.count_nonzero(wf < 0) == 3 * g["ND"] + 2 * F2
+        # one full wrap sends every remaining bit exactly once, and no filler position
+        n_left = 3 * K2 + 12 - 2 * F2
+        sel = oracle.rm_selection_f(K2, n_left, 0, 0, F2)
+        assert len(set(sel)) == n_left and not (set(sel) & gone)
+        # soft inverse: filler positions (systematic and parity 1) hold the fixed value, everything else as without fillers
+        e = np.random.default_rng(K2).standard_normal(n_left)
+        back = oracle.rate_dematch_f(e, K2, 0, 0, F2, fill=-100.0)
+        assert all(back[3 * k] == -100.0 and back[3 * k + 1] == -100.0 for k in range(F2))
+        assert np.array_equal(back[sel], e)
+    assert np.array_equal(oracle.rm_circular_buffer_f(40, 0), oracle.rm_circular_buffer(40))
+
+
 def test_rate_matching_round_trips(oracle):
     rng = np.random.default_rng(3)
     K = 512

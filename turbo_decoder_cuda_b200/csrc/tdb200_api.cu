@@ -165,8 +165,9 @@ struct tdb200_decoder {
     size_t siso_in_bytes = 0;
     void *dem = nullptr;  // demapped / de-rate-matched channel values, device callers of tdb200_decode_{symbols,rm}_batch
     size_t dem_bytes = 0;
+    int filler = 0;  // F: filler bits at the head of every code block of this handle (tdb200_set_filler_bits)
     struct RmTable {
-        int rv = 0, ncb = 0, nnn = 0;
+        int rv = 0, ncb = 0, filler = 0, nnn = 0;
         int *d_perm = nullptr, *d_inv = nullptr;
     };
     std::vector<RmTable> rm_tables;  // one per (rv, N_cb) used so far
@@ -584,7 +585,15 @@ static int launch_dematch_chunk(tdb200_decoder *d, const Source &src, const void
     return TDB200_OK;
 }
 
-// The (rv, N_cb) permutation of a handle, built on first use.
+int tdb200_set_filler_bits(tdb200_decoder *d, int F)
+{
+    if (!d) return fail(TDB200_ERR_INVALID_ARG, "dec is NULL");
+    if (F < 0 || F >= d->cfg.K) return fail(TDB200_ERR_INVALID_ARG, "F=%d filler bits (0 <= F < K=%d)", F, d->cfg.K);
+    d->filler = F;
+    return TDB200_OK;
+}
+
+// The (rv, N_cb, F) permutation of a handle, built on first use.
 static int rm_table(tdb200_decoder *d, int rv, int ncb, const tdb200_decoder::RmTable **out)
 {
     if (rv < 0 || rv > 3) return fail(TDB200_ERR_INVALID_ARG, "rv=%d (0..3)", rv);
@@ -592,11 +601,11 @@ static int rm_table(tdb200_decoder *d, int rv, int ncb, const tdb200_decoder::Rm
     if (ncb < 0) return fail(TDB200_ERR_INVALID_ARG, "ncb=%d", ncb);
     if (ncb == 0 || ncb > Kw) ncb = Kw;
     for (auto &t : d->rm_tables)
-        if (t.rv == rv && t.ncb == ncb) { *out = &t; return TDB200_OK; }
+        if (t.rv == rv && t.ncb == ncb && t.filler == d->filler) { *out = &t; return TDB200_OK; }
     std::vector<int> perm, inv;
-    if (!build_rm_table(d->cfg.K, rv, ncb, perm, inv)) return fail(TDB200_ERR_INVALID_ARG, "ncb=%d leaves no transmittable bit", ncb);
+    if (!build_rm_table(d->cfg.K, rv, ncb, d->filler, perm, inv)) return fail(TDB200_ERR_INVALID_ARG, "ncb=%d leaves no transmittable bit", ncb);
     tdb200_decoder::RmTable t;
-    t.rv = rv; t.ncb = ncb; t.nnn = (int)perm.size();
+    t.rv = rv; t.ncb = ncb; t.filler = d->filler; t.nnn = (int)perm.size();
     TDB_DEVICE(d->cfg.device);
     TDB_CUDA(cudaMalloc(&t.d_perm, sizeof(int) * perm.size()));
     if (cudaMalloc(&t.d_inv, sizeof(int) * inv.size()) != cudaSuccess) { cudaFree(t.d_perm); return fail(TDB200_ERR_ALLOC, "device allocation failed"); }
@@ -604,7 +613,7 @@ static int rm_table(tdb200_decoder *d, int rv, int ncb, const tdb200_decoder::Rm
     if (e == cudaSuccess) e = cudaMemcpy(t.d_inv, inv.data(), sizeof(int) * inv.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(t.d_perm); cudaFree(t.d_inv); return fail(TDB200_ERR_CUDA, "rate-matching table upload: %s", cudaGetErrorString(e)); }
     d->rm_tables.reserve(64);  // pointers into the vector are handed out: keep them stable
-    if (d->rm_tables.size() >= 64) { cudaFree(t.d_perm); cudaFree(t.d_inv); return fail(TDB200_ERR_UNSUPPORTED, "more than 64 distinct (rv, ncb) pairs on one handle"); }
+    if (d->rm_tables.size() >= 64) { cudaFree(t.d_perm); cudaFree(t.d_inv); return fail(TDB200_ERR_UNSUPPORTED, "more than 64 distinct (rv, ncb, filler) triples on one handle"); }
     d->rm_tables.push_back(t);
     *out = &d->rm_tables.back();
     return TDB200_OK;

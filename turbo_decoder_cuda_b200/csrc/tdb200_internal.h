@@ -212,7 +212,12 @@ struct RmArgs {
     int NL, E, n_cb, accumulate;
     int frac_bits, clip;
 };
-bool build_rm_table(int K, int rv, int Ncb, std::vector<int> &perm, std::vector<int> &inv);
+// inv[] marker of a filler position (36.212 5.1.3.2.1: d0 / d1 of the F filler bits are <NULL>, never transmitted, known to
+// be 0) and the soft value the inverse writes there: a confident 0 (positive = 1 in this library), small enough to survive
+// HARQ accumulation in binary16
+constexpr int kRmFiller = -2;
+constexpr int kRmFillerLlr = -100;
+bool build_rm_table(int K, int rv, int Ncb, int F, std::vector<int> &perm, std::vector<int> &inv);
 cudaError_t launch_rate_match(const uint8_t *coded, uint8_t *e_bits, const int *perm, int nnn, int NL, int E, int n_cb, cudaStream_t st);
 cudaError_t launch_rate_dematch(const RmArgs &a, cudaStream_t st);
 

@@ -31,7 +31,7 @@
 namespace tdb200 {
 
 // ---------------------------------------------------------------- host: the permutation
-bool build_rm_table(int K, int rv, int Ncb, std::vector<int> &perm, std::vector<int> &inv)
+bool build_rm_table(int K, int rv, int Ncb, int F, std::vector<int> &perm, std::vector<int> &inv)
 {
     static const int P[32] = {0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30,
                               1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31};
@@ -51,11 +51,13 @@ bool build_rm_table(int K, int rv, int Ncb, std::vector<int> &perm, std::vector<
         else { s = 1 + ((p - Kpi) & 1); k = (p - Kpi) >> 1; }
         if (s < 2) y = (k % R) * 32 + P[k / R];
         else y = (P[k / R] + 32 * (k % R) + 1) % Kpi;
-        return y < ND ? -1 : mux(s, y - ND);
+        // <NULL>: the interleaver's dummy bits, and d0 / d1 of the F filler bits (36.212 5.1.3.2.1)
+        return (y < ND || (s < 2 && y - ND < F)) ? -1 : mux(s, y - ND);
     };
     const long k0 = (long)R * (2L * ((Ncb + 8 * R - 1) / (8 * R)) * rv + 2);
     perm.clear();
     inv.assign(NL, -1);
+    for (int k = 0; k < F; k++) inv[3 * k] = inv[3 * k + 1] = kRmFiller;  // known zeros: the soft inverse writes a fixed value there
     for (int j = 0; j < Ncb; j++) {
         const int n = source((int)((k0 + j) % Ncb));
         if (n >= 0) { inv[n] = (int)perm.size(); perm.push_back(n); }
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(kRmThreads) rate_dematch_kernel(const void *__
         for (int b = 0; b < 4; b++) {
             v[b] = (js[b] >= 0 && js[b] < len) ? tile[swz(js[b])] : (A)0;
             if (accumulate) v[b] = load_as<A, OUT_T>(llr, out0 + 4 * n4 + b) + v[b];
+            if (js[b] == kRmFiller) v[b] = (A)(IN_T == TDB200_LLR_S8 ? -127 : kRmFillerLlr);  // a filler bit (or its parity-1 bit): known 0
         }
         if constexpr (OUT_T == TDB200_LLR_S8) {
             unsigned w = 0;

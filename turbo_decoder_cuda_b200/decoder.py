@@ -98,6 +98,7 @@ def load_library():
                                        C.c_int, C.c_void_p]
     L.tdb200_demap_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                     C.c_size_t, C.c_int, C.c_double, C.c_void_p]
+    L.tdb200_set_filler_bits.argtypes = [C.c_void_p, C.c_int]
     L.tdb200_rate_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.tdb200_rate_dematch_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_void_p]
@@ -323,6 +324,11 @@ class TurboDecoder:
         return outs
 
     # ---- TS 36.212 rate matching (the reference's declared-only rate_match / de_rate_match)
+    def set_filler_bits(self, F):
+        """tdb200_set_filler_bits: the first F information bits of every code block of this handle are filler bits
+        (<NULL> in d0 / d1: not transmitted; the soft inverse writes a confident 0 there)."""
+        _check(self._L.tdb200_set_filler_bits(self._h, int(F)))
+
     def rate_match(self, coded, E, rv=0, ncb=0, stream=0):
         """tdb200_rate_match_batch: coded [n_cb, 3K+12] uint8 -> transmitted bits [n_cb, E]."""
         n_cb = int(coded.shape[0])
