@@ -5,7 +5,9 @@
 //
 // One warp per codeblock.  A CRC is linear over GF(2): crc(A || B) = crc(A) * x^|B| + crc(B) mod g, and
 // leading zeros do not change it (zero initial state).  The n bits are right-aligned in 32 chunks of
-// c = ceil(n/32) bits; every lane runs the bit-serial division over its own chunk, then five
+// c = ceil(n/32) bits; every lane divides its own chunk -- eight bits per step where the chunk is 8-byte
+// aligned (one 64-bit load of eight one-bit bytes, packed into a byte by two multiplies, then the byte-wise
+// table of the generator, built in shared memory by the CTA), bit by bit at the ragged ends -- then five
 // shuffle levels fold the 32 partial remainders together, multiplying the left half by x^(c*2^level)
 // mod g (constants from the host) with a 24-step carry-less multiply.  `attach` writes the parity
 // bits behind the first K-24 bits, `check` divides all K bits and reports remainder == 0.
@@ -28,20 +30,39 @@ __device__ __forceinline__ unsigned mulmod24(unsigned a, unsigned b, unsigned po
     return r;
 }
 
+__device__ __forceinline__ unsigned step1(unsigned crc, unsigned bit, unsigned poly)
+{
+    const unsigned fb = ((crc >> 23) & 1u) ^ (bit & 1u);
+    return ((crc << 1) & 0xffffffu) ^ (fb ? poly : 0u);
+}
+// four one-bit bytes (first bit in the lowest byte) -> a nibble with the first bit on top: the four partial
+// products of the multiply land on distinct bits, so nothing carries
+__device__ __forceinline__ unsigned pack4(unsigned w) { return (((w & 0x01010101u) * 0x08040201u) >> 24) & 0xfu; }
+
 __global__ void __launch_bounds__(128) crc24_kernel(CrcArgs A)
 {
+    __shared__ unsigned tab[256];  // tab[v] = v(x) * x^24 mod g
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+        unsigned r = (unsigned)v << 16;
+        for (int b = 0; b < 8; b++) r = ((r << 1) & 0xffffffu) ^ ((r & 0x800000u) ? A.poly : 0u);
+        tab[v] = r;
+    }
+    __syncthreads();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= A.n_cb) return;
     uint8_t *row = A.bits + (size_t)warp * A.K;
     const int n = A.attach ? A.K - 24 : A.K;
     const int c = A.chunk, z = 32 * c - n;  // z leading virtual zeros
     unsigned crc = 0;
-    for (int i = 0; i < c; i++) {
-        const int idx = lane * c + i - z;
-        const unsigned bit = idx >= 0 ? (row[idx] & 1u) : 0u;
-        const unsigned fb = ((crc >> 23) & 1u) ^ bit;
-        crc = ((crc << 1) & 0xffffffu) ^ (fb ? A.poly : 0u);
+    int i = max(lane * c - z, 0);  // leading zeros leave the zero state alone
+    const int end = lane * c - z + c;
+    for (; i < end && (reinterpret_cast<size_t>(row + i) & 7); i++) crc = step1(crc, row[i], A.poly);
+    for (; i + 8 <= end; i += 8) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(row + i);
+        const unsigned byte = (pack4(w.x) << 4) | pack4(w.y);
+        crc = ((crc << 8) & 0xffffffu) ^ tab[((crc >> 16) ^ byte) & 0xffu];
     }
+    for (; i < end; i++) crc = step1(crc, row[i], A.poly);
 #pragma unroll
     for (int lv = 0; lv < 5; lv++) {
         const int s = 1 << lv;
