@@ -932,11 +932,14 @@ __device__ __forceinline__ void emit_iter_bits(const FastArgs &A, const Smem &sm
     }
 }
 
+#ifndef TDB_MINB_RT
+#define TDB_MINB_RT 2
+#endif
 #ifndef TDB_MINB_P128_NW4
 #define TDB_MINB_P128_NW4 3
 #endif
 template <int LLR_T, int KP, int KNW, int KG, bool CRC, bool LM = false>
-__global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 128 : (KP == -2 ? 192 : 256)), (KP == 128 && KNW == 4 && !LM) ? TDB_MINB_P128_NW4 : (KP ? 2 : 1)) fast_s16_kernel(FastArgs A)
+__global__ void __launch_bounds__(KP > 0 ? ((KP + 31) / 32) * 32 : (KP == -1 ? 128 : (KP == -2 ? 192 : 256)), (KP == 128 && KNW == 4 && !LM) ? TDB_MINB_P128_NW4 : ((KP == -1 && !LM) ? TDB_MINB_RT : (KP ? 2 : 1))) fast_s16_kernel(FastArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FastGeom &g = A.g;
